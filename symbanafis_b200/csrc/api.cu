@@ -1,0 +1,537 @@
+// api.cu -- implementation of the C ABI declared in include/saf_b200.h.
+//
+// Host-side mirror of the reference drivers:
+//   run_chunked_evaluator   src/evaluator/logic/bytecode/execute/drivers/batch.rs:37-78
+//   eval_batch              .../execute/engine/scalar.rs:150-230
+// The Rayon par_chunks_mut(256) of the reference becomes: one interpreter launch per chunk of points,
+// chunks pipelined over internal streams (H2D copy / kernel / D2H copy overlap) for host buffers,
+// one launch for device buffers.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/saf_b200.h"
+#include "kernel.cuh"
+#include "lower.h"
+
+using namespace saf;
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return fail(SAF_ERR_CUDA, m);
+}
+#define SAF_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);                                        \
+    } while (0)
+
+// ---- program handle ---------------------------------------------------------------------------------
+struct DeviceCopy {
+    uint64_t *code = nullptr;
+    double *consts = nullptr;
+};
+
+struct saf_program {
+    std::vector<RefProgram> refs; // kept so that handles can be fused later
+    DeviceProgram dev;
+    std::vector<uint64_t> blob;   // code words followed (when they fit too) by constant bit patterns
+    bool blob_fits = false;       // code fits the constant-bank blob
+    bool consts_in_blob = false;  // ... and so do the constants
+    std::mutex mu;
+    std::map<int, DeviceCopy> copies; // per-device global-memory copy for programs above BLOB_LARGE
+};
+
+static int build_program(std::vector<RefProgram> refs, saf_program **out) {
+    std::unique_ptr<saf_program> p(new (std::nothrow) saf_program());
+    if (!p) return fail(SAF_ERR_ALLOC, "out of host memory");
+    p->refs = std::move(refs);
+    std::vector<const RefProgram *> ptrs;
+    for (auto &r : p->refs) ptrs.push_back(&r);
+    std::string err;
+    int rc = lower(ptrs, p->dev, err);
+    if (rc != SAF_OK) return fail(rc, err);
+    if (p->dev.param_count > (uint32_t)MAX_COLS || p->dev.result_field.size() > (size_t)MAX_OUTS) {
+        return fail(SAF_ERR_UNSUPPORTED, "programs with more than 32 parameters or 32 results are not supported");
+    }
+    p->blob.assign(p->dev.code.begin(), p->dev.code.end());
+    p->blob_fits = p->blob.size() <= (size_t)BLOB_LARGE;
+    p->consts_in_blob = p->blob.size() + p->dev.consts.size() <= (size_t)BLOB_LARGE;
+    if (p->consts_in_blob) {
+        for (double c : p->dev.consts) {
+            uint64_t bits;
+            std::memcpy(&bits, &c, 8);
+            p->blob.push_back(bits);
+        }
+    }
+    *out = p.release();
+    return SAF_OK;
+}
+
+extern "C" int saf_program_create(const uint32_t *flat, size_t n_words, const double *consts, size_t n_consts,
+                                  const uint32_t *pool, size_t n_pool, uint32_t param_count,
+                                  uint32_t workspace_size, const uint32_t *result_regs, uint32_t n_results,
+                                  saf_program **out) {
+    if (!out) return fail(SAF_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!flat || n_words == 0) return fail(SAF_ERR_INVALID_ARGUMENT, "empty bytecode");
+    if ((n_consts && !consts) || (n_pool && !pool) || !result_regs || n_results == 0)
+        return fail(SAF_ERR_INVALID_ARGUMENT, "NULL program component");
+    RefProgram r;
+    r.flat.assign(flat, flat + n_words);
+    if (n_consts) r.consts.assign(consts, consts + n_consts);
+    if (n_pool) r.pool.assign(pool, pool + n_pool);
+    r.param_count = param_count;
+    r.workspace_size = workspace_size;
+    r.result_regs.assign(result_regs, result_regs + n_results);
+    std::vector<RefProgram> v;
+    v.push_back(std::move(r));
+    return build_program(std::move(v), out);
+}
+
+extern "C" int saf_program_fuse(const saf_program *const *programs, size_t n_programs, saf_program **out) {
+    if (!out) return fail(SAF_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!programs || n_programs == 0) return fail(SAF_ERR_INVALID_ARGUMENT, "no programs to fuse");
+    std::vector<RefProgram> v;
+    for (size_t i = 0; i < n_programs; ++i) {
+        if (!programs[i]) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL program in fuse list");
+        for (const auto &r : programs[i]->refs) v.push_back(r);
+    }
+    return build_program(std::move(v), out);
+}
+
+extern "C" void saf_program_destroy(saf_program *p) {
+    if (!p) return;
+    for (auto &kv : p->copies) {
+        int prev = 0;
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(kv.first) == cudaSuccess) {
+            cudaFree(kv.second.code);
+            cudaFree(kv.second.consts);
+            cudaSetDevice(prev);
+        }
+    }
+    delete p;
+}
+
+extern "C" int saf_program_get_info(const saf_program *p, saf_program_info *info) {
+    if (!p || !info) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL argument");
+    info->param_count = p->dev.param_count;
+    info->n_results = (uint32_t)p->dev.result_field.size();
+    info->n_ref_instructions = p->dev.n_ref_instructions;
+    info->n_dev_instructions = (uint32_t)p->dev.code.size() - 1;
+    info->n_slots = p->dev.n_slots;
+    info->n_consts = (uint32_t)p->dev.consts.size();
+    info->n_acc_forwards = p->dev.n_acc_forwards;
+    info->quirk_flags = p->dev.quirk_flags;
+    info->fp64_slots = p->dev.fp64_slots;
+    uint32_t used = 0;
+    for (uint16_t s : p->dev.param_slot) used += (s != NO_SLOT);
+    info->bytes_per_point = 8.0 * (double)(used + p->dev.result_field.size());
+    return SAF_OK;
+}
+
+extern "C" size_t saf_program_disassemble(const saf_program *p, char *buf, size_t cap) {
+    if (!p) return 0;
+    std::string s = disassemble(p->dev);
+    if (buf && cap) {
+        size_t n = std::min(cap - 1, s.size());
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size();
+}
+
+extern "C" int saf_program_export(const saf_program *p, uint64_t *code, size_t cap_code, size_t *n_code,
+                                  double *consts, size_t cap_consts, size_t *n_consts, uint16_t *param_slot,
+                                  uint32_t *result_field) {
+    if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
+    if (n_code) *n_code = p->dev.code.size();
+    if (n_consts) *n_consts = p->dev.consts.size();
+    if (code) std::memcpy(code, p->dev.code.data(), std::min(cap_code, p->dev.code.size()) * 8);
+    if (consts) std::memcpy(consts, p->dev.consts.data(), std::min(cap_consts, p->dev.consts.size()) * 8);
+    if (param_slot) std::copy(p->dev.param_slot.begin(), p->dev.param_slot.end(), param_slot);
+    if (result_field) std::copy(p->dev.result_field.begin(), p->dev.result_field.end(), result_field);
+    return SAF_OK;
+}
+
+// ---- launch -------------------------------------------------------------------------------------------
+static int ensure_device_copy(saf_program *p, int device, DeviceCopy *out) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    auto it = p->copies.find(device);
+    if (it != p->copies.end()) {
+        *out = it->second;
+        return SAF_OK;
+    }
+    DeviceCopy c;
+    SAF_CUDA(cudaMalloc(&c.code, p->dev.code.size() * 8));
+    SAF_CUDA(cudaMalloc(&c.consts, std::max<size_t>(1, p->dev.consts.size()) * 8));
+    SAF_CUDA(cudaMemcpy(c.code, p->dev.code.data(), p->dev.code.size() * 8, cudaMemcpyHostToDevice));
+    if (!p->dev.consts.empty())
+        SAF_CUDA(cudaMemcpy(c.consts, p->dev.consts.data(), p->dev.consts.size() * 8, cudaMemcpyHostToDevice));
+    p->copies[device] = c;
+    *out = c;
+    return SAF_OK;
+}
+
+// cols/outs are DEVICE pointers here; lens are the device-side lengths (already chunk-relative).
+static int launch_on_device(const saf_program *prog, const double *const *cols, const size_t *lens, size_t n_cols,
+                            double *const *outs, size_t n_points, uint64_t iters, unsigned flags,
+                            cudaStream_t stream) {
+    if (n_points == 0) return SAF_OK;
+    const DeviceProgram &dp = prog->dev;
+    LaunchDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.n_points = n_points;
+    d.iters = iters ? iters : 1;
+    d.n_code = (uint32_t)dp.code.size();
+    d.n_consts = (uint32_t)dp.consts.size();
+    d.n_slots = dp.n_slots;
+    d.n_params = dp.param_count;
+    d.n_results = (uint32_t)dp.result_field.size();
+    d.flags = flags;
+    bool aligned = true;
+    for (uint32_t j = 0; j < dp.param_count; ++j) {
+        d.param_slot[j] = dp.param_slot[j];
+        if (j < n_cols && cols[j] != nullptr) {
+            d.cols[j] = cols[j];
+            d.col_len[j] = lens[j];
+            if (dp.param_slot[j] != NO_SLOT && ((uintptr_t)cols[j] & 15u)) aligned = false;
+        } else {
+            d.cols[j] = nullptr; // missing parameter column -> 0.0 (scalar.rs:192-197)
+            d.col_len[j] = 0;
+        }
+    }
+    for (uint32_t k = 0; k < d.n_results; ++k) {
+        d.outs[k] = outs[k];
+        d.result_field[k] = (uint16_t)dp.result_field[k];
+        if ((uintptr_t)outs[k] & 15u) aligned = false;
+    }
+    int device = 0;
+    SAF_CUDA(cudaGetDevice(&device));
+    const uint64_t *blob = nullptr;
+    size_t n_blob = 0;
+    if (prog->blob_fits) {
+        blob = prog->blob.data();
+        n_blob = prog->blob.size();
+    }
+    if (!prog->blob_fits || !prog->consts_in_blob) {
+        DeviceCopy c;
+        int rc = ensure_device_copy(const_cast<saf_program *>(prog), device, &c);
+        if (rc != SAF_OK) return rc;
+        d.code_global = c.code;
+        d.consts_global = c.consts;
+    }
+    LaunchShape shape;
+    cudaError_t e = choose_shape(device, dp.n_slots, n_points, aligned, &shape);
+    if (e == cudaErrorInvalidConfiguration)
+        return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
+    if (e != cudaSuccess) return cuda_fail(e, "choose_shape");
+    e = launch_interpreter(d, blob, n_blob, shape, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "interpreter launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SAF_OK;
+}
+
+// run_chunked_evaluator's argument checks (batch.rs:44-50) / eval_batch's (scalar.rs:157-159)
+static int check_columns(const saf_program *prog, const double *const *cols, const size_t *lens, size_t n_cols,
+                         double *const *outs, size_t n_points, unsigned flags) {
+    if (!prog) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
+    if (n_cols && (!cols || !lens)) return fail(SAF_ERR_INVALID_ARGUMENT, "cols/col_lens is NULL");
+    if (n_points && !outs) return fail(SAF_ERR_INVALID_ARGUMENT, "outs is NULL");
+    if (!(flags & SAF_EVAL_BROADCAST)) {
+        for (size_t j = 0; j < n_cols; ++j)
+            if (lens[j] != n_points)
+                return fail(SAF_ERR_COLUMN_LENGTH_MISMATCH, "All evaluation columns must have the same length");
+    } else {
+        for (size_t j = 0; j < n_cols && j < prog->dev.param_count; ++j)
+            if (n_points && lens[j] == 0)
+                return fail(SAF_ERR_INVALID_ARGUMENT, "broadcast column is empty");
+    }
+    for (size_t j = 0; j < n_cols && j < prog->dev.param_count; ++j)
+        if (n_points && lens[j] && !cols[j]) return fail(SAF_ERR_INVALID_ARGUMENT, "column pointer is NULL");
+    for (size_t k = 0; n_points && k < prog->dev.result_field.size(); ++k)
+        if (!outs[k]) return fail(SAF_ERR_INVALID_ARGUMENT, "output pointer is NULL");
+    return SAF_OK;
+}
+
+extern "C" int saf_eval_device(const saf_program *prog, const double *const *cols, const size_t *lens, size_t n_cols,
+                               double *const *outs, size_t n_points, unsigned flags, void *stream) {
+    int rc = check_columns(prog, cols, lens, n_cols, outs, n_points, flags);
+    if (rc != SAF_OK) return rc;
+    return launch_on_device(prog, cols, lens, n_cols, outs, n_points, 1, flags, (cudaStream_t)stream);
+}
+
+extern "C" int saf_iterate_device(const saf_program *prog, double *const *state, size_t n_state, size_t n_points,
+                                  uint64_t iters, void *stream) {
+    if (!prog || (n_points && !state)) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_state != prog->dev.param_count || n_state != prog->dev.result_field.size())
+        return fail(SAF_ERR_INVALID_ARGUMENT, "iterate needs n_state == param_count == n_results");
+    if (iters == 0 || n_points == 0) return SAF_OK;
+    std::vector<size_t> lens(n_state, n_points);
+    std::vector<const double *> cols(state, state + n_state);
+    return launch_on_device(prog, cols.data(), lens.data(), n_state, state, n_points, iters, 0, (cudaStream_t)stream);
+}
+
+// ---- host-buffer path -----------------------------------------------------------------------------------
+namespace {
+
+// Small per-process cache of device scratch so that repeated host calls (the reference's callers
+// invoke eval_f64 once per simulation step) do not pay cudaMalloc each time.
+struct ScratchPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks[64];
+    void *acquire(int dev, size_t bytes, cudaError_t *err) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto &m = free_blocks[dev & 63];
+            auto it = m.lower_bound(bytes);
+            if (it != m.end() && it->first <= bytes * 2 + (1 << 20)) {
+                void *p = it->second;
+                sizes[p] = it->first;
+                m.erase(it);
+                return p;
+            }
+        }
+        void *p = nullptr;
+        *err = cudaMalloc(&p, bytes);
+        if (*err != cudaSuccess) return nullptr;
+        std::lock_guard<std::mutex> lk(mu);
+        sizes[p] = bytes;
+        return p;
+    }
+    void release(int dev, void *p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        free_blocks[dev & 63].emplace(sizes[p], p);
+    }
+    std::map<void *, size_t> sizes;
+};
+ScratchPool g_pool;
+
+struct StreamSet {
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+};
+std::mutex g_stream_mu;
+std::map<int, std::vector<StreamSet>> g_stream_cache;
+
+int acquire_streams(int dev, StreamSet *out) {
+    {
+        std::lock_guard<std::mutex> lk(g_stream_mu);
+        auto &v = g_stream_cache[dev];
+        if (!v.empty()) {
+            *out = v.back();
+            v.pop_back();
+            return SAF_OK;
+        }
+    }
+    for (auto &s : out->s) SAF_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return SAF_OK;
+}
+void release_streams(int dev, const StreamSet &s) {
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    g_stream_cache[dev].push_back(s);
+}
+
+constexpr size_t kChunkPoints = 1u << 21; // 2 Mi points: 16 MiB per column per chunk
+
+} // namespace
+
+// Evaluates points [begin, end) of host columns on the current device.
+static int eval_host_range(const saf_program *prog, const double *const *cols, const size_t *lens, size_t n_cols,
+                           double *const *outs, size_t begin, size_t end, uint64_t iters, unsigned flags) {
+    if (end <= begin) return SAF_OK;
+    int dev = 0;
+    SAF_CUDA(cudaGetDevice(&dev));
+    const DeviceProgram &dp = prog->dev;
+    const size_t n_in = std::min<size_t>(n_cols, dp.param_count);
+    const size_t n_out = dp.result_field.size();
+    const size_t total = end - begin;
+    // iterated maps keep their state on chip: one chunk per stream is enough, but chunks must be
+    // whole launches, so the same chunking applies.
+    const size_t chunk = std::min(total, kChunkPoints);
+    const int n_buf = (int)std::min<size_t>(3, (total + chunk - 1) / chunk);
+
+    StreamSet ss;
+    int rc = acquire_streams(dev, &ss);
+    if (rc != SAF_OK) return rc;
+    std::vector<void *> scratch;
+    auto cleanup = [&]() {
+        for (void *p : scratch) g_pool.release(dev, p);
+        release_streams(dev, ss);
+    };
+    std::vector<std::vector<double *>> d_in(n_buf, std::vector<double *>(n_in, nullptr));
+    std::vector<std::vector<double *>> d_out(n_buf, std::vector<double *>(n_out, nullptr));
+    for (int b = 0; b < n_buf; ++b) {
+        for (size_t j = 0; j < n_in + n_out; ++j) {
+            if (j < n_in && dp.param_slot[j] == NO_SLOT) continue; // column never read: do not copy it
+            cudaError_t e = cudaSuccess;
+            void *p = g_pool.acquire(dev, chunk * sizeof(double), &e);
+            if (!p) {
+                cleanup();
+                return cuda_fail(e, "cudaMalloc(scratch)");
+            }
+            scratch.push_back(p);
+            if (j < n_in) d_in[b][j] = (double *)p;
+            else d_out[b][j - n_in] = (double *)p;
+        }
+    }
+    int status = SAF_OK;
+    size_t k = 0;
+    for (size_t off = begin; off < end && status == SAF_OK; off += chunk, ++k) {
+        const int b = (int)(k % (size_t)n_buf);
+        cudaStream_t st = ss.s[b];
+        const size_t n = std::min(chunk, end - off);
+        std::vector<const double *> c_ptr(n_in, nullptr);
+        std::vector<size_t> c_len(n_in, 0);
+        for (size_t j = 0; j < n_in; ++j) {
+            if (dp.param_slot[j] == NO_SLOT) continue;
+            const size_t len = lens[j];
+            if (len > off) { // part (or all) of this chunk comes from the column itself
+                const size_t m = std::min(n, len - off);
+                cudaError_t e = cudaMemcpyAsync(d_in[b][j], cols[j] + off, m * sizeof(double), cudaMemcpyHostToDevice, st);
+                if (e != cudaSuccess) { status = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
+                c_len[j] = m;
+            } else { // column exhausted before this chunk: broadcast its last element (scalar.rs:203-207)
+                cudaError_t e = cudaMemcpyAsync(d_in[b][j], cols[j] + (len - 1), sizeof(double), cudaMemcpyHostToDevice, st);
+                if (e != cudaSuccess) { status = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
+                c_len[j] = 1;
+            }
+            c_ptr[j] = d_in[b][j];
+        }
+        if (status != SAF_OK) break;
+        status = launch_on_device(prog, c_ptr.data(), c_len.data(), n_in, d_out[b].data(), n, iters,
+                                  flags | SAF_EVAL_BROADCAST, st);
+        if (status != SAF_OK) break;
+        for (size_t r = 0; r < n_out; ++r) {
+            cudaError_t e = cudaMemcpyAsync(outs[r] + off, d_out[b][r], n * sizeof(double), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) { status = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
+        }
+    }
+    for (int b = 0; b < n_buf; ++b) {
+        cudaError_t e = cudaStreamSynchronize(ss.s[b]);
+        if (e != cudaSuccess && status == SAF_OK) status = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    cleanup();
+    return status;
+}
+
+extern "C" int saf_eval_host(const saf_program *prog, const double *const *cols, const size_t *lens, size_t n_cols,
+                             double *const *outs, size_t n_points, unsigned flags) {
+    int rc = check_columns(prog, cols, lens, n_cols, outs, n_points, flags);
+    if (rc != SAF_OK) return rc;
+    return eval_host_range(prog, cols, lens, n_cols, outs, 0, n_points, 1, flags);
+}
+
+extern "C" int saf_iterate_host(const saf_program *prog, double *const *state, size_t n_state, size_t n_points,
+                                uint64_t iters) {
+    if (!prog || (n_points && !state)) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_state != prog->dev.param_count || n_state != prog->dev.result_field.size())
+        return fail(SAF_ERR_INVALID_ARGUMENT, "iterate needs n_state == param_count == n_results");
+    if (iters == 0 || n_points == 0) return SAF_OK;
+    std::vector<size_t> lens(n_state, n_points);
+    std::vector<const double *> cols(state, state + n_state);
+    return eval_host_range(prog, cols.data(), lens.data(), n_state, state, 0, n_points, iters, 0);
+}
+
+extern "C" int saf_eval_host_multi(const saf_program *prog, const double *const *cols, const size_t *lens,
+                                   size_t n_cols, double *const *outs, size_t n_points, unsigned flags,
+                                   const int *devices, int n_devices) {
+    int rc = check_columns(prog, cols, lens, n_cols, outs, n_points, flags);
+    if (rc != SAF_OK) return rc;
+    if (n_devices <= 0) return fail(SAF_ERR_INVALID_ARGUMENT, "n_devices must be positive");
+    if (n_devices == 1) {
+        int prev = 0;
+        SAF_CUDA(cudaGetDevice(&prev));
+        SAF_CUDA(cudaSetDevice(devices ? devices[0] : 0));
+        rc = eval_host_range(prog, cols, lens, n_cols, outs, 0, n_points, 1, flags);
+        cudaSetDevice(prev);
+        return rc;
+    }
+    // contiguous shards [g*N/G, (g+1)*N/G), one host thread + stream set per device, no collective
+    std::vector<int> rcs(n_devices, SAF_OK);
+    std::vector<std::string> errs(n_devices);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_devices; ++g) {
+        th.emplace_back([&, g]() {
+            const size_t b = (size_t)((unsigned __int128)n_points * (unsigned)g / (unsigned)n_devices);
+            const size_t e = (size_t)((unsigned __int128)n_points * (unsigned)(g + 1) / (unsigned)n_devices);
+            cudaError_t ce = cudaSetDevice(devices ? devices[g] : g);
+            if (ce != cudaSuccess) {
+                rcs[g] = SAF_ERR_CUDA;
+                errs[g] = std::string("cudaSetDevice: ") + cudaGetErrorString(ce);
+                return;
+            }
+            rcs[g] = eval_host_range(prog, cols, lens, n_cols, outs, b, e, 1, flags);
+            if (rcs[g] != SAF_OK) errs[g] = g_last_error;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < n_devices; ++g)
+        if (rcs[g] != SAF_OK) return fail(rcs[g], errs[g]);
+    return SAF_OK;
+}
+
+// ---- misc ---------------------------------------------------------------------------------------------------
+extern "C" const char *saf_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int saf_device_count(int *count) {
+    if (!count) return fail(SAF_ERR_INVALID_ARGUMENT, "count is NULL");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return cuda_fail(e, "cudaGetDeviceCount");
+    }
+    return SAF_OK;
+}
+
+extern "C" int saf_measure_fp64_peak(double *dfma_lanes_per_second) {
+    if (!dfma_lanes_per_second) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL argument");
+    int dev = 0, sms = 0;
+    SAF_CUDA(cudaGetDevice(&dev));
+    SAF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *sink = nullptr;
+    SAF_CUDA(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    SAF_CUDA(cudaEventCreate(&e0));
+    SAF_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        SAF_CUDA(cudaEventRecord(e0, 0));
+        SAF_CUDA(launch_fp64_peak(sink, blocks, iters, 0));
+        SAF_CUDA(cudaEventRecord(e1, 0));
+        SAF_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SAF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double lanes = (double)blocks * 256.0 * (double)iters * 64.0;
+        if (rep > 0 && ms > 0.f) best = std::max(best, lanes / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *dfma_lanes_per_second = best;
+    return SAF_OK;
+}
+
+extern "C" uint64_t saf_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" const char *saf_version(void) { return "symbanafis-b200 0.1.0 (sm_100a)"; }

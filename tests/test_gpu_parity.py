@@ -1,0 +1,394 @@
+"""Parity tests proper: the sm_100a interpreter, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+* integer/IEEE-exact work (+ - * / sqrt fma, powi, the reference's Taylor erf, data movement,
+  broadcast rules) -- bit-identical;
+* transcendentals from the CUDA math library vs glibc -- <= 4 ulp per call;
+* named programs end to end -- relative error <= 1e-12 (plus a 1e-13 absolute floor for results that
+  cancel to ~0), NaN / +-Inf behaviour identical.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import OracleProgram
+from symbanafis_b200 import workloads
+from symbanafis_b200._lib import DeviceProgramHandle, SafError, device_count, kernel_launch_count
+from symbanafis_b200.isa import FNOP, Program, assemble
+from util import (FUZZ_BUILTIN1, FUZZ_BUILTIN2, assert_close, bits_equal, random_program, ulp_distance)
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-12, 1e-13
+
+
+def _handle(prog):
+    return DeviceProgramHandle.create(prog.flat, prog.consts, prog.arg_pool, prog.param_count,
+                                      prog.workspace_size, prog.result_regs)
+
+
+def gpu_eval(prog, cols, n, broadcast=False):
+    h = _handle(prog)
+    outs = [np.full(n, -777.0) for _ in prog.result_regs]
+    h.eval_host([np.ascontiguousarray(c, dtype=np.float64) for c in cols], outs, n, broadcast=broadcast)
+    return outs
+
+
+def single_op(name, *operands, n_in, n_out=1):
+    return Program(flat=assemble([(name, *operands)]), consts=[], arg_pool=[], param_count=n_in,
+                   workspace_size=n_in + n_out, result_regs=list(range(n_in, n_in + n_out)))
+
+
+def test_device_present_and_native_library_loaded():
+    assert device_count() >= 1
+
+
+# ---- exact operations ------------------------------------------------------------------------------
+EXACT_UNARY = ["Neg", "Square", "Cube", "Pow4", "Pow3_2", "InvPow3_2", "InvSqrt", "InvSquare", "InvCube", "Recip",
+               "Sqrt", "Copy"]
+
+
+@pytest.mark.parametrize("op", EXACT_UNARY)
+def test_exact_unary(op):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-10, 10, 4000), rng.uniform(0, 1e-300, 50), [0.0, -0.0, np.inf, -np.inf, np.nan,
+                                                                                  1e308, -1e308, 5e-324]])
+    prog = single_op(op, 1, 0, n_in=1)
+    ref = OracleProgram.from_program(prog).eval_batch([x], x.size)[0]
+    got = gpu_eval(prog, [x], x.size)[0]
+    assert bits_equal(got, ref)
+
+
+@pytest.mark.parametrize("op", ["Add", "Sub", "Mul", "Div", "NegMul"])
+def test_exact_binary(op):
+    rng = np.random.default_rng(2)
+    sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e308, 5e-324, 1.0])
+    a = np.concatenate([rng.normal(0, 100, 5000), np.repeat(sp, sp.size)])
+    b = np.concatenate([rng.normal(0, 100, 5000), np.tile(sp, sp.size)])
+    prog = single_op(op, 2, 0, 1, n_in=2)
+    ref = OracleProgram.from_program(prog).eval_batch([a, b], a.size)[0]
+    assert bits_equal(gpu_eval(prog, [a, b], a.size)[0], ref)
+
+
+@pytest.mark.parametrize("op", ["MulAdd", "MulSub", "NegMulAdd", "NegMulSub", "Add3", "Mul3"])
+def test_exact_ternary_fma_is_fused_and_mul_add_is_not(op):
+    rng = np.random.default_rng(3)
+    # operands chosen so that fused and unfused results differ in the last bit for most points
+    a = 1.0 + rng.uniform(0, 1, 8000) * 2.0 ** -27
+    b = 1.0 + rng.uniform(0, 1, 8000) * 2.0 ** -27
+    c = -1.0 - rng.uniform(0, 1, 8000) * 2.0 ** -28
+    prog = single_op(op, 3, 0, 1, 2, n_in=3)
+    ref = OracleProgram.from_program(prog).eval_batch([a, b, c], a.size)[0]
+    assert bits_equal(gpu_eval(prog, [a, b, c], a.size)[0], ref)
+    # Mul followed by Add must NOT be contracted into an FMA
+    two = Program(flat=assemble([("Mul", 3, 0, 1), ("Add", 4, 3, 2)]), consts=[], arg_pool=[], param_count=3,
+                  workspace_size=5, result_regs=[4])
+    ref2 = OracleProgram.from_program(two).eval_batch([a, b, c], a.size)[0]
+    assert bits_equal(gpu_eval(two, [a, b, c], a.size)[0], ref2)
+    if op == "MulAdd":
+        assert not bits_equal(ref, ref2), "test operands must distinguish fused from unfused"
+
+
+@pytest.mark.parametrize("n", [-7, -3, -2, -1, 0, 1, 2, 3, 5, 10, 31, 64, -(2 ** 31), 2 ** 31 - 1])
+def test_powi_matches_compiler_rt(n):
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.uniform(-3, 3, 2000), [0.0, -0.0, 1.0, -1.0, np.inf, np.nan]])
+    prog = single_op("Powi", 1, 0, n, n_in=1)
+    ref = OracleProgram.from_program(prog).eval_batch([x], x.size)[0]
+    assert bits_equal(gpu_eval(prog, [x], x.size)[0], ref)
+
+
+def test_reference_taylor_erf_is_bit_exact_including_its_divergence():
+    # erf.rs:9-51 uses only + - * /: the device result must be identical, also where the 30-term
+    # series has stopped converging (erf(4) = -245.4 in the reference)
+    x = np.linspace(-6, 6, 4801)
+    prog = single_op("Builtin1", 1, FNOP["erf"], 0, n_in=1)
+    ref = OracleProgram.from_program(prog).eval_batch([x], x.size)[0]
+    got = gpu_eval(prog, [x], x.size)[0]
+    assert bits_equal(got, ref)
+    assert abs(ref[np.argmin(np.abs(x - 0.5))] - 0.5204998778130465) < 1e-15
+    assert got[np.argmin(np.abs(x - 4.0))] < -100.0
+
+
+# ---- transcendentals: <= 4 ulp --------------------------------------------------------------------
+TRANSCENDENTAL = [
+    ("Sin", (-50, 50)), ("Cos", (-50, 50)), ("Exp", (-700, 700)), ("Ln", (1e-300, 1e300)),
+    ("RecipExpm1", (-30, 30)), ("ExpSqr", (-20, 20)), ("ExpSqrNeg", (-20, 20)),
+]
+
+
+@pytest.mark.parametrize("op,rng_", TRANSCENDENTAL)
+def test_transcendental_opcodes_within_4_ulp(op, rng_):
+    rng = np.random.default_rng(5)
+    lo, hi = rng_
+    if op == "Ln":
+        x = np.exp(rng.uniform(np.log(lo), np.log(hi), 20000))
+    else:
+        x = rng.uniform(lo, hi, 20000)
+    x = np.concatenate([x, [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-310, -1.0]])
+    prog = single_op(op, 1, 0, n_in=1)
+    ref = OracleProgram.from_program(prog).eval_batch([x], x.size)[0]
+    got = gpu_eval(prog, [x], x.size)[0]
+    d = ulp_distance(got, ref)
+    assert d.max() <= 4, f"{op}: max ulp {d.max()} at x={x[np.argmax(d)]!r}"
+
+
+def test_sincos_matches_separate_sin_and_cos():
+    rng = np.random.default_rng(6)
+    x = np.concatenate([rng.uniform(-1e4, 1e4, 20000), [0.0, -0.0, np.inf, np.nan, 1e22, 1e300]])
+    prog = single_op("SinCos", 1, 2, 0, n_in=1, n_out=2)
+    ref = OracleProgram.from_program(prog).eval_batch([x], x.size)
+    got = gpu_eval(prog, [x], x.size)
+    assert ulp_distance(got[0], ref[0]).max() <= 4
+    assert ulp_distance(got[1], ref[1]).max() <= 4
+    # the lowering merges Sin(x) + Cos(x) into one SinCos: it must give the same bits as the two calls
+    sep = Program(flat=assemble([("Sin", 1, 0), ("Cos", 2, 0)]), consts=[], arg_pool=[], param_count=1,
+                  workspace_size=3, result_regs=[1, 2])
+    got_s = gpu_eval(single_op("Sin", 1, 0, n_in=1), [x], x.size)[0]
+    got_c = gpu_eval(single_op("Cos", 1, 0, n_in=1), [x], x.size)[0]
+    merged = gpu_eval(sep, [x], x.size)
+    assert bits_equal(merged[0], got_s) and bits_equal(merged[1], got_c)
+
+
+def test_pow_within_4_ulp_and_special_cases():
+    rng = np.random.default_rng(7)
+    a = np.concatenate([rng.uniform(0.01, 30, 10000), rng.uniform(-30, -0.01, 2000)])
+    b = np.concatenate([rng.uniform(-8, 8, 10000), rng.integers(-5, 6, 2000).astype(float)])
+    sp = np.array([0.0, -0.0, 1.0, -1.0, 2.0, -8.0, np.inf, -np.inf, np.nan, 0.5, 1.0 / 3.0])
+    a = np.concatenate([a, np.repeat(sp, sp.size)])
+    b = np.concatenate([b, np.tile(sp, sp.size)])
+    prog = single_op("Pow", 2, 0, 1, n_in=2)
+    ref = OracleProgram.from_program(prog).eval_batch([a, b], a.size)[0]
+    got = gpu_eval(prog, [a, b], a.size)[0]
+    d = ulp_distance(got, ref)
+    assert d.max() <= 4, f"pow: {d.max()} ulp at {a[np.argmax(d)]!r}^{b[np.argmax(d)]!r}"
+
+
+BUILTIN1_DOMAINS = {
+    "asin": (-1, 1), "acos": (-1, 1), "atanh": (-0.999, 0.999), "acosh": (1, 50), "asech": (0.01, 1),
+    "acoth": (1.01, 50), "asec": (1, 50), "acsc": (1, 50), "log1p": (-0.99, 50), "gamma": (-5.5, 20),
+    "lgamma": (-5.5, 50), "digamma": (-5.5, 30), "trigamma": (0.05, 30), "tetragamma": (0.05, 30),
+    "lambert_w": (-0.36, 50), "elliptic_k": (-0.999, 0.999), "elliptic_e": (-1, 1), "zeta": (-8, 30),
+    "erfc": (-6, 30), "sinh": (-30, 30), "cosh": (-30, 30), "expm1": (-30, 30), "exp_neg": (-30, 30),
+    "exp_polar": (-30, 30), "tan": (-1.5, 1.5),
+}
+
+
+@pytest.mark.parametrize("fn", FUZZ_BUILTIN1)
+def test_builtin1(fn):
+    rng = np.random.default_rng(zlib.crc32(fn.encode()))
+    lo, hi = BUILTIN1_DOMAINS.get(fn, (-6, 6))
+    x = np.concatenate([rng.uniform(lo, hi, 6000), [0.0, -0.0, 1.0, -1.0, 2.0, -2.0, 0.5, np.inf, -np.inf, np.nan,
+                                                     -3.0, 1e-15, 1e5]])
+    prog = single_op("Builtin1", 1, FNOP[fn], 0, n_in=1)
+    ref = OracleProgram.from_program(prog).eval_batch([x], x.size)[0]
+    got = gpu_eval(prog, [x], x.size)[0]
+    # special functions chain several libm calls (pow, exp, log, sin) whose <=2 ulp differences are
+    # amplified by the function's own conditioning: the end-to-end bar applies
+    assert_close(got, ref, rtol=2e-11, atol=1e-13, what=fn)
+
+
+@pytest.mark.parametrize("fn", FUZZ_BUILTIN2 + ["zeta_deriv"])
+def test_builtin2(fn):
+    rng = np.random.default_rng(zlib.crc32(fn.encode()))
+    n = 3000
+    if fn in ("bessel_j", "bessel_y", "bessel_i", "bessel_k", "hermite", "polygamma", "zeta_deriv"):
+        hi_order = {"zeta_deriv": 4, "polygamma": 6, "hermite": 12}.get(fn, 9)
+        a = rng.integers(-3 if fn.startswith("bessel") else 0, hi_order, n).astype(float)
+        b = rng.uniform(0.05, 25, n) if fn != "zeta_deriv" else rng.uniform(1.2, 12, n)
+        a = np.concatenate([a, [0.0, 1.0, 2.0, np.nan, 1e10, 2.4]])
+        b = np.concatenate([b, [0.0, -1.0, 1e-12, 1.0, 1.0, 3.0]])
+    elif fn == "log":
+        a = np.concatenate([rng.uniform(0.1, 10, n), [1.0, 0.0, -2.0, 2.0, 10.0, np.nan]])
+        b = np.concatenate([rng.uniform(0.0, 100, n), [5.0, 5.0, 5.0, -1.0, 0.0, 1.0]])
+    elif fn == "beta":
+        a = np.concatenate([rng.uniform(-3.5, 10, n), [0.0, -1.0, 2.0, 0.5]])
+        b = np.concatenate([rng.uniform(-3.5, 10, n), [1.0, 2.0, -2.0, 0.5]])
+    else:  # atan2
+        a = np.concatenate([rng.normal(0, 5, n), [0.0, -0.0, 0.0, 1.0, np.inf, np.nan]])
+        b = np.concatenate([rng.normal(0, 5, n), [0.0, -0.0, -1.0, 0.0, -np.inf, 1.0]])
+    prog = single_op("Builtin2", 2, FNOP[fn], 0, 1, n_in=2)
+    ref = OracleProgram.from_program(prog).eval_batch([a, b], a.size)[0]
+    got = gpu_eval(prog, [a, b], a.size)[0]
+    rtol = 1e-9 if fn in ("bessel_j", "bessel_y", "beta", "zeta_deriv") else 2e-11
+    assert_close(got, ref, rtol=rtol, atol=1e-12, what=fn)
+
+
+def test_builtin3_and_4():
+    rng = np.random.default_rng(8)
+    n = 2000
+    l = rng.integers(0, 7, n).astype(float)
+    m = np.array([rng.integers(-int(li), int(li) + 1) for li in l], dtype=float)
+    x = rng.uniform(-1, 1, n)
+    phi = rng.uniform(-3, 3, n)
+    p3 = single_op("Builtin3", 3, FNOP["assoc_legendre"], 0, 1, 2, n_in=3)
+    ref = OracleProgram.from_program(p3).eval_batch([l, m, x], n)[0]
+    assert_close(gpu_eval(p3, [l, m, x], n)[0], ref, rtol=1e-11, atol=1e-13, what="assoc_legendre")
+    p4 = single_op("Builtin4", 4, FNOP["spherical_harmonic"], 0, 1, 2, 3, n_in=4)
+    theta = rng.uniform(0, 3.1, n)
+    ref = OracleProgram.from_program(p4).eval_batch([l, m, theta, phi], n)[0]
+    assert_close(gpu_eval(p4, [l, m, theta, phi], n)[0], ref, rtol=1e-10, atol=1e-13, what="spherical_harmonic")
+
+
+def test_unreachable_builtin1_is_nan_like_the_reference_release_build():
+    x = np.linspace(0.1, 4, 64)
+    for fn in ("sin", "cos", "exp", "ln", "sqrt"):
+        prog = single_op("Builtin1", 1, FNOP[fn], 0, n_in=1)
+        h = _handle(prog)
+        assert h.info().quirk_flags & 1
+        assert np.isnan(gpu_eval(prog, [x], x.size)[0]).all()
+        assert np.isnan(OracleProgram.from_program(prog).eval_batch([x], x.size)[0]).all()
+
+
+# ---- the five named programs ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(workloads.WORKLOADS))
+@pytest.mark.parametrize("n", [1, 255, 256, 4097, 100_003])
+def test_named_program_single_pass(name, n):
+    w = workloads.get(name)
+    cols = w.make_inputs(n, 17)
+    ref = OracleProgram.from_program(w.program).run_chunked(cols, n)
+    got = gpu_eval(w.program, cols, n)
+    for k, (g, r) in enumerate(zip(got, ref)):
+        assert_close(g, r, RTOL, ATOL, what=f"{name} output {k}")
+
+
+@pytest.mark.parametrize("name", ["clifford", "aizawa", "double_pendulum"])
+def test_in_kernel_iteration_matches_oracle_per_step_and_short_runs(name):
+    w = workloads.get(name)
+    n = 5000
+    cols = w.make_inputs(n, 23)
+    o = OracleProgram.from_program(w.program)
+    h = _handle(w.program)
+    # chaotic maps amplify ulps exponentially, so parity is checked per step from identical inputs
+    state = [c.copy() for c in cols]
+    for _ in range(5):
+        ref = o.iterate(state, 1)
+        got = [s.copy() for s in state]
+        h.iterate_host(got, 1)
+        for g, r in zip(got, ref):
+            assert_close(g, r, RTOL, ATOL, what=f"{name} step")
+        state = ref
+    # and a short in-kernel run keeps its state on chip correctly
+    ref = o.iterate(cols, 3)
+    got = [c.copy() for c in cols]
+    h.iterate_host(got, 3)
+    for g, r in zip(got, ref):
+        assert_close(g, r, 1e-9, 1e-11, what=f"{name} 3 iterations")
+    # iterating k times in one launch == k launches of one iteration (same device code: bit-exact)
+    a = [c.copy() for c in cols]
+    h.iterate_host(a, 7)
+    b = [c.copy() for c in cols]
+    for _ in range(7):
+        h.iterate_host(b, 1)
+    for x, y in zip(a, b):
+        assert bits_equal(x, y)
+
+
+def test_fused_program_equals_separately_compiled_programs_on_device():
+    for name in ("clifford", "aizawa", "terrain_gradient"):
+        w = workloads.get(name)
+        if name == "aizawa":
+            fused = w.extra["field"]
+        else:
+            fused = w.program
+        n = 3000
+        cols = w.make_inputs(n, 3)
+        got = gpu_eval(fused, cols, n)
+        hs = [_handle(p) for p in w.parts]
+        via_abi = DeviceProgramHandle.fuse(hs)
+        outs = [np.empty(n) for _ in w.parts]
+        via_abi.eval_host(cols, outs, n)
+        for k, p in enumerate(w.parts):
+            sep = gpu_eval(p, cols, n)[0]
+            assert bits_equal(outs[k], sep), "saf_program_fuse changed results"
+            assert_close(got[k], sep, RTOL, ATOL, what=f"{name} fused vs separate {k}")
+
+
+# ---- random programs ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(40))
+def test_random_programs_against_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    prog = random_program(rng, n_params=int(rng.integers(1, 5)), n_instr=int(rng.integers(1, 40)),
+                          n_results=int(rng.integers(1, 4)))
+    n = 777
+    cols = [rng.uniform(-3, 3, n) for _ in range(prog.param_count)]
+    ref = OracleProgram.from_program(prog).eval_batch(cols, n)
+    got = gpu_eval(prog, cols, n)
+    for g, r in zip(got, ref):
+        # the reference's own fuzz comparator (fuzz_evaluator.rs:211-230): NaN==NaN, inf sign, rel 1e-6
+        assert_close(g, r, rtol=1e-6, atol=1e-10, what=f"seed {seed}")
+
+
+# ---- driver semantics (batch.rs / scalar.rs) ------------------------------------------------------------
+def test_column_length_mismatch_is_an_error():
+    w = workloads.get("clifford")
+    h = _handle(w.program)
+    x, y = np.zeros(100), np.zeros(99)
+    with pytest.raises(SafError) as ei:
+        h.eval_host([x, y], [np.empty(100), np.empty(100)], 100)
+    assert ei.value.code == 1
+    assert "same length" in ei.value.message
+
+
+def test_broadcast_missing_and_extra_columns():
+    prog = single_op("MulAdd", 3, 0, 1, 2, n_in=3)
+    rng = np.random.default_rng(9)
+    n = 5000
+    a, b, c = rng.normal(size=n), rng.normal(size=1700), rng.normal(size=1)
+    o = OracleProgram.from_program(prog)
+    # short columns broadcast their last value (scalar.rs:203-207), also across chunk boundaries
+    assert bits_equal(gpu_eval(prog, [a, b, c], n, broadcast=True)[0], o.eval_batch([a, b, c], n)[0])
+    # missing columns read as 0.0, extra ones are ignored (scalar.rs:182-197)
+    assert bits_equal(gpu_eval(prog, [a, a], n)[0], o.eval_batch([a, a], n)[0])
+    extra = [a, a, a, a, a]
+    assert bits_equal(gpu_eval(prog, extra, n)[0], o.eval_batch(extra, n)[0])
+    # no columns at all: n_points evaluations of the constant program
+    assert bits_equal(gpu_eval(prog, [], 3)[0], np.zeros(3))
+
+
+def test_empty_and_unaligned_and_large_chunked():
+    w = workloads.get("single_expr")
+    h = _handle(w.program)
+    h.eval_host([np.empty(0)], [np.empty(0)], 0)  # n_points == 0 is Ok (batch.rs:44-47)
+    n = (1 << 21) * 2 + 12345  # three pipeline chunks
+    x = w.make_inputs(n + 1, 1)[0]
+    ref = OracleProgram.from_program(w.program).run_chunked([x[1:]], n)[0]
+    out = np.empty(n + 1)
+    h.eval_host([x[1:]], [out[1:]], n)  # 8-byte aligned, not 16: the 1-point-per-thread path
+    assert_close(out[1:], ref, RTOL, ATOL, what="unaligned host")
+
+
+def test_device_resident_columns_and_streams():
+    import torch
+    w = workloads.get("clifford")
+    h = _handle(w.program)
+    n = 200_001
+    cols = w.make_inputs(n, 5)
+    ref = OracleProgram.from_program(w.program).run_chunked(cols, n)
+    tc = [torch.from_numpy(c).cuda() for c in cols]
+    to = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in ref]
+    s = torch.cuda.Stream()
+    before = kernel_launch_count()
+    with torch.cuda.stream(s):
+        h.eval_device([t.data_ptr() for t in tc], [n, n], [t.data_ptr() for t in to], n, stream=s.cuda_stream)
+    s.synchronize()
+    assert kernel_launch_count() == before + 1
+    for t, r in zip(to, ref):
+        assert_close(t.cpu().numpy(), r, RTOL, ATOL, what="device columns")
+    # odd element offset: 8-byte aligned views
+    to2 = [torch.empty(n + 1, dtype=torch.float64, device="cuda") for _ in ref]
+    h.eval_device([t.data_ptr() for t in tc], [n, n], [t[1:].data_ptr() for t in to2], n)
+    torch.cuda.synchronize()
+    for t, r in zip(to2, ref):
+        assert_close(t[1:].cpu().numpy(), r, RTOL, ATOL, what="unaligned device outputs")
+
+
+def test_large_program_takes_the_global_memory_path():
+    w = workloads.terrain_gradient(n_terms=160)  # code + constants exceed the constant-bank blob
+    n = 2000
+    cols = w.make_inputs(n, 2)
+    ref = OracleProgram.from_program(w.program).run_chunked(cols, n)
+    got = gpu_eval(w.program, cols, n)
+    for g, r in zip(got, ref):
+        assert_close(g, r, RTOL, ATOL, what="large program")

@@ -1,0 +1,102 @@
+"""Host half of the product on CPU: the lowering (value numbering, chain expansion, scheduling,
+accumulator forwarding, slot allocation) must preserve results BIT FOR BIT.
+
+The device program exported by the C ABI is run by tests/dev_emulator.py (kernel state model, oracle
+leaf math) and compared with the oracle executing the original reference bytecode."""
+import numpy as np
+import pytest
+
+from dev_emulator import run_device_program
+from oracle import OracleProgram
+from symbanafis_b200 import workloads
+from symbanafis_b200._lib import DeviceProgramHandle, SafError
+from util import bits_equal, random_program
+
+
+def _handle(prog):
+    return DeviceProgramHandle.create(prog.flat, prog.consts, prog.arg_pool, prog.param_count,
+                                      prog.workspace_size, prog.result_regs)
+
+
+def _check(prog, cols, n, iters=1):
+    h = _handle(prog)
+    code, consts, pslot, rfield = h.export()
+    o = OracleProgram.from_program(prog)
+    ref = o.eval_batch(cols, n) if iters == 1 else o.iterate(cols, iters)
+    got = run_device_program(code, consts, pslot, rfield, cols, n, iters)
+    for k, (r, g) in enumerate(zip(ref, got)):
+        assert bits_equal(g, r), f"result {k} differs"
+    return h
+
+
+@pytest.mark.parametrize("name", list(workloads.WORKLOADS))
+def test_workload_lowering_is_bit_exact(name):
+    w = workloads.get(name)
+    cols = w.make_inputs(96, 11)
+    h = _check(w.program, cols, 96)
+    info = h.info()
+    assert info.n_results == len(w.program.result_regs)
+    assert info.n_slots <= 64, "scheduler must keep the on-chip register file small"
+
+
+@pytest.mark.parametrize("name", ["clifford", "aizawa", "double_pendulum"])
+def test_iterated_lowering_is_bit_exact(name):
+    w = workloads.get(name)
+    cols = w.make_inputs(40, 5)
+    _check(w.program, cols, 40, iters=4)
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_programs(seed):
+    rng = np.random.default_rng(seed)
+    prog = random_program(rng, n_params=int(rng.integers(1, 5)), n_instr=int(rng.integers(1, 40)),
+                          n_results=int(rng.integers(1, 4)))
+    n = 33
+    cols = [rng.uniform(-3, 3, n) for _ in range(prog.param_count)]
+    _check(prog, cols, n)
+
+
+def test_result_is_parameter_or_constant():
+    from symbanafis_b200.isa import Program, assemble
+    # program with no instructions: results are a parameter and a constant
+    prog = Program(flat=assemble([]), consts=[2.5], arg_pool=[], param_count=2, workspace_size=3, result_regs=[1, 2, 1])
+    rng = np.random.default_rng(0)
+    cols = [rng.normal(size=17), rng.normal(size=17)]
+    _check(prog, cols, 17)
+    # swap map (x, y) -> (y, x) iterated: result slots must not alias parameter slots
+    swap = Program(flat=assemble([]), consts=[], arg_pool=[], param_count=2, workspace_size=2, result_regs=[1, 0])
+    _check(swap, cols, 17, iters=3)
+
+
+def test_fuse_matches_separate_programs():
+    w = workloads.get("aizawa")
+    hs = [_handle(p) for p in w.parts]
+    fused = DeviceProgramHandle.fuse(hs)
+    info = fused.info()
+    assert info.n_results == 3
+    assert info.n_dev_instructions < sum(h.info().n_dev_instructions for h in hs)  # (z - 0.7) is shared
+    cols = w.make_inputs(50, 3)
+    code, consts, pslot, rfield = fused.export()
+    got = run_device_program(code, consts, pslot, rfield, cols, 50)
+    for p, g in zip(w.parts, got):
+        ref = OracleProgram.from_program(p).eval_batch(cols, 50)[0]
+        assert bits_equal(g, ref)
+
+
+def test_validator_rejects_malformed_programs():
+    from symbanafis_b200.isa import assemble
+    bad = [
+        (assemble([("Add", 5, 0, 1)]), 2, 3, [2]),               # destination out of bounds
+        (assemble([("Add", 2, 0, 3)]), 2, 4, [2]),               # read before definition
+        (np.asarray([4, 2, 0, 1], dtype=np.uint32), 2, 3, [2]),  # no End sentinel
+        (np.asarray([99, 0], dtype=np.uint32), 2, 3, [0]),       # unknown opcode
+        (assemble([("AddN", 2, 0, 3)]), 2, 3, [2]),              # arg pool out of range
+        (assemble([("Builtin1", 2, 200, 0)]), 2, 3, [2]),        # unknown FnOp
+        (assemble([("Add", 2, 0, 1)]), 2, 3, [7]),               # result register out of bounds
+    ]
+    for flat, pc, ws, res in bad:
+        with pytest.raises(SafError) as ei:
+            DeviceProgramHandle.create(flat, [], [], pc, ws, res)
+        assert ei.value.code == 2
+        with pytest.raises(Exception):
+            OracleProgram(flat, [], [], pc, ws, res)
