@@ -17,6 +17,13 @@
 #define SAF_FRAC_2_PI 0.636619772367581343075535053490057448 /* f64::consts::FRAC_2_PI */
 #define SAF_EPSILON 1e-14                              /* crate::EPSILON, src/lib.rs:321 */
 
+/* Work caps (documented deviation, DESIGN.md "Unbounded loops of the reference"): the reference walks
+ * `while xv < 6 { xv += 1 }` recurrences and order-n loops without any bound, so trigamma(-inf) never
+ * returns and besselj(2^31-1, x) runs for minutes.  Oracle and device both answer NaN instead when the
+ * reference would need more than SAF_MAX_SHIFT recurrence steps or an order above SAF_MAX_ORDER. */
+#define SAF_MAX_SHIFT 4194304.0
+#define SAF_MAX_ORDER 65536
+
 /* ---- Rust std / compiler-rt pieces that are not under /root/reference ---- */
 
 /* f64::powi -> llvm.powi.f64.i32 -> compiler-rt __powidf2 (published algorithm:
@@ -219,6 +226,7 @@ double saf_o_digamma(double x) {
 /* ---- polygamma.rs:49-68 ---- */
 double saf_o_trigamma(double x) {
     if (x <= 0.0 && fract(x) == 0.0) return INFINITY;
+    if (x < -SAF_MAX_SHIFT) return NAN; /* work cap */
     double xv = x, r = 0.0;
     const double six = 6.0, one = 1.0;
     while (xv < six) {
@@ -238,6 +246,7 @@ double saf_o_tetragamma(double x) {
         double sign = -sign_from_delta(delta);
         return signed_infinity(sign);
     }
+    if (x < -SAF_MAX_SHIFT) return NAN; /* work cap */
     double xv = x, r = 0.0;
     const double six = 6.0, one = 1.0, two = 2.0;
     while (xv < six) {
@@ -253,6 +262,7 @@ double saf_o_polygamma(int32_t n, double x) {
     if (n < 0) return NAN;
     if (n == 0) return saf_o_digamma(x);
     if (n == 1) return saf_o_trigamma(x);
+    if (n > SAF_MAX_ORDER || x < -SAF_MAX_SHIFT) return NAN; /* work cap */
 
     if (x <= 0.0 && fract(x) == 0.0) {
         double delta = x - round(x);
@@ -452,6 +462,7 @@ static double zeta_deriv_reflection(int32_t n, double s) {
 double saf_o_zeta_deriv(int32_t n, double x) {
     if (n < 0) return NAN;
     if (n == 0) return saf_o_zeta(x);
+    if (n > 16) return NAN; /* work cap: the reference needs 2^(n-4) zeta evaluations below s = 1 */
     const double one = 1.0, epsilon = 1e-10;
     double delta = x - one;
     if (fabs(delta) < epsilon) {
@@ -713,6 +724,7 @@ static double bessel_j_miller(int32_t n, double x) {
 
 /* ---- bessel.rs:16-35 ---- */
 double saf_o_bessel_j(int32_t n, double x) {
+    if (n > SAF_MAX_ORDER || n < -SAF_MAX_ORDER) return NAN; /* work cap */
     int32_t n_abs = n < 0 ? -n : n;
     double ax = fabs(x);
     const double threshold = 1e-10;
@@ -776,6 +788,7 @@ static double bessel_y1(double x) {
 
 /* ---- bessel.rs:256-281 ---- */
 double saf_o_bessel_y(int32_t n, double x) {
+    if (n > SAF_MAX_ORDER || n < -SAF_MAX_ORDER) return NAN; /* work cap */
     if (x <= 0.0) return NAN;
     int32_t n_abs = n < 0 ? -n : n;
     double y0 = bessel_y0(x);
@@ -833,6 +846,7 @@ static double bessel_i1(double x) {
 
 /* ---- bessel.rs:410-477 ---- */
 double saf_o_bessel_i(int32_t n, double x) {
+    if (n > SAF_MAX_ORDER || n < -SAF_MAX_ORDER) return NAN; /* work cap */
     int32_t n_abs = n < 0 ? -n : n;
     if (n_abs == 0) return bessel_i0(x);
     if (n_abs == 1) return bessel_i1(x);
@@ -903,6 +917,7 @@ static double bessel_k1(double x) {
 
 /* ---- bessel.rs:565-590 ---- */
 double saf_o_bessel_k(int32_t n, double x) {
+    if (n > SAF_MAX_ORDER || n < -SAF_MAX_ORDER) return NAN; /* work cap */
     if (x <= 0.0) return NAN;
     int32_t n_abs = n < 0 ? -n : n;
     double k0 = bessel_k0(x);
@@ -923,6 +938,7 @@ double saf_o_bessel_k(int32_t n, double x) {
 
 /* ---- polynomials.rs:10-31 ---- */
 double saf_o_hermite(int32_t n, double x) {
+    if (n > SAF_MAX_ORDER) return NAN; /* work cap */
     if (n < 0) return NAN;
     if (n == 0) return 1.0;
     const double two = 2.0;
@@ -940,6 +956,7 @@ double saf_o_hermite(int32_t n, double x) {
 
 /* ---- polynomials.rs:39-88 ---- */
 double saf_o_assoc_legendre(int32_t l, int32_t m, double x) {
+    if (l > SAF_MAX_ORDER) return NAN; /* work cap */
     int32_t m_abs = m < 0 ? -m : m;
     if (l < 0 || m_abs > l) return NAN;
     double x_abs = fabs(x);
@@ -975,6 +992,7 @@ double saf_o_assoc_legendre(int32_t l, int32_t m, double x) {
 
 /* ---- polynomials.rs:96-128 ---- */
 double saf_o_spherical_harmonic(int32_t l, int32_t m, double theta, double phi) {
+    if (l > SAF_MAX_ORDER) return NAN; /* work cap */
     int32_t m_abs = m < 0 ? -m : m;
     if (l < 0 || m_abs > l) return NAN;
     double cos_theta = cos(theta);

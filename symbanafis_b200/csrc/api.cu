@@ -136,7 +136,7 @@ extern "C" int saf_program_get_info(const saf_program *p, saf_program_info *info
     info->param_count = p->dev.param_count;
     info->n_results = (uint32_t)p->dev.result_field.size();
     info->n_ref_instructions = p->dev.n_ref_instructions;
-    info->n_dev_instructions = (uint32_t)p->dev.code.size() - 1;
+    info->n_dev_instructions = p->dev.n_dev_instructions;
     info->n_slots = p->dev.n_slots;
     info->n_consts = (uint32_t)p->dev.consts.size();
     info->n_acc_forwards = p->dev.n_acc_forwards;
@@ -244,7 +244,7 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     if (e == cudaErrorInvalidConfiguration)
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_shape");
-    e = launch_interpreter(d, blob, n_blob, shape, stream);
+    e = launch_interpreter(d, blob, n_blob, prog->consts_in_blob, shape, stream);
     if (e != cudaSuccess) return cuda_fail(e, "interpreter launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return SAF_OK;

@@ -1,24 +1,28 @@
 // kernel.cu -- the sm_100a interpreter kernel for SymbAnaFis device programs.
 //
-// One thread evaluates P points (P = 1 or 2).  Every lane of every warp runs the SAME device
-// program on different points, so the program counter, the fetched instruction word and the opcode
-// switch are warp-uniform: there is no divergence in the dispatch, only inside data-dependent
-// special-function loops.
+// One thread evaluates P points (P = 1 or 2), 128 threads per block.  Every lane of every warp runs
+// the SAME device program on different points, so the program counter, the fetched instruction word
+// and the opcode jump are warp-uniform: there is no divergence in the dispatch, only inside the
+// data-dependent loops of a few special functions.
 //
 //   program words + constants : kernel parameter space = constant bank (ConstBlob), read through the
 //                               constant cache with uniform addresses; global-memory fallback
-//                               (read-only path) for programs above BLOB_LARGE words
+//                               (read-only path) for programs that do not fit
 //   live values ("registers")  : shared memory laid out [slot][thread] as f64 (P=1) or f64x2 (P=2):
-//                               consecutive lanes touch consecutive 8/16-byte words -> conflict free
+//                               consecutive lanes touch consecutive 8/16-byte words -> conflict free;
+//                               the slot stride is a compile-time constant (fixed block size)
 //   accumulator                : the result of the previous instruction stays in real registers; the
 //                               lowering (lower.cpp) routes single-use values through it so they
 //                               never touch shared memory
+//   dispatch                   : one dense switch over opcodes that are specialised by operand kind
+//                               for the cheap operations (no per-operand branches in their handlers)
 //   columns                    : struct-of-arrays f64, one coalesced 128-bit (P=2) or 64-bit load per
 //                               column per thread, streaming cache hints; results likewise
 //
 // Arithmetic handlers use the explicit-rounding intrinsics (__dadd_rn, __dmul_rn, __fma_rn, ...) so
 // that nvcc can never contract a Mul followed by an Add: the reference distinguishes Mul;Add from
-// MulAdd (macros.rs:69-75 vs :128-138).
+// MulAdd (macros.rs:69-75 vs :128-138).  -fmad stays at its default because the CUDA math library
+// needs it (see devmath.cuh).
 #include "kernel.cuh"
 
 #include <cstdio>
@@ -49,57 +53,62 @@ __device__ __forceinline__ void st_stream2(double *p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
+// Shared-memory register file.  `my` points at this thread's element of slot 0; slot i lives
+// SLOT_BYTES further.  A field is index << 2 | kind, so (field & ~3) * (SLOT_BYTES / 4) is the byte
+// offset of an S field: one LOP3 + one IMAD.
 template <int P>
-__device__ __forceinline__ void slot_load(const double *base, uint32_t stride, uint32_t idx, Pt<P> &o) {
-    const double *p = base + (size_t)idx * stride;
-    if constexpr (P == 2) {
-        double2 t = *reinterpret_cast<const double2 *>(p);
-        o.v[0] = t.x;
-        o.v[1] = t.y;
-    } else {
-        o.v[0] = *p;
+struct Rf {
+    static constexpr uint32_t SLOT_BYTES = BLOCK_THREADS * P * 8;
+    __device__ __forceinline__ static void load(const char *my, uint32_t field, Pt<P> &o) {
+        const char *p = my + (field & 0xfffcu) * (SLOT_BYTES / 4);
+        if constexpr (P == 2) {
+            double2 t = *reinterpret_cast<const double2 *>(p);
+            o.v[0] = t.x;
+            o.v[1] = t.y;
+        } else {
+            o.v[0] = *reinterpret_cast<const double *>(p);
+        }
     }
-}
-template <int P>
-__device__ __forceinline__ void slot_store(double *base, uint32_t stride, uint32_t idx, const Pt<P> &o) {
-    double *p = base + (size_t)idx * stride;
-    if constexpr (P == 2) {
-        *reinterpret_cast<double2 *>(p) = make_double2(o.v[0], o.v[1]);
-    } else {
-        *p = o.v[0];
+    __device__ __forceinline__ static void store(char *my, uint32_t field, const Pt<P> &o) {
+        char *p = my + (field & 0xfffcu) * (SLOT_BYTES / 4);
+        if constexpr (P == 2) {
+            *reinterpret_cast<double2 *>(p) = make_double2(o.v[0], o.v[1]);
+        } else {
+            *reinterpret_cast<double *>(p) = o.v[0];
+        }
     }
-}
+};
 
 #define SAF_FOR_P _Pragma("unroll") for (int p = 0; p < P; ++p)
 
 } // namespace
 
-// WORDS > 0: program in the constant bank; WORDS == 0: program in global memory.
-template <int P, int WORDS>
-__global__ void __launch_bounds__(256, 2)
-saf_interp_kernel(const __grid_constant__ LaunchDesc d,
-                  const __grid_constant__ ConstBlob<(WORDS > 0 ? WORDS : 1)> blob) {
+// CODE_IN_BLOB / K_IN_BLOB: program words / constants come from the constant bank (kernel
+// parameter `blob`), otherwise from global memory through the read-only path.
+template <int P, int WORDS, bool CODE_IN_BLOB, bool K_IN_BLOB>
+__global__ void __launch_bounds__(BLOCK_THREADS, 4)
+saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ ConstBlob<WORDS> blob) {
     extern __shared__ __align__(16) unsigned char saf_smem[];
-    const uint32_t stride = blockDim.x * P;                       // doubles between consecutive slots
-    double *const my = reinterpret_cast<double *>(saf_smem) + threadIdx.x * P;
+    char *const my = reinterpret_cast<char *>(saf_smem) + threadIdx.x * (P * 8);
+    using RF = Rf<P>;
 
-    auto fetch_word = [&](uint32_t pc) -> uint64_t {
-        if constexpr (WORDS > 0) return blob.w[pc];
-        else return __ldg(reinterpret_cast<const unsigned long long *>(d.code_global) + pc);
+    auto fetch_word = [&](uint32_t pc) -> uint2 {
+        unsigned long long w;
+        if constexpr (CODE_IN_BLOB) w = blob.w[pc];
+        else w = __ldg(reinterpret_cast<const unsigned long long *>(d.code_global) + pc);
+        return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
     };
-    auto fetch_const = [&](uint32_t idx) -> double {
-        if constexpr (WORDS > 0) {
-            // constants ride in the blob right after the code unless they did not fit
-            if (d.consts_global == nullptr) return __longlong_as_double((long long)blob.w[d.n_code + idx]);
-        }
-        return __ldg(d.consts_global + idx);
+    auto konst = [&](uint32_t field) -> double { // K field -> value (warp-uniform load)
+        const uint32_t idx = field >> KIND_BITS;
+        if constexpr (K_IN_BLOB) return __longlong_as_double((long long)blob.w[d.n_code + idx]);
+        else return __ldg(d.consts_global + idx);
     };
 
-    const unsigned long long tile_points = (unsigned long long)blockDim.x * P;
-    const unsigned long long n_tiles = (d.n_points + tile_points - 1) / tile_points;
+    constexpr unsigned long long TILE = (unsigned long long)BLOCK_THREADS * P;
+    const unsigned long long n_tiles = (d.n_points + TILE - 1) / TILE;
 
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned long long i0 = tile * tile_points + (unsigned long long)threadIdx.x * P;
+        const unsigned long long i0 = tile * TILE + (unsigned long long)threadIdx.x * P;
 
         // ---- prologue: columns -> parameter slots (scalar.rs:182-207 rules) ----
         for (uint32_t j = 0; j < d.n_params; ++j) {
@@ -119,7 +128,7 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d,
                     }
                 }
             }
-            slot_store<P>(my, stride, s, v);
+            RF::store(my, s << KIND_BITS, v);
         }
 
         Pt<P> acc, x0, x1;
@@ -129,99 +138,142 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d,
             // ---- the interpreter loop: warp-uniform pc / opcode ----
             uint32_t pc = 0;
             for (;;) {
-                const uint64_t w = fetch_word(pc++);
-                const uint32_t op = (uint32_t)w & 0xffu;
-                if (op == D_END) break;
-                const uint32_t fd = (uint32_t)(w >> 8) & FIELD_MASK;
-                const uint32_t fa = (uint32_t)(w >> 22) & FIELD_MASK;
-                const uint32_t fb = (uint32_t)(w >> 36) & FIELD_MASK;
-                const uint32_t fc = (uint32_t)(w >> 50) & FIELD_MASK;
+                const uint2 w = fetch_word(pc++);
+                const uint32_t xop = w.x & 0xffu;
+                const uint32_t fd = w.x >> 16;
+                const uint32_t fa = w.y & 0xffffu;
+                const uint32_t fb = w.y >> 16;
 
-                auto operand = [&](uint32_t f, Pt<P> &o) {
-                    const uint32_t kind = f >> INDEX_BITS, idx = f & INDEX_MASK;
+                // run-time operand fetch for the heavy opcodes
+                auto any = [&](uint32_t f, Pt<P> &o) {
+                    const uint32_t kind = f & KIND_MASK;
                     if (kind == KIND_S) {
-                        slot_load<P>(my, stride, idx, o);
+                        RF::load(my, f, o);
                     } else if (kind == KIND_K) {
-                        const double k = fetch_const(idx);
+                        const double k = konst(f);
                         SAF_FOR_P o.v[p] = k;
                     } else {
                         o = acc;
                     }
                 };
 
-                Pt<P> a, b, c, r;
-                operand(fa, a);
-                if (op >= D_FIRST_BINARY) operand(fb, b);
-                if (op >= D_FIRST_TERNARY) operand(fc, c);
+                Pt<P> a, b, r;
+                bool done = false;
 
-                switch (op) {
-                case D_COPY: r = a; break;
-                case D_NEG: SAF_FOR_P r.v[p] = -a.v[p]; break;
-                case D_SQUARE: SAF_FOR_P r.v[p] = __dmul_rn(a.v[p], a.v[p]); break;
-                case D_CUBE: SAF_FOR_P r.v[p] = __dmul_rn(__dmul_rn(a.v[p], a.v[p]), a.v[p]); break;
-                case D_POW4: SAF_FOR_P { double t = __dmul_rn(a.v[p], a.v[p]); r.v[p] = __dmul_rn(t, t); } break;
-                case D_POW3_2: SAF_FOR_P r.v[p] = __dmul_rn(a.v[p], __dsqrt_rn(a.v[p])); break;
-                case D_INVPOW3_2: SAF_FOR_P r.v[p] = __ddiv_rn(1.0, __dmul_rn(a.v[p], __dsqrt_rn(a.v[p]))); break;
-                case D_INVSQRT: SAF_FOR_P r.v[p] = __ddiv_rn(1.0, __dsqrt_rn(a.v[p])); break;
-                case D_INVSQUARE: SAF_FOR_P r.v[p] = __ddiv_rn(1.0, __dmul_rn(a.v[p], a.v[p])); break;
-                case D_INVCUBE: SAF_FOR_P r.v[p] = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(a.v[p], a.v[p]), a.v[p])); break;
-                case D_RECIP: SAF_FOR_P r.v[p] = __ddiv_rn(1.0, a.v[p]); break;
-                case D_SIN: SAF_FOR_P r.v[p] = sin(a.v[p]); break;
-                case D_COS: SAF_FOR_P r.v[p] = cos(a.v[p]); break;
-                case D_EXP: SAF_FOR_P r.v[p] = exp(a.v[p]); break;
-                case D_LN: SAF_FOR_P r.v[p] = log(a.v[p]); break;
-                case D_SQRT: SAF_FOR_P r.v[p] = __dsqrt_rn(a.v[p]); break;
-                case D_RECIPEXPM1: SAF_FOR_P r.v[p] = __ddiv_rn(1.0, expm1(a.v[p])); break;
-                case D_EXPSQR: SAF_FOR_P r.v[p] = exp(__dmul_rn(a.v[p], a.v[p])); break;
-                case D_EXPSQRNEG: SAF_FOR_P r.v[p] = exp(-__dmul_rn(a.v[p], a.v[p])); break;
-                case D_EXPNEG: SAF_FOR_P r.v[p] = exp(-a.v[p]); break;
-                case D_SINCOS: {
+#define SAF_A_S RF::load(my, fa, a);
+#define SAF_A_K { const double k_ = konst(fa); SAF_FOR_P a.v[p] = k_; }
+#define SAF_A_A a = acc;
+#define SAF_B_S RF::load(my, fb, b);
+#define SAF_B_K { const double k_ = konst(fb); SAF_FOR_P b.v[p] = k_; }
+#define SAF_B_A b = acc;
+// light unary: two forms (a from a slot / from ACC)
+#define SAF_ULIGHT(OP, EXPR)                                                                       \
+    case X_ULIGHT + 2 * ((OP) - D_FIRST_LIGHT_UNARY): SAF_A_S SAF_FOR_P { EXPR; } break;           \
+    case X_ULIGHT + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_A_A SAF_FOR_P { EXPR; } break;
+// light binary: eight forms (K,K is never emitted)
+#define SAF_BCASE(OP, KA, KB, LA, LB, EXPR)                                                        \
+    case X_BLIGHT + 9 * ((OP) - D_FIRST_LIGHT_BINARY) + 3 * (KA) + (KB): LA LB SAF_FOR_P { EXPR; } break;
+#define SAF_BLIGHT(OP, EXPR)                                                                       \
+    SAF_BCASE(OP, KIND_S, KIND_S, SAF_A_S, SAF_B_S, EXPR)                                          \
+    SAF_BCASE(OP, KIND_S, KIND_K, SAF_A_S, SAF_B_K, EXPR)                                          \
+    SAF_BCASE(OP, KIND_S, KIND_ACC, SAF_A_S, SAF_B_A, EXPR)                                        \
+    SAF_BCASE(OP, KIND_K, KIND_S, SAF_A_K, SAF_B_S, EXPR)                                          \
+    SAF_BCASE(OP, KIND_K, KIND_ACC, SAF_A_K, SAF_B_A, EXPR)                                        \
+    SAF_BCASE(OP, KIND_ACC, KIND_S, SAF_A_A, SAF_B_S, EXPR)                                        \
+    SAF_BCASE(OP, KIND_ACC, KIND_K, SAF_A_A, SAF_B_K, EXPR)                                        \
+    SAF_BCASE(OP, KIND_ACC, KIND_ACC, SAF_A_A, SAF_B_A, EXPR)
+#define SAF_UHEAVY(OP, EXPR)                                                                       \
+    case X_UHEAVY + ((OP) - D_FIRST_HEAVY_UNARY): any(fa, a); SAF_FOR_P { EXPR; } break;
+#define SAF_BHEAVY(OP, EXPR)                                                                       \
+    case X_BHEAVY + ((OP) - D_FIRST_HEAVY_BINARY): any(fa, a); any(fb, b); SAF_FOR_P { EXPR; } break;
+#define SAF_TERN(OP, EXPR)                                                                         \
+    case X_TERN + ((OP) - D_FIRST_TERNARY): {                                                      \
+        const uint2 h = fetch_word(pc++);                                                          \
+        Pt<P> c;                                                                                   \
+        any(fa, a); any(fb, b); any(h.x & 0xffffu, c);                                             \
+        SAF_FOR_P { EXPR; }                                                                        \
+    } break;
+
+                switch (xop) {
+                case X_END: done = true; break;
+                case X_LOADK: SAF_A_K r = a; break;
+
+                SAF_ULIGHT(D_COPY, r.v[p] = a.v[p])
+                SAF_ULIGHT(D_NEG, r.v[p] = -a.v[p])
+                SAF_ULIGHT(D_SQUARE, r.v[p] = __dmul_rn(a.v[p], a.v[p]))
+                SAF_ULIGHT(D_CUBE, r.v[p] = __dmul_rn(__dmul_rn(a.v[p], a.v[p]), a.v[p]))
+                SAF_ULIGHT(D_POW4, double t_ = __dmul_rn(a.v[p], a.v[p]); r.v[p] = __dmul_rn(t_, t_))
+                SAF_ULIGHT(D_POW3_2, r.v[p] = __dmul_rn(a.v[p], __dsqrt_rn(a.v[p])))
+                SAF_ULIGHT(D_INVPOW3_2, r.v[p] = __ddiv_rn(1.0, __dmul_rn(a.v[p], __dsqrt_rn(a.v[p]))))
+                SAF_ULIGHT(D_INVSQRT, r.v[p] = __ddiv_rn(1.0, __dsqrt_rn(a.v[p])))
+                SAF_ULIGHT(D_INVSQUARE, r.v[p] = __ddiv_rn(1.0, __dmul_rn(a.v[p], a.v[p])))
+                SAF_ULIGHT(D_INVCUBE, r.v[p] = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(a.v[p], a.v[p]), a.v[p])))
+                SAF_ULIGHT(D_RECIP, r.v[p] = __ddiv_rn(1.0, a.v[p]))
+                SAF_ULIGHT(D_SQRT, r.v[p] = __dsqrt_rn(a.v[p]))
+
+                SAF_UHEAVY(D_SIN, r.v[p] = sin(a.v[p]))
+                SAF_UHEAVY(D_COS, r.v[p] = cos(a.v[p]))
+                SAF_UHEAVY(D_EXP, r.v[p] = exp(a.v[p]))
+                SAF_UHEAVY(D_LN, r.v[p] = log(a.v[p]))
+                SAF_UHEAVY(D_RECIPEXPM1, r.v[p] = __ddiv_rn(1.0, expm1(a.v[p])))
+                SAF_UHEAVY(D_EXPSQR, r.v[p] = exp(__dmul_rn(a.v[p], a.v[p])))
+                SAF_UHEAVY(D_EXPSQRNEG, r.v[p] = exp(-__dmul_rn(a.v[p], a.v[p])))
+                SAF_UHEAVY(D_EXPNEG, r.v[p] = exp(-a.v[p]))
+                case X_UHEAVY + (D_SINCOS - D_FIRST_HEAVY_UNARY): {
+                    const uint2 h = fetch_word(pc++);
+                    any(fa, a);
                     Pt<P> cs;
                     SAF_FOR_P sincos(a.v[p], &r.v[p], &cs.v[p]);
-                    if ((fc >> INDEX_BITS) == KIND_S) slot_store<P>(my, stride, fc & INDEX_MASK, cs);
+                    if ((h.x & KIND_MASK) == KIND_S) RF::store(my, h.x & 0xffffu, cs);
                 } break;
-                case D_BUILTIN1: {
-                    const uint32_t fn = fb & INDEX_MASK;
-#pragma unroll 1
-                    for (int p = 0; p < P; ++p) r.v[p] = dm::builtin1(fn, a.v[p]);
+                case X_UHEAVY + (D_BUILTIN1 - D_FIRST_HEAVY_UNARY): {
+                    const uint2 h = fetch_word(pc++);
+                    any(fa, a);
+                    SAF_FOR_P r.v[p] = dm::builtin1(h.y, a.v[p]).v;
                 } break;
-                case D_BUILTIN3: {
-                    const uint32_t fn = fb & INDEX_MASK;
-#pragma unroll 1
-                    for (int p = 0; p < P; ++p) r.v[p] = dm::builtin3(fn, x0.v[p], x1.v[p], a.v[p]);
+                case X_UHEAVY + (D_BUILTIN3 - D_FIRST_HEAVY_UNARY): {
+                    const uint2 h = fetch_word(pc++);
+                    any(fa, a);
+                    SAF_FOR_P r.v[p] = dm::builtin3(h.y, x0.v[p], x1.v[p], a.v[p]).v;
                 } break;
-                case D_ADD: SAF_FOR_P r.v[p] = __dadd_rn(a.v[p], b.v[p]); break;
-                case D_SUB: SAF_FOR_P r.v[p] = __dsub_rn(a.v[p], b.v[p]); break;
-                case D_MUL: SAF_FOR_P r.v[p] = __dmul_rn(a.v[p], b.v[p]); break;
-                case D_DIV: SAF_FOR_P r.v[p] = __ddiv_rn(a.v[p], b.v[p]); break;
-                case D_POW: SAF_FOR_P r.v[p] = pow(a.v[p], b.v[p]); break;
-                case D_NEGMUL: SAF_FOR_P r.v[p] = -__dmul_rn(a.v[p], b.v[p]); break;
-                case D_POWI: {
-                    const int n = (int)b.v[0]; // K field, warp-uniform
-                    SAF_FOR_P r.v[p] = dm::powi(a.v[p], n);
+
+                SAF_BLIGHT(D_ADD, r.v[p] = __dadd_rn(a.v[p], b.v[p]))
+                SAF_BLIGHT(D_SUB, r.v[p] = __dsub_rn(a.v[p], b.v[p]))
+                SAF_BLIGHT(D_MUL, r.v[p] = __dmul_rn(a.v[p], b.v[p]))
+                SAF_BLIGHT(D_NEGMUL, r.v[p] = -__dmul_rn(a.v[p], b.v[p]))
+
+                SAF_BHEAVY(D_DIV, r.v[p] = __ddiv_rn(a.v[p], b.v[p]))
+                SAF_BHEAVY(D_POW, r.v[p] = pow(a.v[p], b.v[p]))
+                case X_BHEAVY + (D_POWI - D_FIRST_HEAVY_BINARY): {
+                    const uint2 h = fetch_word(pc++);
+                    any(fa, a);
+                    const int n = (int)h.y;
+                    SAF_FOR_P r.v[p] = dm::powi(a.v[p], n).v;
                 } break;
-                case D_BUILTIN2: {
-                    const uint32_t fn = fc & INDEX_MASK;
-#pragma unroll 1
-                    for (int p = 0; p < P; ++p) r.v[p] = dm::builtin2(fn, a.v[p], b.v[p]);
+                case X_BHEAVY + (D_BUILTIN2 - D_FIRST_HEAVY_BINARY): {
+                    const uint2 h = fetch_word(pc++);
+                    any(fa, a); any(fb, b);
+                    SAF_FOR_P r.v[p] = dm::builtin2(h.y, a.v[p], b.v[p]).v;
                 } break;
-                case D_BUILTIN4: {
-                    const uint32_t fn = fc & INDEX_MASK;
-#pragma unroll 1
-                    for (int p = 0; p < P; ++p) r.v[p] = dm::builtin4(fn, x0.v[p], x1.v[p], a.v[p], b.v[p]);
+                case X_BHEAVY + (D_BUILTIN4 - D_FIRST_HEAVY_BINARY): {
+                    const uint2 h = fetch_word(pc++);
+                    any(fa, a); any(fb, b);
+                    SAF_FOR_P r.v[p] = dm::builtin4(h.y, x0.v[p], x1.v[p], a.v[p], b.v[p]).v;
                 } break;
-                case D_ARG2:
-                    x0 = a;
-                    x1 = b;
+                case X_BHEAVY + (D_ARG2 - D_FIRST_HEAVY_BINARY):
+                    any(fa, x0);
+                    any(fb, x1);
                     continue; // stages operands only: ACC and slots untouched
-                case D_FMA: SAF_FOR_P r.v[p] = __fma_rn(a.v[p], b.v[p], c.v[p]); break;
-                case D_FMS: SAF_FOR_P r.v[p] = __fma_rn(a.v[p], b.v[p], -c.v[p]); break;
-                case D_FNMA: SAF_FOR_P r.v[p] = __fma_rn(-a.v[p], b.v[p], c.v[p]); break;
-                case D_FNMS: SAF_FOR_P r.v[p] = __fma_rn(-a.v[p], b.v[p], -c.v[p]); break;
+
+                SAF_TERN(D_FMA, r.v[p] = __fma_rn(a.v[p], b.v[p], c.v[p]))
+                SAF_TERN(D_FMS, r.v[p] = __fma_rn(a.v[p], b.v[p], -c.v[p]))
+                SAF_TERN(D_FNMA, r.v[p] = __fma_rn(-a.v[p], b.v[p], c.v[p]))
+                SAF_TERN(D_FNMS, r.v[p] = __fma_rn(-a.v[p], b.v[p], -c.v[p]))
                 default: SAF_FOR_P r.v[p] = dm::nan_(); break;
                 }
+                if (done) break;
                 acc = r;
-                if ((fd >> INDEX_BITS) == KIND_S) slot_store<P>(my, stride, fd & INDEX_MASK, r);
+                if ((fd & KIND_MASK) == KIND_S) RF::store(my, fd, r);
             }
 
             if (++it >= d.iters) break;
@@ -232,13 +284,13 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d,
                 if (s == 0xffffu) continue;
                 const uint32_t f = d.result_field[j];
                 Pt<P> v;
-                if ((f >> INDEX_BITS) == KIND_S) {
-                    slot_load<P>(my, stride, f & INDEX_MASK, v);
+                if ((f & KIND_MASK) == KIND_S) {
+                    RF::load(my, f, v);
                 } else {
-                    const double k = fetch_const(f & INDEX_MASK);
+                    const double k = konst(f);
                     SAF_FOR_P v.v[p] = k;
                 }
-                slot_store<P>(my, stride, s, v);
+                RF::store(my, s << KIND_BITS, v);
             }
         }
 
@@ -246,10 +298,10 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d,
         for (uint32_t k = 0; k < d.n_results; ++k) {
             const uint32_t f = d.result_field[k];
             Pt<P> v;
-            if ((f >> INDEX_BITS) == KIND_S) {
-                slot_load<P>(my, stride, f & INDEX_MASK, v);
+            if ((f & KIND_MASK) == KIND_S) {
+                RF::load(my, f, v);
             } else {
-                const double kv = fetch_const(f & INDEX_MASK);
+                const double kv = konst(f);
                 SAF_FOR_P v.v[p] = kv;
             }
             double *out = d.outs[k];
@@ -289,10 +341,10 @@ cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t s
 
 // ---- host side -------------------------------------------------------------------------------------
 
-template <int P, int WORDS>
+template <int P, int WORDS, bool CODE_IN_BLOB, bool K_IN_BLOB>
 static cudaError_t launch_one(const LaunchDesc &desc, const uint64_t *words, size_t n_words,
                               const LaunchShape &shape, cudaStream_t stream) {
-    auto kern = saf_interp_kernel<P, WORDS>;
+    auto kern = saf_interp_kernel<P, WORDS, CODE_IN_BLOB, K_IN_BLOB>;
     // opt in once per (instantiation, device) to the full dynamic shared-memory carve-out
     static bool configured[64] = {};
     int dev = 0;
@@ -306,8 +358,8 @@ static cudaError_t launch_one(const LaunchDesc &desc, const uint64_t *words, siz
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    ConstBlob<(WORDS > 0 ? WORDS : 1)> blob;
-    if (WORDS > 0) {
+    ConstBlob<WORDS> blob;
+    if (CODE_IN_BLOB) {
         for (size_t i = 0; i < n_words; ++i) blob.w[i] = words[i];
     }
     kern<<<shape.grid, shape.block, shape.smem_bytes, stream>>>(desc, blob);
@@ -315,18 +367,20 @@ static cudaError_t launch_one(const LaunchDesc &desc, const uint64_t *words, siz
 }
 
 template <int P>
-static cudaError_t launch_p(const LaunchDesc &desc, const uint64_t *words, size_t n_words,
+static cudaError_t launch_p(const LaunchDesc &desc, const uint64_t *words, size_t n_words, bool consts_in_blob,
                             const LaunchShape &shape, cudaStream_t stream) {
-    if (words == nullptr || n_words > (size_t)BLOB_LARGE) return launch_one<P, 0>(desc, nullptr, 0, shape, stream);
-    if (n_words <= (size_t)BLOB_SMALL) return launch_one<P, BLOB_SMALL>(desc, words, n_words, shape, stream);
-    if (n_words <= (size_t)BLOB_MEDIUM) return launch_one<P, BLOB_MEDIUM>(desc, words, n_words, shape, stream);
-    return launch_one<P, BLOB_LARGE>(desc, words, n_words, shape, stream);
+    if (words == nullptr || n_words > (size_t)BLOB_LARGE)
+        return launch_one<P, 1, false, false>(desc, nullptr, 0, shape, stream);
+    if (!consts_in_blob) return launch_one<P, BLOB_LARGE, true, false>(desc, words, n_words, shape, stream);
+    if (n_words <= (size_t)BLOB_SMALL) return launch_one<P, BLOB_SMALL, true, true>(desc, words, n_words, shape, stream);
+    return launch_one<P, BLOB_LARGE, true, true>(desc, words, n_words, shape, stream);
 }
 
 cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *blob_words, size_t n_blob_words,
-                               const LaunchShape &shape, cudaStream_t stream) {
-    if (shape.points_per_thread == 2) return launch_p<2>(desc, blob_words, n_blob_words, shape, stream);
-    return launch_p<1>(desc, blob_words, n_blob_words, shape, stream);
+                               bool consts_in_blob, const LaunchShape &shape, cudaStream_t stream) {
+    if (shape.points_per_thread == 2)
+        return launch_p<2>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
+    return launch_p<1>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
 }
 
 cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
@@ -337,32 +391,22 @@ cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_poin
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
     const size_t smem_sm = (size_t)smem_optin; // per-block opt-in limit ~= per-SM capacity minus 1 KB
+    const int block = BLOCK_THREADS;
+    auto bytes = [&](int p) { return (size_t)n_slots * (size_t)block * (size_t)p * 8; };
 
-    // Two points per thread once there is enough work to keep every SM busy with 2-point threads.
-    int P = (aligned16 && n_points >= (unsigned long long)sms * 2048ull) ? 2 : 1;
-    int block = 256;
-    auto bytes = [&](int blk, int p) { return (size_t)n_slots * (size_t)blk * (size_t)p * 8; };
-    // keep at least two resident blocks per SM when the register file of the program allows it
-    while (block > 32 && bytes(block, P) * 2 > smem_sm) {
-        if (P == 2 && block <= 128) P = 1; else block /= 2;
-    }
-    if (bytes(block, P) > smem_sm) {
-        if (P == 2) P = 1;
-        while (block > 32 && bytes(block, P) > smem_sm) block /= 2;
-    }
-    if (bytes(block, P) > smem_sm) return cudaErrorInvalidConfiguration;
-    // small problems: shrink the block so that every SM gets work
-    while (block > 64 && n_points < (unsigned long long)sms * (unsigned long long)block * (unsigned long long)P)
-        block /= 2;
+    // Two points per thread when there is enough work to fill the chip with 2-point threads and the
+    // register file of two points still leaves room for at least two resident blocks per SM.
+    int P = (aligned16 && n_points >= (unsigned long long)sms * 4ull * block * 2ull) ? 2 : 1;
+    if (P == 2 && bytes(2) * 2 > smem_sm) P = 1;
+    if (bytes(P) > smem_sm) return cudaErrorInvalidConfiguration;
 
-    const size_t smem = bytes(block, P);
-    size_t blocks_by_smem = smem ? (smem_sm + 1024) / (smem + 1024) : 32;
-    if (blocks_by_smem < 1) blocks_by_smem = 1;
-    size_t blocks_by_threads = 2048 / (size_t)block;
-    size_t resident = blocks_by_smem < blocks_by_threads ? blocks_by_smem : blocks_by_threads;
-    if (resident > 32) resident = 32;
+    const size_t smem = bytes(P);
+    size_t resident = 4; // __launch_bounds__(128, 4): 128 registers x 512 threads
+    size_t by_smem = smem ? (smem_sm + 1024) / (smem + 1024) : resident;
+    if (by_smem < resident) resident = by_smem;
+    if (resident < 1) resident = 1;
     const unsigned long long tile = (unsigned long long)block * P;
-    unsigned long long n_tiles = (n_points + tile - 1) / tile;
+    const unsigned long long n_tiles = (n_points + tile - 1) / tile;
     unsigned long long grid = (unsigned long long)sms * resident;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;

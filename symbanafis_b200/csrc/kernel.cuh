@@ -36,21 +36,21 @@ struct ConstBlob {
 
 // Blob size classes (8-byte words).  With LaunchDesc (< 1 KB) the largest stays under the 32764-byte
 // kernel parameter limit of CUDA 12.1+.
-constexpr int BLOB_SMALL = 192;
-constexpr int BLOB_MEDIUM = 1024;
+constexpr int BLOB_SMALL = 448;
 constexpr int BLOB_LARGE = 3840;
 
 struct LaunchShape {
     int points_per_thread; // 1 or 2
-    int block;             // threads per block
+    int block;             // threads per block (always BLOCK_THREADS)
     int grid;
     size_t smem_bytes;
 };
 
-// Launches the interpreter.  `blob` holds n_code + n_consts words when they fit BLOB_LARGE, otherwise
-// it is ignored and desc.code_global / desc.consts_global are read.
+// Launches the interpreter.  `blob_words` holds the code words (followed by the constants when
+// `consts_in_blob`) if they fit BLOB_LARGE; otherwise pass nullptr and the kernel reads
+// desc.code_global / desc.consts_global.
 cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *blob_words, size_t n_blob_words,
-                               const LaunchShape &shape, cudaStream_t stream);
+                               bool consts_in_blob, const LaunchShape &shape, cudaStream_t stream);
 
 // Picks points-per-thread / block / grid for a program with n_slots live values on `device`.
 cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,

@@ -734,6 +734,8 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
         int32_t cosval;   // for SINCOS
     };
     std::vector<Emit> E;
+    constexpr int32_t SRC_LOADK = -2; // operand comes from ACC, loaded by a D_LOADK emitted just before
+    auto is_const = [&](int32_t v) { return v >= 0 && g.nodes[v].op == V_CONST; };
     for (int32_t i : order) {
         const Node &n = g.nodes[i];
         if (n.op == D_BUILTIN3) {
@@ -746,6 +748,17 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
             auto it = g.cos_of.find(i);
             int32_t cv = (it != g.cos_of.end() && live[it->second]) ? it->second : -1;
             E.push_back({i, n.op, {n.a, -1, -1}, cv});
+        } else if (n.op == D_POWI) {
+            E.push_back({i, n.op, {n.a, -1, -1}, -1}); // the exponent travels as an immediate
+        } else if (n.op >= D_FIRST_LIGHT_UNARY && n.op < D_FIRST_LIGHT_UNARY + D_N_LIGHT_UNARY && is_const(n.a)) {
+            // the kind-specialised light opcodes have no constant-operand form for these shapes:
+            // materialise the constant in ACC first
+            E.push_back({-1, (uint8_t)D_LOADK, {n.a, -1, -1}, -1});
+            E.push_back({i, n.op, {SRC_LOADK, -1, -1}, -1});
+        } else if (n.op >= D_FIRST_LIGHT_BINARY && n.op < D_FIRST_LIGHT_BINARY + D_N_LIGHT_BINARY &&
+                   is_const(n.a) && is_const(n.b)) {
+            E.push_back({-1, (uint8_t)D_LOADK, {n.a, -1, -1}, -1});
+            E.push_back({i, n.op, {SRC_LOADK, n.b, -1}, -1});
         } else {
             E.push_back({i, n.op, {n.a, n.b, n.c}, -1});
         }
@@ -814,21 +827,23 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
             kidx[bits] = i;
         } else
             i = it->second;
-        return make_field(KIND_K, i & INDEX_MASK);
+        return make_field(KIND_K, i & (MAX_INDEX - 1));
     };
 
     out.code.clear();
-    out.code.reserve(NE + 1);
+    out.code.reserve(2 * (size_t)NE + 2);
     bool overflow = false;
+    auto sfield = [&](int32_t sl) { return make_field(KIND_S, (uint32_t)sl & (MAX_INDEX - 1)); };
     for (int32_t j = 0; j < NE; ++j) {
         const Emit &e = E[j];
         uint32_t f[3] = {FIELD_NONE, FIELD_NONE, FIELD_NONE};
         for (int k = 0; k < 3; ++k) {
             int32_t s = e.src[k];
+            if (s == SRC_LOADK) { f[k] = FIELD_ACC; continue; }
             if (s < 0) continue;
             if (g.nodes[s].op == V_CONST) f[k] = kfield(s);
             else if (j > 0 && E[j - 1].node == s && is_instr_value(s)) f[k] = FIELD_ACC;
-            else f[k] = make_field(KIND_S, (uint32_t)slot[s] & INDEX_MASK);
+            else f[k] = sfield(slot[s]);
         }
         // sources dying here release their slots before the destination is placed: the kernel
         // reads every source before it writes (same contract as macros.rs, fusion.rs:742-753)
@@ -836,36 +851,54 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
         uint32_t fd = FIELD_ACC;
         if (e.node >= 0 && needs_slot[e.node]) {
             slot[e.node] = alloc();
-            fd = make_field(KIND_S, (uint32_t)slot[e.node] & INDEX_MASK);
+            fd = sfield(slot[e.node]);
         } else if (e.node < 0) {
             fd = FIELD_NONE;
         }
         const Node *n = e.node >= 0 ? &g.nodes[e.node] : nullptr;
-        uint32_t fa = f[0], fb = f[1], fc = f[2];
-        switch (e.op) {
-        case D_SINCOS:
-            fc = FIELD_NONE;
-            if (e.cosval >= 0 && needs_slot[e.cosval]) {
-                slot[e.cosval] = alloc();
-                fc = make_field(KIND_S, (uint32_t)slot[e.cosval] & INDEX_MASK);
+        uint32_t fa = f[0], fb = f[1], fc = f[2], imm = 0;
+        const uint32_t op = e.op;
+        uint32_t xop;
+        if (op == D_LOADK) {
+            xop = X_LOADK;
+        } else if (op >= D_FIRST_LIGHT_UNARY && op < D_FIRST_LIGHT_UNARY + D_N_LIGHT_UNARY) {
+            xop = X_ULIGHT + 2 * (op - D_FIRST_LIGHT_UNARY) + (field_kind(fa) == KIND_ACC ? 1 : 0);
+        } else if (op >= D_FIRST_HEAVY_UNARY && op < D_FIRST_HEAVY_UNARY + D_N_HEAVY_UNARY) {
+            xop = X_UHEAVY + (op - D_FIRST_HEAVY_UNARY);
+            if (op == D_SINCOS) {
+                fc = FIELD_NONE;
+                if (e.cosval >= 0 && needs_slot[e.cosval]) {
+                    slot[e.cosval] = alloc();
+                    fc = sfield(slot[e.cosval]);
+                }
+            } else if (op == D_BUILTIN1 || op == D_BUILTIN3) {
+                imm = n->imm;
             }
-            break;
-        case D_BUILTIN1:
-        case D_BUILTIN3: fb = make_field(KIND_NONE, n->imm & INDEX_MASK); break;
-        case D_BUILTIN2:
-        case D_BUILTIN4: fc = make_field(KIND_NONE, n->imm & INDEX_MASK); break;
-        default: break;
+        } else if (op >= D_FIRST_LIGHT_BINARY && op < D_FIRST_LIGHT_BINARY + D_N_LIGHT_BINARY) {
+            xop = X_BLIGHT + 9 * (op - D_FIRST_LIGHT_BINARY) + 3 * field_kind(fa) + field_kind(fb);
+        } else if (op >= D_FIRST_HEAVY_BINARY && op < D_FIRST_HEAVY_BINARY + D_N_HEAVY_BINARY) {
+            xop = X_BHEAVY + (op - D_FIRST_HEAVY_BINARY);
+            if (op == D_POWI) {
+                double nd;
+                std::memcpy(&nd, &g.nodes[n->b].bits, 8);
+                imm = (uint32_t)(int32_t)nd;
+            } else if (op == D_BUILTIN2 || op == D_BUILTIN4) {
+                imm = n->imm;
+            }
+        } else {
+            xop = X_TERN + (op - D_FIRST_TERNARY);
         }
-        // a cos half that is live but only ever read... is always read from its slot (never ACC)
-        out.code.push_back(make_word(e.op, fd, fa, fb, fc));
+        out.code.push_back(make_lo(xop, fd, fa, fb));
+        if (xop_has_hi(xop)) out.code.push_back(make_hi(fc, imm));
+        ++out.n_dev_instructions;
         if (n_slots > MAX_INDEX || out.consts.size() > MAX_INDEX) overflow = true;
     }
-    out.code.push_back(make_word(D_END, FIELD_NONE, FIELD_NONE, FIELD_NONE, FIELD_NONE));
+    out.code.push_back(make_lo(X_END, FIELD_NONE, FIELD_NONE, FIELD_NONE));
 
     out.result_field.clear();
     for (int32_t r : results) {
         if (g.nodes[r].op == V_CONST) out.result_field.push_back(kfield(r));
-        else out.result_field.push_back(make_field(KIND_S, (uint32_t)slot[r] & INDEX_MASK));
+        else out.result_field.push_back(make_field(KIND_S, (uint32_t)slot[r] & (MAX_INDEX - 1)));
     }
     if (n_slots > MAX_INDEX || out.consts.size() > MAX_INDEX || overflow) {
         std::ostringstream os;
@@ -916,24 +949,25 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
 
 // ------------------------------------------------------------------------------------------------
 static const char *DEV_NAMES[D_OPCOUNT] = {
-    "end", "copy", "neg", "square", "cube", "pow4", "pow3_2", "invpow3_2", "invsqrt", "invsquare",
-    "invcube", "recip", "sin", "cos", "exp", "ln", "sqrt", "recipexpm1", "expsqr", "expsqrneg",
-    "expneg", "sincos", "builtin1", "builtin3", "add", "sub", "mul", "div", "pow", "negmul", "powi",
-    "builtin2", "builtin4", "arg2", "fma", "fms", "fnma", "fnms"};
+    "end", "loadk", "copy", "neg", "square", "cube", "pow4", "pow3_2", "invpow3_2", "invsqrt", "invsquare",
+    "invcube", "recip", "sqrt", "sin", "cos", "exp", "ln", "recipexpm1", "expsqr", "expsqrneg", "expneg",
+    "sincos", "builtin1", "builtin3", "add", "sub", "mul", "negmul", "div", "pow", "powi", "builtin2",
+    "builtin4", "arg2", "fma", "fms", "fnma", "fnms"};
 
 static void fmt_field(std::ostringstream &os, uint32_t f) {
-    uint32_t kind = f >> INDEX_BITS, idx = f & INDEX_MASK;
+    uint32_t kind = field_kind(f), idx = field_index(f);
     if (kind == KIND_S) os << "S" << idx;
     else if (kind == KIND_K) os << "K" << idx;
     else if (kind == KIND_ACC) os << "ACC";
-    else os << "#" << idx;
+    else os << "-";
 }
 
 std::string disassemble(const DeviceProgram &p) {
     std::ostringstream os;
+    const size_t n_instr = p.n_dev_instructions;
     os << "=== Device program ===\n";
     os << "params " << p.param_count << ", results " << p.result_field.size() << ", slots " << p.n_slots
-       << ", constants " << p.consts.size() << ", instructions " << (p.code.size() - 1)
+       << ", constants " << p.consts.size() << ", instructions " << n_instr
        << ", acc-forwards " << p.n_acc_forwards << ", fp64 slots/point " << p.fp64_slots << "\n";
     for (size_t j = 0; j < p.param_slot.size(); ++j) {
         os << "  param " << j << " -> ";
@@ -944,22 +978,27 @@ std::string disassemble(const DeviceProgram &p) {
         os.precision(17);
         os << "  K" << i << " = " << p.consts[i] << "\n";
     }
-    for (size_t i = 0; i + 1 < p.code.size(); ++i) {
-        uint64_t w = p.code[i];
-        uint32_t op = w & 0xff, d = (w >> 8) & FIELD_MASK, a = (w >> 22) & FIELD_MASK,
-                 b = (w >> 36) & FIELD_MASK, c = (w >> 50) & FIELD_MASK;
+    for (size_t i = 0, pc = 0; i < n_instr; ++i) {
+        const uint64_t lo = p.code[pc++];
+        const uint64_t hi = xop_has_hi((uint32_t)(lo & 0xff)) ? p.code[pc++] : make_hi(FIELD_NONE, 0);
+        const uint32_t x = lo & 0xff, d = (lo >> 16) & 0xffff, a = (lo >> 32) & 0xffff, b = (lo >> 48) & 0xffff,
+                       c = hi & 0xffff, imm = (uint32_t)(hi >> 32);
+        uint32_t op, ka, kb;
+        decode_xop(x, &op, &ka, &kb);
         os << "  [" << i << "] ";
         fmt_field(os, d);
         os << " = " << (op < D_OPCOUNT ? DEV_NAMES[op] : "?") << "(";
         fmt_field(os, a);
-        if (op >= D_FIRST_BINARY || (b >> INDEX_BITS) != KIND_NONE || (b & INDEX_MASK)) {
+        if (field_kind(b) != KIND_NONE) {
             os << ", ";
             fmt_field(os, b);
         }
-        if (op >= D_FIRST_TERNARY || (c >> INDEX_BITS) != KIND_NONE || (c & INDEX_MASK)) {
-            os << ", ";
+        if (field_kind(c) != KIND_NONE) {
+            os << (op == D_SINCOS ? "; cos -> " : ", ");
             fmt_field(os, c);
         }
+        if (op == D_POWI) os << ", n=" << (int32_t)imm;
+        if (op == D_BUILTIN1 || op == D_BUILTIN2 || op == D_BUILTIN3 || op == D_BUILTIN4) os << ", fn=" << imm;
         os << ")\n";
     }
     for (size_t k = 0; k < p.result_field.size(); ++k) {

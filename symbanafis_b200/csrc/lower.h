@@ -17,7 +17,7 @@ struct RefProgram {
 };
 
 struct DeviceProgram {
-    std::vector<uint64_t> code;         // device words, D_END terminated
+    std::vector<uint64_t> code;         // device word stream (lo [+ hi] per instruction), X_END terminated
     std::vector<double> consts;         // K table
     uint32_t n_slots = 0;               // S slots per point
     uint32_t param_count = 0;
@@ -25,6 +25,7 @@ struct DeviceProgram {
     std::vector<uint32_t> result_field; // S or K field of each result
     // statistics
     uint32_t n_ref_instructions = 0;
+    uint32_t n_dev_instructions = 0;    // excluding the end marker
     uint32_t n_acc_forwards = 0;
     uint32_t quirk_flags = 0;
     double fp64_slots = 0.0;

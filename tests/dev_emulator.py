@@ -17,17 +17,42 @@ import numpy as np
 from oracle import OracleProgram
 from symbanafis_b200.isa import assemble
 
-# device opcode numbering: symbanafis_b200/csrc/saf_isa.h (enum DevOp)
+# device encoding: symbanafis_b200/csrc/saf_isa.h (enum DevOp, X_* opcode layout, field = index << 2 | kind)
 DEV_OPS = [
-    "end", "copy", "neg", "square", "cube", "pow4", "pow3_2", "invpow3_2", "invsqrt", "invsquare",
-    "invcube", "recip", "sin", "cos", "exp", "ln", "sqrt", "recipexpm1", "expsqr", "expsqrneg",
-    "expneg", "sincos", "builtin1", "builtin3", "add", "sub", "mul", "div", "pow", "negmul", "powi",
-    "builtin2", "builtin4", "arg2", "fma", "fms", "fnma", "fnms",
+    "end", "loadk", "copy", "neg", "square", "cube", "pow4", "pow3_2", "invpow3_2", "invsqrt", "invsquare",
+    "invcube", "recip", "sqrt", "sin", "cos", "exp", "ln", "recipexpm1", "expsqr", "expsqrneg", "expneg",
+    "sincos", "builtin1", "builtin3", "add", "sub", "mul", "negmul", "div", "pow", "powi", "builtin2",
+    "builtin4", "arg2", "fma", "fms", "fnma", "fnms",
 ]
 D = {n: i for i, n in enumerate(DEV_OPS)}
-FIRST_BINARY = D["add"]
-FIRST_TERNARY = D["fma"]
 KIND_S, KIND_K, KIND_ACC, KIND_NONE = 0, 1, 2, 3
+N_LIGHT_UNARY, N_HEAVY_UNARY, N_LIGHT_BINARY, N_HEAVY_BINARY = 12, 11, 4, 6
+X_END, X_LOADK, X_ULIGHT = 0, 1, 2
+X_UHEAVY = X_ULIGHT + 2 * N_LIGHT_UNARY
+X_BLIGHT = X_UHEAVY + N_HEAVY_UNARY
+X_BHEAVY = X_BLIGHT + 9 * N_LIGHT_BINARY
+X_TERN = X_BHEAVY + N_HEAVY_BINARY
+HAS_HI = {"sincos", "builtin1", "builtin2", "builtin3", "builtin4", "powi", "fma", "fms", "fnma", "fnms"}
+
+
+def decode_xop(x: int):
+    """encoded opcode -> (name, kind(a) or None, kind(b) or None)"""
+    if x == X_END:
+        return "end", None, None
+    if x == X_LOADK:
+        return "loadk", KIND_K, None
+    if x < X_UHEAVY:
+        r = x - X_ULIGHT
+        return DEV_OPS[D["copy"] + r // 2], (KIND_ACC if r & 1 else KIND_S), None
+    if x < X_BLIGHT:
+        return DEV_OPS[D["sin"] + x - X_UHEAVY], None, None
+    if x < X_BHEAVY:
+        r = x - X_BLIGHT
+        return DEV_OPS[D["add"] + r // 9], (r % 9) // 3, r % 3
+    if x < X_TERN:
+        return DEV_OPS[D["div"] + x - X_BHEAVY], None, None
+    return DEV_OPS[D["fma"] + x - X_TERN], None, None
+
 
 _UNARY_REF = {
     "neg": "Neg", "square": "Square", "cube": "Cube", "pow4": "Pow4", "pow3_2": "Pow3_2",
@@ -54,82 +79,90 @@ def _leaf(instr: tuple, n_in: int, n_out: int = 1) -> OracleProgram:
 def run_device_program(code: Sequence[int], consts: np.ndarray, param_slot: Sequence[int],
                        result_field: Sequence[int], cols: Sequence[np.ndarray], n_points: int,
                        iters: int = 1) -> List[np.ndarray]:
-    n_slots = 1 + max([int(s) for s in param_slot if s != 0xFFFF] +
-                      [((int(w) >> sh) & 0xFFF) for w in code for sh in (8, 22, 36, 50)
-                       if ((int(w) >> (sh + 12)) & 3) == KIND_S] + [0])
-    S = [np.zeros(n_points) for _ in range(n_slots)]
+    code = [int(w) for w in code]
+    S: Dict[int, np.ndarray] = {}
     for j, s in enumerate(param_slot):
         if s == 0xFFFF:
             continue
         if j < len(cols):
             c = np.asarray(cols[j], dtype=np.float64)
             idx = np.minimum(np.arange(n_points), len(c) - 1)
-            S[s] = c[idx].copy()
+            S[int(s)] = c[idx].copy()
         else:
-            S[s] = np.zeros(n_points)
+            S[int(s)] = np.zeros(n_points)
     acc = np.zeros(n_points)
     x0 = x1 = np.zeros(n_points)
 
-    def operand(f: int) -> np.ndarray:
-        kind, idx = f >> 12, f & 0xFFF
+    def operand(f: int, forced_kind=None) -> np.ndarray:
+        kind, idx = f & 3, f >> 2
+        if forced_kind is not None:
+            assert kind == forced_kind, "opcode specialisation disagrees with the operand field"
         if kind == KIND_S:
-            return S[idx]
+            return S[idx]  # KeyError = read of a slot that was never written
         if kind == KIND_K:
             return np.full(n_points, consts[idx])
         assert kind == KIND_ACC, "operand field of kind none was read"
         return acc
 
     def result_value(f: int) -> np.ndarray:
-        kind, idx = f >> 12, f & 0xFFF
+        kind, idx = f & 3, f >> 2
         return S[idx].copy() if kind == KIND_S else np.full(n_points, consts[idx])
 
     for it in range(iters):
-        for w in code:
-            w = int(w)
-            op = w & 0xFF
-            if op == D["end"]:
+        pc = 0
+        while True:
+            lo = code[pc]
+            pc += 1
+            name, ka, kb = decode_xop(lo & 0xFF)
+            if name == "end":
                 break
-            fd, fa, fb, fc = (w >> 8) & 0x3FFF, (w >> 22) & 0x3FFF, (w >> 36) & 0x3FFF, (w >> 50) & 0x3FFF
-            name = DEV_OPS[op]
-            a = operand(fa)
-            b = operand(fb) if op >= FIRST_BINARY else None
-            c = operand(fc) if op >= FIRST_TERNARY else None
-            if name == "copy":
-                r = a.copy()
+            fd, fa, fb = (lo >> 16) & 0xFFFF, (lo >> 32) & 0xFFFF, (lo >> 48) & 0xFFFF
+            fc, imm = KIND_NONE, 0
+            if name in HAS_HI:
+                hi = code[pc]
+                pc += 1
+                fc, imm = hi & 0xFFFF, (hi >> 32) & 0xFFFFFFFF
+            if name == "loadk":
+                r = operand(fa, KIND_K).copy()
+            elif name == "copy":
+                r = operand(fa, ka).copy()
             elif name in _UNARY_REF:
-                r = _leaf((_UNARY_REF[name], 1, 0), 1).eval_batch([a], n_points)[0]
+                r = _leaf((_UNARY_REF[name], 1, 0), 1).eval_batch([operand(fa, ka)], n_points)[0]
             elif name == "expneg":
-                r = _leaf(("Builtin1", 1, "exp_neg", 0), 1).eval_batch([a], n_points)[0]
+                r = _leaf(("Builtin1", 1, "exp_neg", 0), 1).eval_batch([operand(fa)], n_points)[0]
             elif name == "sincos":
-                s_, c_ = _leaf(("SinCos", 1, 2, 0), 1, 2).eval_batch([a], n_points)
+                s_, c_ = _leaf(("SinCos", 1, 2, 0), 1, 2).eval_batch([operand(fa)], n_points)
                 r = s_
-                if (fc >> 12) == KIND_S:
-                    S[fc & 0xFFF] = c_
+                if (fc & 3) == KIND_S:
+                    S[fc >> 2] = c_
             elif name == "builtin1":
-                r = _leaf(("Builtin1", 1, fb & 0xFFF, 0), 1).eval_batch([a], n_points)[0]
+                r = _leaf(("Builtin1", 1, imm, 0), 1).eval_batch([operand(fa)], n_points)[0]
             elif name == "builtin3":
-                r = _leaf(("Builtin3", 3, fb & 0xFFF, 0, 1, 2), 3).eval_batch([x0, x1, a], n_points)[0]
+                r = _leaf(("Builtin3", 3, imm, 0, 1, 2), 3).eval_batch([x0, x1, operand(fa)], n_points)[0]
             elif name in _BINARY_REF:
+                a, b = operand(fa, ka), operand(fb, kb)
                 r = _leaf((_BINARY_REF[name], 2, 0, 1), 2).eval_batch([a, b], n_points)[0]
             elif name == "powi":
-                n = int(b[0])
-                r = _leaf(("Powi", 1, 0, n), 1).eval_batch([a], n_points)[0]
+                n = imm - (1 << 32) if imm >= (1 << 31) else imm
+                r = _leaf(("Powi", 1, 0, n), 1).eval_batch([operand(fa)], n_points)[0]
             elif name == "builtin2":
-                r = _leaf(("Builtin2", 2, fc & 0xFFF, 0, 1), 2).eval_batch([a, b], n_points)[0]
+                r = _leaf(("Builtin2", 2, imm, 0, 1), 2).eval_batch([operand(fa), operand(fb)], n_points)[0]
             elif name == "builtin4":
-                r = _leaf(("Builtin4", 4, fc & 0xFFF, 0, 1, 2, 3), 4).eval_batch([x0, x1, a, b], n_points)[0]
+                r = _leaf(("Builtin4", 4, imm, 0, 1, 2, 3), 4).eval_batch([x0, x1, operand(fa), operand(fb)],
+                                                                          n_points)[0]
             elif name == "arg2":
-                x0, x1 = a.copy(), b.copy()
+                x0, x1 = operand(fa).copy(), operand(fb).copy()
                 continue
             elif name in _TERNARY_REF:
+                a, b, c = operand(fa), operand(fb), operand(fc)
                 r = _leaf((_TERNARY_REF[name], 3, 0, 1, 2), 3).eval_batch([a, b, c], n_points)[0]
             else:
-                raise AssertionError(f"unknown device opcode {op}")
+                raise AssertionError(f"unknown device opcode {name}")
             acc = r
-            if (fd >> 12) == KIND_S:
-                S[fd & 0xFFF] = r.copy()
+            if (fd & 3) == KIND_S:
+                S[fd >> 2] = r.copy()
         if it + 1 < iters:
             for j, s in enumerate(param_slot):  # sequential, exactly like the kernel's feedback loop
                 if s != 0xFFFF:
-                    S[s] = result_value(int(result_field[j]))
+                    S[int(s)] = result_value(int(result_field[j]))
     return [result_value(int(f)) for f in result_field]

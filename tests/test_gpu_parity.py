@@ -211,7 +211,11 @@ def test_builtin2(fn):
     prog = single_op("Builtin2", 2, FNOP[fn], 0, 1, n_in=2)
     ref = OracleProgram.from_program(prog).eval_batch([a, b], a.size)[0]
     got = gpu_eval(prog, [a, b], a.size)[0]
-    rtol = 1e-9 if fn in ("bessel_j", "bessel_y", "beta", "zeta_deriv") else 2e-11
+    rtol = 1e-9 if fn in ("bessel_j", "bessel_y", "beta") else 2e-11
+    if fn == "zeta_deriv":
+        # below s = 1 the reference differentiates by finite differences with h = 1e-7 (zeta.rs:276-302):
+        # a 1-ulp difference in pow/sin/gamma is amplified by 1/(2h) = 5e6 by construction
+        rtol = 1e-7
     assert_close(got, ref, rtol=rtol, atol=1e-12, what=fn)
 
 

@@ -19,14 +19,21 @@ def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
 
 
 def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
-    """Distance in units in the last place; 0 for NaN/NaN and equal infinities, inf on class mismatch."""
+    """Distance in units in the last place; 0 for NaN/NaN and equal infinities, inf on class mismatch.
+    Computed in exact integer arithmetic (a float64 cannot hold the difference of two 63-bit keys)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
-    ia = a.view(np.int64).copy()
-    ib = b.view(np.int64).copy()
-    ia = np.where(ia < 0, np.int64(-(2 ** 63)) - ia, ia)
-    ib = np.where(ib < 0, np.int64(-(2 ** 63)) - ib, ib)
-    d = np.abs(ia.astype(np.float64) - ib.astype(np.float64))
+
+    def ordered(x):  # monotone map float64 -> int64 (two's complement ordering, -0.0 == +0.0)
+        i = x.view(np.int64)
+        return np.where(i < 0, np.int64(-(2 ** 63)) - i, i)
+
+    ia, ib = ordered(a), ordered(b)
+    same_sign = (ia < 0) == (ib < 0)
+    with np.errstate(over="ignore"):
+        d_int = np.abs(ia - ib)                      # exact when both keys have the same sign
+    d_mixed = np.abs(ia.astype(np.float64)) + np.abs(ib.astype(np.float64))  # huge anyway
+    d = np.where(same_sign, d_int.astype(np.float64), d_mixed)
     both_nan = np.isnan(a) & np.isnan(b)
     mismatch = np.isnan(a) ^ np.isnan(b)
     d = np.where(both_nan, 0.0, d)
