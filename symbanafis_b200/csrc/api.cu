@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -240,7 +241,11 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
         d.consts_global = c.consts;
     }
     LaunchShape shape;
-    cudaError_t e = choose_shape(device, dp.n_slots, n_points, aligned, &shape);
+    static const int forced_ppt = []() {
+        const char *v = getenv("SAF_POINTS_PER_THREAD"); // tuning knob, see DESIGN.md
+        return v ? atoi(v) : 0;
+    }();
+    cudaError_t e = choose_shape(device, dp.n_slots, n_points, aligned, forced_ppt, &shape);
     if (e == cudaErrorInvalidConfiguration)
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_shape");

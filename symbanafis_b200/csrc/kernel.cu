@@ -1,23 +1,26 @@
 // kernel.cu -- the sm_100a interpreter kernel for SymbAnaFis device programs.
 //
-// One thread evaluates P points (P = 1 or 2), 128 threads per block.  Every lane of every warp runs
+// One thread evaluates P points (P = 1, 2 or 4), 128 threads per block.  Every lane of every warp runs
 // the SAME device program on different points, so the program counter, the fetched instruction word
-// and the opcode jump are warp-uniform: there is no divergence in the dispatch, only inside the
+// and the opcode branch are warp-uniform: there is no divergence in the dispatch, only inside the
 // data-dependent loops of a few special functions.
 //
 //   program words + constants : kernel parameter space = constant bank (ConstBlob), read through the
 //                               constant cache with uniform addresses; global-memory fallback
 //                               (read-only path) for programs that do not fit
-//   live values ("registers")  : shared memory laid out [slot][thread] as f64 (P=1) or f64x2 (P=2):
-//                               consecutive lanes touch consecutive 8/16-byte words -> conflict free;
+//   live values ("registers")  : shared memory laid out [slot][pair][thread] as f64x2 (f64 for P=1):
+//                               consecutive lanes touch consecutive 16-byte words -> conflict free;
 //                               the slot stride is a compile-time constant (fixed block size)
 //   accumulator                : the result of the previous instruction stays in real registers; the
 //                               lowering (lower.cpp) routes single-use values through it so they
 //                               never touch shared memory
 //   dispatch                   : one dense switch over opcodes that are specialised by operand kind
-//                               for the cheap operations (no per-operand branches in their handlers)
-//   columns                    : struct-of-arrays f64, one coalesced 128-bit (P=2) or 64-bit load per
-//                               column per thread, streaming cache hints; results likewise
+//                               for the cheap operations (no per-operand branches in their handlers);
+//                               P points per thread amortise it
+//   hot transcendentals        : issue-lean sin/cos/sincos/exp (leanmath.cuh), everything else from
+//                               the CUDA math library / devmath.cuh
+//   columns                    : struct-of-arrays f64, coalesced 128-bit loads/stores (64-bit for
+//                               P=1), streaming cache hints
 //
 // Arithmetic handlers use the explicit-rounding intrinsics (__dadd_rn, __dmul_rn, __fma_rn, ...) so
 // that nvcc can never contract a Mul followed by an Add: the reference distinguishes Mul;Add from
@@ -28,6 +31,7 @@
 #include <cstdio>
 
 #include "devmath.cuh"
+#include "leanmath.cuh"
 
 namespace saf {
 
@@ -53,28 +57,34 @@ __device__ __forceinline__ void st_stream2(double *p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
-// Shared-memory register file.  `my` points at this thread's element of slot 0; slot i lives
-// SLOT_BYTES further.  A field is index << 2 | kind, so (field & ~3) * (SLOT_BYTES / 4) is the byte
-// offset of an S field: one LOP3 + one IMAD.
+// Shared-memory register file.  For P >= 2 a thread's points are stored as P/2 pairs; pair g of slot i
+// lives at  i * SLOT_BYTES + g * PAIR_BYTES + tid * 16.  A field is index << 2 | kind, so
+// (field & ~3) * (SLOT_BYTES / 4) is the byte offset of an S field: one LOP3 + one IMAD.
 template <int P>
 struct Rf {
     static constexpr uint32_t SLOT_BYTES = BLOCK_THREADS * P * 8;
+    static constexpr uint32_t PAIR_BYTES = BLOCK_THREADS * 16;
     __device__ __forceinline__ static void load(const char *my, uint32_t field, Pt<P> &o) {
         const char *p = my + (field & 0xfffcu) * (SLOT_BYTES / 4);
-        if constexpr (P == 2) {
-            double2 t = *reinterpret_cast<const double2 *>(p);
-            o.v[0] = t.x;
-            o.v[1] = t.y;
-        } else {
+        if constexpr (P == 1) {
             o.v[0] = *reinterpret_cast<const double *>(p);
+        } else {
+#pragma unroll
+            for (int g = 0; g < P / 2; ++g) {
+                double2 t = *reinterpret_cast<const double2 *>(p + g * PAIR_BYTES);
+                o.v[2 * g] = t.x;
+                o.v[2 * g + 1] = t.y;
+            }
         }
     }
     __device__ __forceinline__ static void store(char *my, uint32_t field, const Pt<P> &o) {
         char *p = my + (field & 0xfffcu) * (SLOT_BYTES / 4);
-        if constexpr (P == 2) {
-            *reinterpret_cast<double2 *>(p) = make_double2(o.v[0], o.v[1]);
-        } else {
+        if constexpr (P == 1) {
             *reinterpret_cast<double *>(p) = o.v[0];
+        } else {
+#pragma unroll
+            for (int g = 0; g < P / 2; ++g)
+                *reinterpret_cast<double2 *>(p + g * PAIR_BYTES) = make_double2(o.v[2 * g], o.v[2 * g + 1]);
         }
     }
 };
@@ -83,14 +93,27 @@ struct Rf {
 
 } // namespace
 
+// Points of a thread.  P == 1: i = tile_base + tid.  P >= 2: pair g covers points
+// tile_base + g * 2 * BLOCK + 2 * tid + {0, 1}: every 128-bit access of a warp is fully coalesced.
+template <int P>
+__device__ __forceinline__ unsigned long long point_index(unsigned long long tile_base, int p) {
+    if constexpr (P == 1) return tile_base + threadIdx.x;
+    else return tile_base + (unsigned long long)(p >> 1) * (2 * BLOCK_THREADS) + 2 * threadIdx.x + (p & 1);
+}
+
 // CODE_IN_BLOB / K_IN_BLOB: program words / constants come from the constant bank (kernel
 // parameter `blob`), otherwise from global memory through the read-only path.
 template <int P, int WORDS, bool CODE_IN_BLOB, bool K_IN_BLOB>
-__global__ void __launch_bounds__(BLOCK_THREADS, 4)
+__global__ void __launch_bounds__(BLOCK_THREADS, (P == 4 ? 3 : 4))
 saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ ConstBlob<WORDS> blob) {
     extern __shared__ __align__(16) unsigned char saf_smem[];
-    char *const my = reinterpret_cast<char *>(saf_smem) + threadIdx.x * (P * 8);
+    char *const my = reinterpret_cast<char *>(saf_smem) + threadIdx.x * (P == 1 ? 8 : 16);
     using RF = Rf<P>;
+
+    // trig coefficient table behind the register file
+    double *const trig_tab = reinterpret_cast<double *>(saf_smem + (size_t)d.n_slots * RF::SLOT_BYTES);
+    if (threadIdx.x < 14) trig_tab[threadIdx.x] = (&lm::kTrigTable[0][0])[threadIdx.x];
+    __syncthreads();
 
     auto fetch_word = [&](uint32_t pc) -> uint2 {
         unsigned long long w;
@@ -98,17 +121,17 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
         else w = __ldg(reinterpret_cast<const unsigned long long *>(d.code_global) + pc);
         return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
     };
-    auto konst = [&](uint32_t field) -> double { // K field -> value (warp-uniform load)
-        const uint32_t idx = field >> KIND_BITS;
+    auto konst_at = [&](uint32_t idx) -> double { // constant table entry (warp-uniform load)
         if constexpr (K_IN_BLOB) return __longlong_as_double((long long)blob.w[d.n_code + idx]);
         else return __ldg(d.consts_global + idx);
     };
+    auto konst = [&](uint32_t field) -> double { return konst_at(field >> KIND_BITS); };
 
     constexpr unsigned long long TILE = (unsigned long long)BLOCK_THREADS * P;
     const unsigned long long n_tiles = (d.n_points + TILE - 1) / TILE;
 
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned long long i0 = tile * TILE + (unsigned long long)threadIdx.x * P;
+        const unsigned long long tile_base = tile * TILE;
 
         // ---- prologue: columns -> parameter slots (scalar.rs:182-207 rules) ----
         for (uint32_t j = 0; j < d.n_params; ++j) {
@@ -119,12 +142,19 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
             Pt<P> v;
             SAF_FOR_P v.v[p] = 0.0; // missing column reads as 0.0
             if (col != nullptr && len != 0ull) {
-                if (P == 2 && i0 + 1 < len && i0 + 1 < d.n_points) {
-                    ld_stream2(col + i0, v.v[0], v.v[P - 1]);
+                if constexpr (P == 1) {
+                    const unsigned long long i = point_index<P>(tile_base, 0);
+                    if (i < d.n_points) v.v[0] = ld_stream(col + (i < len ? i : len - 1));
                 } else {
-                    SAF_FOR_P {
-                        const unsigned long long i = i0 + p;
-                        if (i < d.n_points) v.v[p] = ld_stream(col + (i < len ? i : len - 1));
+#pragma unroll
+                    for (int g = 0; g < P / 2; ++g) {
+                        const unsigned long long i = point_index<P>(tile_base, 2 * g);
+                        if (i + 1 < len && i + 1 < d.n_points) {
+                            ld_stream2(col + i, v.v[2 * g], v.v[2 * g + 1]);
+                        } else {
+                            if (i < d.n_points) v.v[2 * g] = ld_stream(col + (i < len ? i : len - 1));
+                            if (i + 1 < d.n_points) v.v[2 * g + 1] = ld_stream(col + (i + 1 < len ? i + 1 : len - 1));
+                        }
                     }
                 }
             }
@@ -156,9 +186,23 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
                         o = acc;
                     }
                 };
+                // operand of a heavy unary opcode, with the optional affine prefix (saf_isa.h)
+                auto unary_arg = [&](Pt<P> &o) {
+                    any(fa, o);
+                    const uint32_t mode = (w.x >> 8) & 0xffu;
+                    if (mode != PREFIX_NONE) {
+                        const uint32_t ki = fb >> KIND_BITS;
+                        const double k1 = konst_at(ki);
+                        if (mode == PREFIX_MUL) {
+                            SAF_FOR_P o.v[p] = __dmul_rn(o.v[p], k1);
+                        } else {
+                            const double k2 = konst_at(ki + 1);
+                            SAF_FOR_P o.v[p] = __fma_rn(o.v[p], k1, k2);
+                        }
+                    }
+                };
 
                 Pt<P> a, b, r;
-                bool done = false;
 
 #define SAF_A_S RF::load(my, fa, a);
 #define SAF_A_K { const double k_ = konst(fa); SAF_FOR_P a.v[p] = k_; }
@@ -183,7 +227,7 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
     SAF_BCASE(OP, KIND_ACC, KIND_K, SAF_A_A, SAF_B_K, EXPR)                                        \
     SAF_BCASE(OP, KIND_ACC, KIND_ACC, SAF_A_A, SAF_B_A, EXPR)
 #define SAF_UHEAVY(OP, EXPR)                                                                       \
-    case X_UHEAVY + ((OP) - D_FIRST_HEAVY_UNARY): any(fa, a); SAF_FOR_P { EXPR; } break;
+    case X_UHEAVY + ((OP) - D_FIRST_HEAVY_UNARY): unary_arg(a); SAF_FOR_P { EXPR; } break;
 #define SAF_BHEAVY(OP, EXPR)                                                                       \
     case X_BHEAVY + ((OP) - D_FIRST_HEAVY_BINARY): any(fa, a); any(fb, b); SAF_FOR_P { EXPR; } break;
 #define SAF_TERN(OP, EXPR)                                                                         \
@@ -195,7 +239,7 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
     } break;
 
                 switch (xop) {
-                case X_END: done = true; break;
+                case X_END: goto program_end;
                 case X_LOADK: SAF_A_K r = a; break;
 
                 SAF_ULIGHT(D_COPY, r.v[p] = a.v[p])
@@ -211,19 +255,19 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
                 SAF_ULIGHT(D_RECIP, r.v[p] = __ddiv_rn(1.0, a.v[p]))
                 SAF_ULIGHT(D_SQRT, r.v[p] = __dsqrt_rn(a.v[p]))
 
-                SAF_UHEAVY(D_SIN, r.v[p] = sin(a.v[p]))
-                SAF_UHEAVY(D_COS, r.v[p] = cos(a.v[p]))
-                SAF_UHEAVY(D_EXP, r.v[p] = exp(a.v[p]))
+                SAF_UHEAVY(D_SIN, r.v[p] = lm::sin(a.v[p], trig_tab))
+                SAF_UHEAVY(D_COS, r.v[p] = lm::cos(a.v[p], trig_tab))
+                SAF_UHEAVY(D_EXP, r.v[p] = lm::exp(a.v[p]))
                 SAF_UHEAVY(D_LN, r.v[p] = log(a.v[p]))
                 SAF_UHEAVY(D_RECIPEXPM1, r.v[p] = __ddiv_rn(1.0, expm1(a.v[p])))
-                SAF_UHEAVY(D_EXPSQR, r.v[p] = exp(__dmul_rn(a.v[p], a.v[p])))
-                SAF_UHEAVY(D_EXPSQRNEG, r.v[p] = exp(-__dmul_rn(a.v[p], a.v[p])))
-                SAF_UHEAVY(D_EXPNEG, r.v[p] = exp(-a.v[p]))
+                SAF_UHEAVY(D_EXPSQR, r.v[p] = lm::exp(__dmul_rn(a.v[p], a.v[p])))
+                SAF_UHEAVY(D_EXPSQRNEG, r.v[p] = lm::exp(-__dmul_rn(a.v[p], a.v[p])))
+                SAF_UHEAVY(D_EXPNEG, r.v[p] = lm::exp(-a.v[p]))
                 case X_UHEAVY + (D_SINCOS - D_FIRST_HEAVY_UNARY): {
                     const uint2 h = fetch_word(pc++);
-                    any(fa, a);
+                    unary_arg(a);
                     Pt<P> cs;
-                    SAF_FOR_P sincos(a.v[p], &r.v[p], &cs.v[p]);
+                    SAF_FOR_P lm::sincos(a.v[p], r.v[p], cs.v[p], trig_tab);
                     if ((h.x & KIND_MASK) == KIND_S) RF::store(my, h.x & 0xffffu, cs);
                 } break;
                 case X_UHEAVY + (D_BUILTIN1 - D_FIRST_HEAVY_UNARY): {
@@ -271,10 +315,10 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
                 SAF_TERN(D_FNMS, r.v[p] = __fma_rn(-a.v[p], b.v[p], -c.v[p]))
                 default: SAF_FOR_P r.v[p] = dm::nan_(); break;
                 }
-                if (done) break;
                 acc = r;
                 if ((fd & KIND_MASK) == KIND_S) RF::store(my, fd, r);
             }
+        program_end:
 
             if (++it >= d.iters) break;
             // ---- in-kernel feedback: parameter j <- result j (result slots never alias parameter
@@ -305,10 +349,19 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
                 SAF_FOR_P v.v[p] = kv;
             }
             double *out = d.outs[k];
-            if (P == 2 && i0 + 1 < d.n_points) {
-                st_stream2(out + i0, v.v[0], v.v[P - 1]);
+            if constexpr (P == 1) {
+                const unsigned long long i = point_index<P>(tile_base, 0);
+                if (i < d.n_points) st_stream(out + i, v.v[0]);
             } else {
-                SAF_FOR_P if (i0 + p < d.n_points) st_stream(out + i0 + p, v.v[p]);
+#pragma unroll
+                for (int g = 0; g < P / 2; ++g) {
+                    const unsigned long long i = point_index<P>(tile_base, 2 * g);
+                    if (i + 1 < d.n_points) {
+                        st_stream2(out + i, v.v[2 * g], v.v[2 * g + 1]);
+                    } else if (i < d.n_points) {
+                        st_stream(out + i, v.v[2 * g]);
+                    }
+                }
             }
         }
     }
@@ -378,13 +431,19 @@ static cudaError_t launch_p(const LaunchDesc &desc, const uint64_t *words, size_
 
 cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *blob_words, size_t n_blob_words,
                                bool consts_in_blob, const LaunchShape &shape, cudaStream_t stream) {
-    if (shape.points_per_thread == 2)
-        return launch_p<2>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
-    return launch_p<1>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
+    switch (shape.points_per_thread) {
+    case 4: return launch_p<4>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
+    case 2: return launch_p<2>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
+    default: return launch_p<1>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
+    }
+}
+
+size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread) {
+    return (size_t)n_slots * (size_t)BLOCK_THREADS * (size_t)points_per_thread * 8 + 128; // + trig table
 }
 
 cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
-                         LaunchShape *shape) {
+                         int force_points_per_thread, LaunchShape *shape) {
     int sms = 0, smem_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -392,17 +451,28 @@ cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_poin
     if (e != cudaSuccess) return e;
     const size_t smem_sm = (size_t)smem_optin; // per-block opt-in limit ~= per-SM capacity minus 1 KB
     const int block = BLOCK_THREADS;
-    auto bytes = [&](int p) { return (size_t)n_slots * (size_t)block * (size_t)p * 8; };
 
-    // Two points per thread when there is enough work to fill the chip with 2-point threads and the
-    // register file of two points still leaves room for at least two resident blocks per SM.
-    int P = (aligned16 && n_points >= (unsigned long long)sms * 4ull * block * 2ull) ? 2 : 1;
-    if (P == 2 && bytes(2) * 2 > smem_sm) P = 1;
-    if (bytes(P) > smem_sm) return cudaErrorInvalidConfiguration;
+    // More points per thread amortise the dispatch; they need (a) 16-byte aligned columns, (b) enough
+    // points to still give every SM several blocks, (c) a register file that leaves >= 2 blocks per SM.
+    auto fits = [&](int p, int min_blocks) {
+        return interpreter_smem_bytes(n_slots, p) * (size_t)min_blocks <= smem_sm;
+    };
+    auto enough = [&](int p) {
+        return n_points >= (unsigned long long)sms * 3ull * (unsigned long long)block * (unsigned long long)p;
+    };
+    int P = 1;
+    if (aligned16 && enough(4) && fits(4, 2)) P = 4;
+    else if (aligned16 && enough(2) && fits(2, 2)) P = 2;
+    if (force_points_per_thread == 1 || (aligned16 && (force_points_per_thread == 2 || force_points_per_thread == 4)))
+        P = force_points_per_thread;
+    if (!fits(P, 1)) {
+        P = 1;
+        if (!fits(1, 1)) return cudaErrorInvalidConfiguration;
+    }
 
-    const size_t smem = bytes(P);
-    size_t resident = 4; // __launch_bounds__(128, 4): 128 registers x 512 threads
-    size_t by_smem = smem ? (smem_sm + 1024) / (smem + 1024) : resident;
+    const size_t smem = interpreter_smem_bytes(n_slots, P);
+    size_t resident = (P == 4) ? 3 : 4; // __launch_bounds__ register budget
+    size_t by_smem = (smem_sm + 1024) / (smem + 1024);
     if (by_smem < resident) resident = by_smem;
     if (resident < 1) resident = 1;
     const unsigned long long tile = (unsigned long long)block * P;

@@ -40,7 +40,7 @@ constexpr int BLOB_SMALL = 448;
 constexpr int BLOB_LARGE = 3840;
 
 struct LaunchShape {
-    int points_per_thread; // 1 or 2
+    int points_per_thread; // 1, 2 or 4
     int block;             // threads per block (always BLOCK_THREADS)
     int grid;
     size_t smem_bytes;
@@ -52,9 +52,11 @@ struct LaunchShape {
 cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *blob_words, size_t n_blob_words,
                                bool consts_in_blob, const LaunchShape &shape, cudaStream_t stream);
 
-// Picks points-per-thread / block / grid for a program with n_slots live values on `device`.
+// Picks points-per-thread / grid for a program with n_slots live values on `device`.
+// force_points_per_thread: 0 = automatic, 1 / 2 / 4 = tuning override (SAF_POINTS_PER_THREAD).
 cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
-                         LaunchShape *shape);
+                         int force_points_per_thread, LaunchShape *shape);
+size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread);
 
 // FP64-pipe peak probe: blocks x 256 threads, each `iters` x 64 dependent-chain DFMAs.
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);

@@ -728,10 +728,12 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
     out.n_ref_instructions = n_ref_instructions;
 
     struct Emit {
-        int32_t node;     // producing node, -1 for ARG2
+        int32_t node;     // producing node, -1 for ARG2 / LOADK
         uint8_t op;
         int32_t src[3];   // value ids
         int32_t cosval;   // for SINCOS
+        uint8_t prefix = PREFIX_NONE; // affine prefix folded into a heavy unary op
+        int32_t pk1 = -1, pk2 = -1;   // constant nodes of the prefix
     };
     std::vector<Emit> E;
     constexpr int32_t SRC_LOADK = -2; // operand comes from ACC, loaded by a D_LOADK emitted just before
@@ -763,6 +765,49 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
             E.push_back({i, n.op, {n.a, n.b, n.c}, -1});
         }
         out.fp64_slots += op_fp64_slots(n);
+    }
+
+    // ---- affine-prefix fusion: f(Mul(x, K)) and f(MulAdd(x, K1, K2)) become one instruction ----
+    {
+        std::vector<int32_t> uses(N, 0);
+        for (const Emit &e : E)
+            for (int32_t s_ : e.src)
+                if (s_ >= 0) ++uses[s_];
+        for (int32_t r : results) ++uses[r];
+        for (auto &kv : g.cos_of)
+            if (live[kv.second]) uses[kv.first] += 0; // the cos half is a separate value id
+        auto prefixable = [](uint8_t op) {
+            return op == D_SIN || op == D_COS || op == D_EXP || op == D_LN || op == D_EXPNEG || op == D_SINCOS ||
+                   op == D_RECIPEXPM1 || op == D_EXPSQR || op == D_EXPSQRNEG;
+        };
+        std::vector<Emit> F;
+        F.reserve(E.size());
+        for (size_t j = 0; j < E.size(); ++j) {
+            Emit e = E[j];
+            if (!F.empty() && prefixable(e.op) && e.src[0] >= 0 && F.back().node == e.src[0] &&
+                F.back().node >= 0 && uses[e.src[0]] == 1 && F.back().prefix == PREFIX_NONE) {
+                const Emit &m = F.back();
+                const Node &mn = g.nodes[m.node];
+                int32_t x = -1, k1 = -1, k2 = -1;
+                if (m.op == D_MUL) {
+                    if (is_const(mn.a) && !is_const(mn.b)) { x = mn.b; k1 = mn.a; }
+                    else if (is_const(mn.b) && !is_const(mn.a)) { x = mn.a; k1 = mn.b; }
+                } else if (m.op == D_FMA && is_const(mn.c)) {
+                    if (is_const(mn.a) && !is_const(mn.b)) { x = mn.b; k1 = mn.a; k2 = mn.c; }
+                    else if (is_const(mn.b) && !is_const(mn.a)) { x = mn.a; k1 = mn.b; k2 = mn.c; }
+                }
+                // the producer must really have been emitted as that plain Mul / MulAdd
+                if (x >= 0 && m.src[0] != SRC_LOADK) {
+                    e.src[0] = x;
+                    e.prefix = (k2 >= 0) ? PREFIX_FMA : PREFIX_MUL;
+                    e.pk1 = k1;
+                    e.pk2 = k2;
+                    F.pop_back();
+                }
+            }
+            F.push_back(e);
+        }
+        E.swap(F);
     }
 
     // ---- accumulator forwarding + last uses ----
@@ -830,6 +875,28 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
         return make_field(KIND_K, i & (MAX_INDEX - 1));
     };
 
+    // (K1, K2) pairs of an FMA prefix sit in adjacent table entries
+    std::unordered_multimap<uint64_t, uint32_t> kpair_idx;
+    auto kpair_field = [&](int32_t v1, int32_t v2) -> uint32_t {
+        const uint64_t b1 = g.nodes[v1].bits, b2 = g.nodes[v2].bits;
+        const uint64_t key = b1 * 0x9E3779B97F4A7C15ull ^ (b2 + 0x7F4A7C159E3779B9ull + (b1 << 6) + (b1 >> 2));
+        for (auto range = kpair_idx.equal_range(key); range.first != range.second; ++range.first) {
+            uint32_t i = range.first->second;
+            uint64_t c1, c2;
+            std::memcpy(&c1, &out.consts[i], 8);
+            std::memcpy(&c2, &out.consts[i + 1], 8);
+            if (c1 == b1 && c2 == b2) return make_field(KIND_K, i & (MAX_INDEX - 1));
+        }
+        const uint32_t i = (uint32_t)out.consts.size();
+        double d1, d2;
+        std::memcpy(&d1, &b1, 8);
+        std::memcpy(&d2, &b2, 8);
+        out.consts.push_back(d1);
+        out.consts.push_back(d2);
+        kpair_idx.emplace(key, i);
+        return make_field(KIND_K, i & (MAX_INDEX - 1));
+    };
+
     out.code.clear();
     out.code.reserve(2 * (size_t)NE + 2);
     bool overflow = false;
@@ -888,7 +955,10 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
         } else {
             xop = X_TERN + (op - D_FIRST_TERNARY);
         }
-        out.code.push_back(make_lo(xop, fd, fa, fb));
+        if (e.prefix == PREFIX_MUL) fb = kfield(e.pk1);
+        else if (e.prefix == PREFIX_FMA) fb = kpair_field(e.pk1, e.pk2);
+        if (e.prefix != PREFIX_NONE) ++out.n_prefix_fusions;
+        out.code.push_back(make_lo(xop, fd, fa, fb, e.prefix));
         if (xop_has_hi(xop)) out.code.push_back(make_hi(fc, imm));
         ++out.n_dev_instructions;
         if (n_slots > MAX_INDEX || out.consts.size() > MAX_INDEX) overflow = true;
@@ -987,9 +1057,17 @@ std::string disassemble(const DeviceProgram &p) {
         decode_xop(x, &op, &ka, &kb);
         os << "  [" << i << "] ";
         fmt_field(os, d);
+        const uint32_t prefix = (lo >> 8) & 0xff;
         os << " = " << (op < D_OPCOUNT ? DEV_NAMES[op] : "?") << "(";
         fmt_field(os, a);
-        if (field_kind(b) != KIND_NONE) {
+        if (prefix == PREFIX_MUL) {
+            os << " * ";
+            fmt_field(os, b);
+        } else if (prefix == PREFIX_FMA) {
+            os << " * ";
+            fmt_field(os, b);
+            os << " + K" << field_index(b) + 1;
+        } else if (field_kind(b) != KIND_NONE) {
             os << ", ";
             fmt_field(os, b);
         }

@@ -27,6 +27,7 @@ struct DeviceProgram {
     uint32_t n_ref_instructions = 0;
     uint32_t n_dev_instructions = 0;    // excluding the end marker
     uint32_t n_acc_forwards = 0;
+    uint32_t n_prefix_fusions = 0;
     uint32_t quirk_flags = 0;
     double fp64_slots = 0.0;
 };

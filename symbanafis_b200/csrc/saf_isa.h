@@ -8,7 +8,7 @@
 // Every instruction has a `lo` word; opcodes that need a third field or an immediate (the FMA
 // family, SinCos, Powi, the builtins -- see xop_has_hi) are followed by a `hi` word:
 //     lo  [ 7: 0] device opcode         hi  [15: 0] c   third source field / second destination
-//         [15: 8] (reserved)                [63:32] imm FnOp id or i32 immediate
+//         [15: 8] prefix mode (heavy unary)  [63:32] imm FnOp id or i32 immediate
 //         [31:16] d   destination field
 //         [47:32] a   first source field
 //         [63:48] b   second source field
@@ -18,6 +18,13 @@
 //     kind 2 = ACC       the accumulator: result of the previous instruction, kept in real registers
 //     kind 3 = none
 // Every value-producing instruction leaves its result in ACC; if d is an S field it is also stored.
+//
+// Affine prefix (heavy unary opcodes only): the lowering folds a preceding single-use `Mul(x, K)` or
+// `MulAdd(x, K1, K2)` into the transcendental that consumes it -- sin(a*x), sincos(f*x + p),
+// exp(-u/w) are the dominant shapes of the reference's workloads -- saving one dispatch each:
+//     mode 0: arg = a     mode 1: arg = a * K[b]     mode 2: arg = fma(a, K[b], K[b+1])
+// with b the K field in lo[63:48].  The same correctly rounded operation runs, so results are
+// unchanged bit for bit.
 //
 // The hot, cheap opcodes are SPECIALISED BY OPERAND KIND at lowering time (the opcode number says
 // where each source comes from), so their handlers contain no operand-kind branches at all; the
@@ -105,8 +112,10 @@ constexpr uint32_t X_BHEAVY = X_BLIGHT + 9 * D_N_LIGHT_BINARY; // 73
 constexpr uint32_t X_TERN = X_BHEAVY + D_N_HEAVY_BINARY;       // 79
 constexpr uint32_t X_OPCOUNT = X_TERN + D_N_TERNARY;           // 83
 
-constexpr uint64_t make_lo(uint32_t xop, uint32_t d, uint32_t a, uint32_t b) {
-    return (uint64_t)xop | ((uint64_t)d << 16) | ((uint64_t)a << 32) | ((uint64_t)b << 48);
+constexpr uint32_t PREFIX_NONE = 0, PREFIX_MUL = 1, PREFIX_FMA = 2;
+constexpr uint64_t make_lo(uint32_t xop, uint32_t d, uint32_t a, uint32_t b, uint32_t prefix = 0) {
+    return (uint64_t)xop | ((uint64_t)prefix << 8) | ((uint64_t)d << 16) | ((uint64_t)a << 32) |
+           ((uint64_t)b << 48);
 }
 constexpr uint64_t make_hi(uint32_t c, uint32_t imm) { return (uint64_t)c | ((uint64_t)imm << 32); }
 

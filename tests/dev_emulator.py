@@ -104,6 +104,19 @@ def run_device_program(code: Sequence[int], consts: np.ndarray, param_slot: Sequ
         assert kind == KIND_ACC, "operand field of kind none was read"
         return acc
 
+    def unary_arg(fa: int, fb: int, prefix: int) -> np.ndarray:
+        """operand of a heavy unary opcode with its affine prefix (saf_isa.h): a, a*K[b] or fma(a,K[b],K[b+1])"""
+        a = operand(fa)
+        if prefix == 0:
+            return a
+        assert (fb & 3) == KIND_K
+        k1 = np.full(n_points, consts[fb >> 2])
+        if prefix == 1:
+            return _leaf(("Mul", 2, 0, 1), 2).eval_batch([a, k1], n_points)[0]
+        assert prefix == 2
+        k2 = np.full(n_points, consts[(fb >> 2) + 1])
+        return _leaf(("MulAdd", 3, 0, 1, 2), 3).eval_batch([a, k1, k2], n_points)[0]
+
     def result_value(f: int) -> np.ndarray:
         kind, idx = f & 3, f >> 2
         return S[idx].copy() if kind == KIND_S else np.full(n_points, consts[idx])
@@ -117,6 +130,7 @@ def run_device_program(code: Sequence[int], consts: np.ndarray, param_slot: Sequ
             if name == "end":
                 break
             fd, fa, fb = (lo >> 16) & 0xFFFF, (lo >> 32) & 0xFFFF, (lo >> 48) & 0xFFFF
+            prefix = (lo >> 8) & 0xFF
             fc, imm = KIND_NONE, 0
             if name in HAS_HI:
                 hi = code[pc]
@@ -127,11 +141,12 @@ def run_device_program(code: Sequence[int], consts: np.ndarray, param_slot: Sequ
             elif name == "copy":
                 r = operand(fa, ka).copy()
             elif name in _UNARY_REF:
-                r = _leaf((_UNARY_REF[name], 1, 0), 1).eval_batch([operand(fa, ka)], n_points)[0]
+                arg = operand(fa, ka) if ka is not None else unary_arg(fa, fb, prefix)
+                r = _leaf((_UNARY_REF[name], 1, 0), 1).eval_batch([arg], n_points)[0]
             elif name == "expneg":
-                r = _leaf(("Builtin1", 1, "exp_neg", 0), 1).eval_batch([operand(fa)], n_points)[0]
+                r = _leaf(("Builtin1", 1, "exp_neg", 0), 1).eval_batch([unary_arg(fa, fb, prefix)], n_points)[0]
             elif name == "sincos":
-                s_, c_ = _leaf(("SinCos", 1, 2, 0), 1, 2).eval_batch([operand(fa)], n_points)
+                s_, c_ = _leaf(("SinCos", 1, 2, 0), 1, 2).eval_batch([unary_arg(fa, fb, prefix)], n_points)
                 r = s_
                 if (fc & 3) == KIND_S:
                     S[fc >> 2] = c_
