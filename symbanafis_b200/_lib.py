@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsaf_b200.so")
+LIB_PATH = os.environ.get("SAF_B200_LIB") or os.path.join(_PKG, "libsaf_b200.so")  # env: tuning builds only
 CSRC = os.path.join(_PKG, "csrc")
 
 SAF_OK = 0

@@ -33,6 +33,17 @@
 #include "devmath.cuh"
 #include "leanmath.cuh"
 
+// resident blocks per SM the register allocation aims for, per points-per-thread variant (tuning knobs)
+#ifndef SAF_MINB_P4
+#define SAF_MINB_P4 3
+#endif
+#ifndef SAF_MINB_P2
+#define SAF_MINB_P2 4
+#endif
+#ifndef SAF_MINB_P1
+#define SAF_MINB_P1 4
+#endif
+
 namespace saf {
 
 namespace {
@@ -104,7 +115,7 @@ __device__ __forceinline__ unsigned long long point_index(unsigned long long til
 // CODE_IN_BLOB / K_IN_BLOB: program words / constants come from the constant bank (kernel
 // parameter `blob`), otherwise from global memory through the read-only path.
 template <int P, int WORDS, bool CODE_IN_BLOB, bool K_IN_BLOB>
-__global__ void __launch_bounds__(BLOCK_THREADS, (P == 4 ? 3 : 4))
+__global__ void __launch_bounds__(BLOCK_THREADS, (P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1))
 saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ ConstBlob<WORDS> blob) {
     extern __shared__ __align__(16) unsigned char saf_smem[];
     char *const my = reinterpret_cast<char *>(saf_smem) + threadIdx.x * (P == 1 ? 8 : 16);
@@ -255,19 +266,31 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
                 SAF_ULIGHT(D_RECIP, r.v[p] = __ddiv_rn(1.0, a.v[p]))
                 SAF_ULIGHT(D_SQRT, r.v[p] = __dsqrt_rn(a.v[p]))
 
-                SAF_UHEAVY(D_SIN, r.v[p] = lm::sin(a.v[p], trig_tab))
-                SAF_UHEAVY(D_COS, r.v[p] = lm::cos(a.v[p], trig_tab))
-                SAF_UHEAVY(D_EXP, r.v[p] = lm::exp(a.v[p]))
+                case X_UHEAVY + (D_SIN - D_FIRST_HEAVY_UNARY): unary_arg(a); lm::sin_n<P>(a.v, r.v, trig_tab); break;
+                case X_UHEAVY + (D_COS - D_FIRST_HEAVY_UNARY): unary_arg(a); lm::cos_n<P>(a.v, r.v, trig_tab); break;
+                case X_UHEAVY + (D_EXP - D_FIRST_HEAVY_UNARY): unary_arg(a); lm::exp_n<P>(a.v, r.v); break;
                 SAF_UHEAVY(D_LN, r.v[p] = log(a.v[p]))
                 SAF_UHEAVY(D_RECIPEXPM1, r.v[p] = __ddiv_rn(1.0, expm1(a.v[p])))
-                SAF_UHEAVY(D_EXPSQR, r.v[p] = lm::exp(__dmul_rn(a.v[p], a.v[p])))
-                SAF_UHEAVY(D_EXPSQRNEG, r.v[p] = lm::exp(-__dmul_rn(a.v[p], a.v[p])))
-                SAF_UHEAVY(D_EXPNEG, r.v[p] = lm::exp(-a.v[p]))
+                case X_UHEAVY + (D_EXPSQR - D_FIRST_HEAVY_UNARY):
+                    unary_arg(a);
+                    SAF_FOR_P a.v[p] = __dmul_rn(a.v[p], a.v[p]);
+                    lm::exp_n<P>(a.v, r.v);
+                    break;
+                case X_UHEAVY + (D_EXPSQRNEG - D_FIRST_HEAVY_UNARY):
+                    unary_arg(a);
+                    SAF_FOR_P a.v[p] = -__dmul_rn(a.v[p], a.v[p]);
+                    lm::exp_n<P>(a.v, r.v);
+                    break;
+                case X_UHEAVY + (D_EXPNEG - D_FIRST_HEAVY_UNARY):
+                    unary_arg(a);
+                    SAF_FOR_P a.v[p] = -a.v[p];
+                    lm::exp_n<P>(a.v, r.v);
+                    break;
                 case X_UHEAVY + (D_SINCOS - D_FIRST_HEAVY_UNARY): {
                     const uint2 h = fetch_word(pc++);
                     unary_arg(a);
                     Pt<P> cs;
-                    SAF_FOR_P lm::sincos(a.v[p], r.v[p], cs.v[p], trig_tab);
+                    lm::sincos_n<P>(a.v, r.v, cs.v, trig_tab);
                     if ((h.x & KIND_MASK) == KIND_S) RF::store(my, h.x & 0xffffu, cs);
                 } break;
                 case X_UHEAVY + (D_BUILTIN1 - D_FIRST_HEAVY_UNARY): {
@@ -471,7 +494,7 @@ cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_poin
     }
 
     const size_t smem = interpreter_smem_bytes(n_slots, P);
-    size_t resident = (P == 4) ? 3 : 4; // __launch_bounds__ register budget
+    size_t resident = (P == 4) ? SAF_MINB_P4 : (P == 2) ? SAF_MINB_P2 : SAF_MINB_P1; // __launch_bounds__ budget
     size_t by_smem = (smem_sm + 1024) / (smem + 1024);
     if (by_smem < resident) resident = by_smem;
     if (resident < 1) resident = 1;

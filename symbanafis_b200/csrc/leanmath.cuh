@@ -74,28 +74,47 @@ __device__ __forceinline__ double trig_eval(double r, int q, const double *tab) 
     return __hiloint2double(hi, __double2loint(v));
 }
 
-__device__ __forceinline__ double sin(double x, const double *tab) {
-    if (trig_slow(x)) return ::sin(x);
-    int q;
-    const double r = trig_reduce(x, q);
-    return trig_eval(r, q, tab);
-}
-__device__ __forceinline__ double cos(double x, const double *tab) {
-    // zero and denormals are fine for cos (no signed-zero result), but they share the slow test
-    if (trig_slow(x)) return ::cos(x);
-    int q;
-    const double r = trig_reduce(x, q);
-    return trig_eval(r, q + 1, tab);
-}
-__device__ __forceinline__ void sincos(double x, double &s, double &c, const double *tab) {
-    if (trig_slow(x)) {
-        ::sincos(x, &s, &c);
-        return;
+// ---- P-wide entry points -------------------------------------------------------------------------
+// The fast path runs branch-free over all P points of a thread (the compiler interleaves the P
+// dependent FMA chains: instruction-level parallelism instead of occupancy); points outside the fast
+// range are then recomputed one by one with the CUDA math library.  Every point's result depends only
+// on its own input -- never on which other points share the thread.
+template <int P>
+__device__ __forceinline__ void sin_n(const double (&x)[P], double (&out)[P], const double *tab) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        int q;
+        const double r = trig_reduce(x[p], q);
+        out[p] = trig_eval(r, q, tab);
     }
-    int q;
-    const double r = trig_reduce(x, q);
-    s = trig_eval(r, q, tab);
-    c = trig_eval(r, q + 1, tab);
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        if (trig_slow(x[p])) out[p] = ::sin(x[p]);
+}
+template <int P>
+__device__ __forceinline__ void cos_n(const double (&x)[P], double (&out)[P], const double *tab) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        int q;
+        const double r = trig_reduce(x[p], q);
+        out[p] = trig_eval(r, q + 1, tab);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        if (trig_slow(x[p])) out[p] = ::cos(x[p]);
+}
+template <int P>
+__device__ __forceinline__ void sincos_n(const double (&x)[P], double (&s)[P], double (&c)[P], const double *tab) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        int q;
+        const double r = trig_reduce(x[p], q);
+        s[p] = trig_eval(r, q, tab);
+        c[p] = trig_eval(r, q + 1, tab);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        if (trig_slow(x[p])) ::sincos(x[p], &s[p], &c[p]);
 }
 
 // exp: k = rint(x log2 e), r = x - k ln2 (hi + lo), degree-13 Taylor kernel (remainder < 2^-57 on
@@ -103,28 +122,28 @@ __device__ __forceinline__ void sincos(double x, double &s, double &c, const dou
 constexpr double kLog2e = 1.44269504088896338700e+00;
 constexpr double kLn2Hi = 6.93147180369123816490e-01;
 constexpr double kLn2Lo = 1.90821492927058770002e-10;
+__device__ __constant__ double kExpTaylor[14] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0,       1.0 / 720.0,       1.0 / 120.0,      1.0 / 24.0,      1.0 / 6.0,      0.5,
+    1.0,                1.0};
 
-__device__ __forceinline__ double exp(double x) {
-    if (!(fabs(x) < 700.0)) return ::exp(x);
+__device__ __forceinline__ double exp_fast(double x) {
     const int k = __double2int_rn(__dmul_rn(x, kLog2e));
     const double kd = __int2double_rn(k);
     double r = __fma_rn(kd, -kLn2Hi, x);
     r = __fma_rn(kd, -kLn2Lo, r);
-    double p = 1.0 / 6227020800.0;
-    p = __fma_rn(p, r, 1.0 / 479001600.0);
-    p = __fma_rn(p, r, 1.0 / 39916800.0);
-    p = __fma_rn(p, r, 1.0 / 3628800.0);
-    p = __fma_rn(p, r, 1.0 / 362880.0);
-    p = __fma_rn(p, r, 1.0 / 40320.0);
-    p = __fma_rn(p, r, 1.0 / 5040.0);
-    p = __fma_rn(p, r, 1.0 / 720.0);
-    p = __fma_rn(p, r, 1.0 / 120.0);
-    p = __fma_rn(p, r, 1.0 / 24.0);
-    p = __fma_rn(p, r, 1.0 / 6.0);
-    p = __fma_rn(p, r, 0.5);
-    p = __fma_rn(p, r, 1.0);
-    p = __fma_rn(p, r, 1.0);
+    double p = kExpTaylor[0];
+#pragma unroll
+    for (int i = 1; i < 14; ++i) p = __fma_rn(p, r, kExpTaylor[i]);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+template <int P>
+__device__ __forceinline__ void exp_n(const double (&x)[P], double (&out)[P]) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) out[p] = exp_fast(x[p]);
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        if (!(fabs(x[p]) < 700.0)) out[p] = ::exp(x[p]);
 }
 
 } // namespace lm
