@@ -114,6 +114,16 @@ SAF_API int saf_program_export(const saf_program *prog, uint64_t *code, size_t c
                        double *consts, size_t cap_consts, size_t *n_consts,
                        uint16_t *param_slot, uint32_t *result_field);
 
+/* Copies out the PACKED micro-instruction image the kernel executes for `points_per_thread` in {1, 2, 4}
+ * (layout: symbanafis_b200/csrc/uop.h): constants first, micro-instructions from byte `code_off`.
+ * param_off / result_off are byte offsets (-1 = parameter never read), result_is_k[k] = 1 when result k is
+ * a constant whose offset points into the image.  For the CPU emulator of the test-suite and for tooling.
+ * Any pointer may be NULL; n_words always receives the full size. */
+SAF_API int saf_program_export_packed(const saf_program *prog, int points_per_thread,
+                              uint64_t *image, size_t cap_words, size_t *n_words,
+                              uint32_t *code_off, uint32_t *n_slots, int32_t *x_off /* [2] */,
+                              int32_t *param_off, int32_t *result_off, uint8_t *result_is_k);
+
 /* ---- evaluation --------------------------------------------------------------------------- */
 
 /* Replaces run_chunked_evaluator / eval_batch with DEVICE-resident struct-of-arrays columns.

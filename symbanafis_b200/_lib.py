@@ -61,7 +61,7 @@ _lib: Optional[C.CDLL] = None
 
 EXPORTED_SYMBOLS = [
     "saf_program_create", "saf_program_fuse", "saf_program_destroy", "saf_program_get_info",
-    "saf_program_disassemble", "saf_program_export", "saf_eval_device", "saf_eval_host",
+    "saf_program_disassemble", "saf_program_export", "saf_program_export_packed", "saf_eval_device", "saf_eval_host",
     "saf_eval_host_multi", "saf_iterate_device", "saf_iterate_host", "saf_last_error",
     "saf_device_count", "saf_kernel_launch_count", "saf_version", "saf_measure_fp64_peak",
 ]
@@ -90,6 +90,9 @@ def lib() -> C.CDLL:
     L.saf_program_disassemble.restype = sz
     L.saf_program_export.argtypes = [vp, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), vp, vp]
     L.saf_program_export.restype = C.c_int
+    L.saf_program_export_packed.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(u32), C.POINTER(u32),
+                                            vp, vp, vp, vp]
+    L.saf_program_export_packed.restype = C.c_int
     L.saf_eval_device.argtypes = [vp, PP, C.POINTER(sz), sz, PP, sz, C.c_uint, vp]
     L.saf_eval_device.restype = C.c_int
     L.saf_eval_host.argtypes = [vp, PP, C.POINTER(sz), sz, PP, sz, C.c_uint]
@@ -206,6 +209,26 @@ class DeviceProgramHandle:
         check(lib().saf_program_export(self._h, code.ctypes.data, code.size, C.byref(nc), consts.ctypes.data,
                                        consts.size, C.byref(nk), pslot.ctypes.data, rfield.ctypes.data))
         return code, consts[:nk.value], pslot[:info.param_count], rfield[:info.n_results]
+
+    def export_packed(self, points_per_thread: int):
+        """The packed micro-instruction image for one register-file layout (csrc/uop.h):
+        dict(image uint64[], code_off, n_slots, x_off int32[2], param_off int32[], result_off int32[],
+        result_is_k uint8[])."""
+        nw, co, ns = C.c_size_t(), C.c_uint32(), C.c_uint32()
+        check(lib().saf_program_export_packed(self._h, points_per_thread, None, 0, C.byref(nw), C.byref(co),
+                                              C.byref(ns), None, None, None, None))
+        info = self.info()
+        image = np.zeros(nw.value, dtype=np.uint64)
+        x_off = np.zeros(2, dtype=np.int32)
+        poff = np.zeros(max(1, info.param_count), dtype=np.int32)
+        roff = np.zeros(max(1, info.n_results), dtype=np.int32)
+        rk = np.zeros(max(1, info.n_results), dtype=np.uint8)
+        check(lib().saf_program_export_packed(self._h, points_per_thread, image.ctypes.data, image.size, C.byref(nw),
+                                              C.byref(co), C.byref(ns), x_off.ctypes.data, poff.ctypes.data,
+                                              roff.ctypes.data, rk.ctypes.data))
+        return {"image": image, "code_off": co.value, "n_slots": ns.value, "x_off": x_off,
+                "param_off": poff[:info.param_count], "result_off": roff[:info.n_results],
+                "result_is_k": rk[:info.n_results], "points_per_thread": points_per_thread}
 
     # -- evaluation ----------------------------------------------------------------------------
     def eval_host(self, cols: Sequence[np.ndarray], outs: Sequence[np.ndarray], n_points: int,

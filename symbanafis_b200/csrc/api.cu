@@ -23,6 +23,7 @@
 #include "../../include/saf_b200.h"
 #include "kernel.cuh"
 #include "lower.h"
+#include "pack.h"
 
 using namespace saf;
 
@@ -45,20 +46,17 @@ static int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 // ---- program handle ---------------------------------------------------------------------------------
-struct DeviceCopy {
-    uint64_t *code = nullptr;
-    double *consts = nullptr;
-};
-
 struct saf_program {
     std::vector<RefProgram> refs; // kept so that handles can be fused later
     DeviceProgram dev;
-    std::vector<uint64_t> blob;   // code words followed (when they fit too) by constant bit patterns
-    bool blob_fits = false;       // code fits the constant-bank blob
-    bool consts_in_blob = false;  // ... and so do the constants
     std::mutex mu;
-    std::map<int, DeviceCopy> copies; // per-device global-memory copy for programs above BLOB_LARGE
+    // packed micro-instruction images, one per register-file layout (P = 1, 2, 4), built on first use
+    PackedProgram packed[3];
+    bool packed_ready[3] = {false, false, false};
+    std::map<std::pair<int, int>, unsigned char *> copies; // (device, P) -> global-memory image for big programs
 };
+
+static int layout_index(int P) { return P == 4 ? 2 : P == 2 ? 1 : 0; }
 
 static int build_program(std::vector<RefProgram> refs, saf_program **out) {
     std::unique_ptr<saf_program> p(new (std::nothrow) saf_program());
@@ -72,16 +70,10 @@ static int build_program(std::vector<RefProgram> refs, saf_program **out) {
     if (p->dev.param_count > (uint32_t)MAX_COLS || p->dev.result_field.size() > (size_t)MAX_OUTS) {
         return fail(SAF_ERR_UNSUPPORTED, "programs with more than 32 parameters or 32 results are not supported");
     }
-    p->blob.assign(p->dev.code.begin(), p->dev.code.end());
-    p->blob_fits = p->blob.size() <= (size_t)BLOB_LARGE;
-    p->consts_in_blob = p->blob.size() + p->dev.consts.size() <= (size_t)BLOB_LARGE;
-    if (p->consts_in_blob) {
-        for (double c : p->dev.consts) {
-            uint64_t bits;
-            std::memcpy(&bits, &c, 8);
-            p->blob.push_back(bits);
-        }
-    }
+    // pack the widest layout now so that encoding problems surface at creation time
+    rc = pack_program(p->dev, 4, p->packed[2], err);
+    if (rc != SAF_OK) return fail(rc, err);
+    p->packed_ready[2] = true;
     *out = p.release();
     return SAF_OK;
 }
@@ -123,9 +115,8 @@ extern "C" void saf_program_destroy(saf_program *p) {
     if (!p) return;
     for (auto &kv : p->copies) {
         int prev = 0;
-        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(kv.first) == cudaSuccess) {
-            cudaFree(kv.second.code);
-            cudaFree(kv.second.consts);
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(kv.first.first) == cudaSuccess) {
+            cudaFree(kv.second);
             cudaSetDevice(prev);
         }
     }
@@ -174,21 +165,32 @@ extern "C" int saf_program_export(const saf_program *p, uint64_t *code, size_t c
 }
 
 // ---- launch -------------------------------------------------------------------------------------------
-static int ensure_device_copy(saf_program *p, int device, DeviceCopy *out) {
+static int packed_for(saf_program *p, int P, const PackedProgram **out) {
+    const int li = layout_index(P);
     std::lock_guard<std::mutex> lk(p->mu);
-    auto it = p->copies.find(device);
+    if (!p->packed_ready[li]) {
+        std::string err;
+        int rc = pack_program(p->dev, P, p->packed[li], err);
+        if (rc != SAF_OK) return fail(rc, err);
+        p->packed_ready[li] = true;
+    }
+    *out = &p->packed[li];
+    return SAF_OK;
+}
+
+static int ensure_device_image(saf_program *p, int device, const PackedProgram &pk, const unsigned char **out) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    const auto key = std::make_pair(device, pk.points_per_thread);
+    auto it = p->copies.find(key);
     if (it != p->copies.end()) {
         *out = it->second;
         return SAF_OK;
     }
-    DeviceCopy c;
-    SAF_CUDA(cudaMalloc(&c.code, p->dev.code.size() * 8));
-    SAF_CUDA(cudaMalloc(&c.consts, std::max<size_t>(1, p->dev.consts.size()) * 8));
-    SAF_CUDA(cudaMemcpy(c.code, p->dev.code.data(), p->dev.code.size() * 8, cudaMemcpyHostToDevice));
-    if (!p->dev.consts.empty())
-        SAF_CUDA(cudaMemcpy(c.consts, p->dev.consts.data(), p->dev.consts.size() * 8, cudaMemcpyHostToDevice));
-    p->copies[device] = c;
-    *out = c;
+    unsigned char *dptr = nullptr;
+    SAF_CUDA(cudaMalloc(&dptr, pk.image.size() * 8));
+    SAF_CUDA(cudaMemcpy(dptr, pk.image.data(), pk.image.size() * 8, cudaMemcpyHostToDevice));
+    p->copies[key] = dptr;
+    *out = dptr;
     return SAF_OK;
 }
 
@@ -202,15 +204,11 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     std::memset(&d, 0, sizeof d);
     d.n_points = n_points;
     d.iters = iters ? iters : 1;
-    d.n_code = (uint32_t)dp.code.size();
-    d.n_consts = (uint32_t)dp.consts.size();
-    d.n_slots = dp.n_slots;
     d.n_params = dp.param_count;
     d.n_results = (uint32_t)dp.result_field.size();
     d.flags = flags;
     bool aligned = true;
     for (uint32_t j = 0; j < dp.param_count; ++j) {
-        d.param_slot[j] = dp.param_slot[j];
         if (j < n_cols && cols[j] != nullptr) {
             d.cols[j] = cols[j];
             d.col_len[j] = lens[j];
@@ -222,36 +220,71 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     }
     for (uint32_t k = 0; k < d.n_results; ++k) {
         d.outs[k] = outs[k];
-        d.result_field[k] = (uint16_t)dp.result_field[k];
         if ((uintptr_t)outs[k] & 15u) aligned = false;
     }
     int device = 0;
     SAF_CUDA(cudaGetDevice(&device));
-    const uint64_t *blob = nullptr;
-    size_t n_blob = 0;
-    if (prog->blob_fits) {
-        blob = prog->blob.data();
-        n_blob = prog->blob.size();
-    }
-    if (!prog->blob_fits || !prog->consts_in_blob) {
-        DeviceCopy c;
-        int rc = ensure_device_copy(const_cast<saf_program *>(prog), device, &c);
-        if (rc != SAF_OK) return rc;
-        d.code_global = c.code;
-        d.consts_global = c.consts;
-    }
-    LaunchShape shape;
     static const int forced_ppt = []() {
         const char *v = getenv("SAF_POINTS_PER_THREAD"); // tuning knob, see DESIGN.md
         return v ? atoi(v) : 0;
     }();
-    cudaError_t e = choose_shape(device, dp.n_slots, n_points, aligned, forced_ppt, &shape);
+    int P = 1;
+    cudaError_t e = choose_points_per_thread(device, dp.n_slots, n_points, aligned, forced_ppt, &P);
+    if (e == cudaErrorInvalidConfiguration)
+        return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
+    if (e != cudaSuccess) return cuda_fail(e, "choose_points_per_thread");
+    const PackedProgram *pk = nullptr;
+    int rc = packed_for(const_cast<saf_program *>(prog), P, &pk);
+    if (rc != SAF_OK) return rc;
+    d.code_off = pk->code_off;
+    d.n_slots = pk->n_slots;
+    d.x0_off = pk->x0_off;
+    d.x1_off = pk->x1_off;
+    for (uint32_t j = 0; j < dp.param_count; ++j) d.param_off[j] = pk->param_off[j];
+    for (uint32_t k = 0; k < d.n_results; ++k) {
+        d.result_off[k] = pk->result_off[k];
+        if (pk->result_is_k[k]) d.result_k_mask |= 1u << k;
+    }
+    const uint64_t *image = nullptr;
+    size_t n_image = 0;
+    if (pk->image.size() <= (size_t)BLOB_LARGE) {
+        image = pk->image.data();
+        n_image = pk->image.size();
+    } else {
+        rc = ensure_device_image(const_cast<saf_program *>(prog), device, *pk, &d.image_global);
+        if (rc != SAF_OK) return rc;
+    }
+    LaunchShape shape;
+    e = choose_shape(device, pk->n_slots, n_points, P, &shape);
     if (e == cudaErrorInvalidConfiguration)
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_shape");
-    e = launch_interpreter(d, blob, n_blob, prog->consts_in_blob, shape, stream);
+    e = launch_interpreter(d, image, n_image, shape, stream);
     if (e != cudaSuccess) return cuda_fail(e, "interpreter launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SAF_OK;
+}
+
+extern "C" int saf_program_export_packed(const saf_program *p, int points_per_thread, uint64_t *image, size_t cap_words,
+                                         size_t *n_words, uint32_t *code_off, uint32_t *n_slots, int32_t *x_off,
+                                         int32_t *param_off, int32_t *result_off, uint8_t *result_is_k) {
+    if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
+    if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4)
+        return fail(SAF_ERR_INVALID_ARGUMENT, "points_per_thread must be 1, 2 or 4");
+    const PackedProgram *pk = nullptr;
+    int rc = packed_for(const_cast<saf_program *>(p), points_per_thread, &pk);
+    if (rc != SAF_OK) return rc;
+    if (n_words) *n_words = pk->image.size();
+    if (image) std::memcpy(image, pk->image.data(), std::min(cap_words, pk->image.size()) * 8);
+    if (code_off) *code_off = pk->code_off;
+    if (n_slots) *n_slots = pk->n_slots;
+    if (x_off) {
+        x_off[0] = pk->x0_off;
+        x_off[1] = pk->x1_off;
+    }
+    if (param_off) std::copy(pk->param_off.begin(), pk->param_off.end(), param_off);
+    if (result_off) std::copy(pk->result_off.begin(), pk->result_off.end(), result_off);
+    if (result_is_k) std::copy(pk->result_is_k.begin(), pk->result_is_k.end(), result_is_k);
     return SAF_OK;
 }
 

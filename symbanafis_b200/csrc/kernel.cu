@@ -1,26 +1,30 @@
 // kernel.cu -- the sm_100a interpreter kernel for SymbAnaFis device programs.
 //
 // One thread evaluates P points (P = 1, 2 or 4), 128 threads per block.  Every lane of every warp runs
-// the SAME device program on different points, so the program counter, the fetched instruction word
-// and the opcode branch are warp-uniform: there is no divergence in the dispatch, only inside the
-// data-dependent loops of a few special functions.
+// the SAME program on different points, so the program counter, the fetched micro-instruction and the
+// opcode branch are warp-uniform: there is no divergence in the dispatch, only inside the data-dependent
+// slow paths of a few special functions.
 //
-//   program words + constants : kernel parameter space = constant bank (ConstBlob), read through the
-//                               constant cache with uniform addresses; global-memory fallback
-//                               (read-only path) for programs that do not fit
-//   live values ("registers")  : shared memory laid out [slot][pair][thread] as f64x2 (f64 for P=1):
-//                               consecutive lanes touch consecutive 16-byte words -> conflict free;
-//                               the slot stride is a compile-time constant (fixed block size)
-//   accumulator                : the result of the previous instruction stays in real registers; the
-//                               lowering (lower.cpp) routes single-use values through it so they
-//                               never touch shared memory
-//   dispatch                   : one dense switch over opcodes that are specialised by operand kind
-//                               for the cheap operations (no per-operand branches in their handlers);
-//                               P points per thread amortise it
-//   hot transcendentals        : issue-lean sin/cos/sincos/exp (leanmath.cuh), everything else from
-//                               the CUDA math library / devmath.cuh
-//   columns                    : struct-of-arrays f64, coalesced 128-bit loads/stores (64-bit for
-//                               P=1), streaming cache hints
+//   program image               : packed micro-instructions + constants (uop.h / pack.cpp) in the kernel
+//                                 parameter space = constant bank, read through the constant cache with
+//                                 uniform addresses; the NEXT instruction is fetched before the current
+//                                 one is dispatched (programs are straight-line), so the fetch latency is
+//                                 off the critical path; global-memory image (read-only path) for
+//                                 programs that do not fit
+//   live values ("registers")   : shared memory laid out [slot][pair][thread] as f64x2 (f64 for P=1):
+//                                 consecutive lanes touch consecutive 16-byte words -> conflict free;
+//                                 operands arrive as byte offsets: one integer add per access
+//   accumulator                 : the result of the previous instruction stays in real registers; the
+//                                 lowering (lower.cpp) routes single-use values through it so they
+//                                 never touch shared memory
+//   dispatch                    : one dense switch over micro-ops that are specialised by operand kind
+//                                 (S slot / K constant / A accumulator): handlers contain no operand
+//                                 decoding at all; P points per thread amortise the switch
+//   hot transcendentals         : issue-lean sin/cos/sincos/exp (leanmath.cuh: FP64 instructions plus
+//                                 three integer instructions per point), everything else from the CUDA
+//                                 math library / devmath.cuh
+//   columns                     : struct-of-arrays f64, coalesced 128-bit loads/stores (64-bit for
+//                                 P=1), streaming cache hints
 //
 // Arithmetic handlers use the explicit-rounding intrinsics (__dadd_rn, __dmul_rn, __fma_rn, ...) so
 // that nvcc can never contract a Mul followed by an Add: the reference distinguishes Mul;Add from
@@ -35,7 +39,7 @@
 
 // resident blocks per SM the register allocation aims for, per points-per-thread variant (tuning knobs)
 #ifndef SAF_MINB_P4
-#define SAF_MINB_P4 3
+#define SAF_MINB_P4 4
 #endif
 #ifndef SAF_MINB_P2
 #define SAF_MINB_P2 4
@@ -68,15 +72,13 @@ __device__ __forceinline__ void st_stream2(double *p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
-// Shared-memory register file.  For P >= 2 a thread's points are stored as P/2 pairs; pair g of slot i
-// lives at  i * SLOT_BYTES + g * PAIR_BYTES + tid * 16.  A field is index << 2 | kind, so
-// (field & ~3) * (SLOT_BYTES / 4) is the byte offset of an S field: one LOP3 + one IMAD.
+// Shared-memory register file.  For P >= 2 a thread's points are stored as P/2 pairs; pair g of the slot
+// at byte offset `off` lives at  off + g * PAIR_BYTES + tid * 16  (`my` already includes tid * 16).
 template <int P>
 struct Rf {
-    static constexpr uint32_t SLOT_BYTES = BLOCK_THREADS * P * 8;
     static constexpr uint32_t PAIR_BYTES = BLOCK_THREADS * 16;
-    __device__ __forceinline__ static void load(const char *my, uint32_t field, Pt<P> &o) {
-        const char *p = my + (field & 0xfffcu) * (SLOT_BYTES / 4);
+    __device__ __forceinline__ static void load(const char *my, uint32_t off, Pt<P> &o) {
+        const char *p = my + off;
         if constexpr (P == 1) {
             o.v[0] = *reinterpret_cast<const double *>(p);
         } else {
@@ -88,8 +90,8 @@ struct Rf {
             }
         }
     }
-    __device__ __forceinline__ static void store(char *my, uint32_t field, const Pt<P> &o) {
-        char *p = my + (field & 0xfffcu) * (SLOT_BYTES / 4);
+    __device__ __forceinline__ static void store(char *my, uint32_t off, const Pt<P> &o) {
+        char *p = my + off;
         if constexpr (P == 1) {
             *reinterpret_cast<double *>(p) = o.v[0];
         } else {
@@ -102,6 +104,8 @@ struct Rf {
 
 #define SAF_FOR_P _Pragma("unroll") for (int p = 0; p < P; ++p)
 
+__device__ __forceinline__ uint2 split64(unsigned long long w) { return make_uint2((uint32_t)w, (uint32_t)(w >> 32)); }
+
 } // namespace
 
 // Points of a thread.  P == 1: i = tile_base + tid.  P >= 2: pair g covers points
@@ -112,31 +116,22 @@ __device__ __forceinline__ unsigned long long point_index(unsigned long long til
     else return tile_base + (unsigned long long)(p >> 1) * (2 * BLOCK_THREADS) + 2 * threadIdx.x + (p & 1);
 }
 
-// CODE_IN_BLOB / K_IN_BLOB: program words / constants come from the constant bank (kernel
-// parameter `blob`), otherwise from global memory through the read-only path.
-template <int P, int WORDS, bool CODE_IN_BLOB, bool K_IN_BLOB>
+// IN_BLOB: the packed image comes from the constant bank (kernel parameter `blob`), otherwise from global
+// memory through the read-only path.
+template <int P, int WORDS, bool IN_BLOB>
 __global__ void __launch_bounds__(BLOCK_THREADS, (P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1))
 saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ ConstBlob<WORDS> blob) {
     extern __shared__ __align__(16) unsigned char saf_smem[];
     char *const my = reinterpret_cast<char *>(saf_smem) + threadIdx.x * (P == 1 ? 8 : 16);
     using RF = Rf<P>;
 
-    // trig coefficient table behind the register file
-    double *const trig_tab = reinterpret_cast<double *>(saf_smem + (size_t)d.n_slots * RF::SLOT_BYTES);
-    if (threadIdx.x < 14) trig_tab[threadIdx.x] = (&lm::kTrigTable[0][0])[threadIdx.x];
-    __syncthreads();
-
-    auto fetch_word = [&](uint32_t pc) -> uint2 {
-        unsigned long long w;
-        if constexpr (CODE_IN_BLOB) w = blob.w[pc];
-        else w = __ldg(reinterpret_cast<const unsigned long long *>(d.code_global) + pc);
-        return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+    auto img64 = [&](uint32_t off) -> unsigned long long { // 8 bytes of the image (warp-uniform address)
+        if constexpr (IN_BLOB)
+            return *reinterpret_cast<const unsigned long long *>(reinterpret_cast<const char *>(blob.w) + off);
+        else
+            return __ldg(reinterpret_cast<const unsigned long long *>(d.image_global + off));
     };
-    auto konst_at = [&](uint32_t idx) -> double { // constant table entry (warp-uniform load)
-        if constexpr (K_IN_BLOB) return __longlong_as_double((long long)blob.w[d.n_code + idx]);
-        else return __ldg(d.consts_global + idx);
-    };
-    auto konst = [&](uint32_t field) -> double { return konst_at(field >> KIND_BITS); };
+    auto konst = [&](uint32_t off) -> double { return __longlong_as_double((long long)img64(off)); };
 
     constexpr unsigned long long TILE = (unsigned long long)BLOCK_THREADS * P;
     const unsigned long long n_tiles = (d.n_points + TILE - 1) / TILE;
@@ -146,8 +141,8 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
 
         // ---- prologue: columns -> parameter slots (scalar.rs:182-207 rules) ----
         for (uint32_t j = 0; j < d.n_params; ++j) {
-            const uint32_t s = d.param_slot[j];
-            if (s == 0xffffu) continue;
+            const int32_t s = d.param_off[j];
+            if (s < 0) continue;
             const double *col = d.cols[j];
             const unsigned long long len = d.col_len[j];
             Pt<P> v;
@@ -169,25 +164,78 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
                     }
                 }
             }
-            RF::store(my, s << KIND_BITS, v);
+            RF::store(my, (uint32_t)s, v);
         }
 
-        Pt<P> acc, x0, x1;
-        SAF_FOR_P { acc.v[p] = 0.0; x0.v[p] = 0.0; x1.v[p] = 0.0; }
+        Pt<P> acc;
+        SAF_FOR_P acc.v[p] = 0.0;
 
         for (unsigned long long it = 0;;) {
-            // ---- the interpreter loop: warp-uniform pc / opcode ----
-            uint32_t pc = 0;
+            // ---- the interpreter loop: warp-uniform pc / micro-op ----
+            uint32_t pc = d.code_off;
+            uint2 q0 = split64(img64(pc)), q1 = split64(img64(pc + 8));
             for (;;) {
-                const uint2 w = fetch_word(pc++);
-                const uint32_t xop = w.x & 0xffu;
-                const uint32_t fd = w.x >> 16;
-                const uint32_t fa = w.y & 0xffffu;
-                const uint32_t fb = w.y >> 16;
+                const uint32_t uop = q0.x;
+                const int32_t fd = (int32_t)q0.y;
+                const uint32_t fa = q1.x, fb = q1.y;
+                const uint32_t cur = pc;
+                pc += UINSTR_BYTES;
+                // fetch the next instruction now: straight-line code, its latency hides behind this one
+                q0 = split64(img64(pc));
+                q1 = split64(img64(pc + 8));
 
-                // run-time operand fetch for the heavy opcodes
-                auto any = [&](uint32_t f, Pt<P> &o) {
-                    const uint32_t kind = f & KIND_MASK;
+                Pt<P> a, b, c;
+
+#define LS(x, f) RF::load(my, (f), x);
+#define LK(x, f) { const double k_ = konst(f); SAF_FOR_P x.v[p] = k_; }
+#define LA(x) x = acc;
+#define FC (split64(img64(cur + 16)).x) /* third operand offset */
+#define IMM (split64(img64(cur + 16)).y)
+#define KINDS (split64(img64(cur + 24)).x)
+
+// light unary: a from a slot / from ACC
+#define U1CASE(OP, EXPR)                                                                                   \
+    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY): LS(a, fa) SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } break;
+// heavy unary: {S, A} x {plain, affine prefix}; BODY maps a.v -> acc.v
+#define H1PREFIX { const double k1_ = konst(fb), k2_ = konst(fb + 8); SAF_FOR_P a.v[p] = __fma_rn(a.v[p], k1_, k2_); }
+#define H1CASE(H, BODY)                                                                                    \
+    case U_H1 + 4 * (H) + 0: LS(a, fa) { BODY } break;                                                     \
+    case U_H1 + 4 * (H) + 1: LA(a) { BODY } break;                                                         \
+    case U_H1 + 4 * (H) + 2: LS(a, fa) H1PREFIX { BODY } break;                                            \
+    case U_H1 + 4 * (H) + 3: LA(a) H1PREFIX { BODY } break;
+// commutative binary: SS SK SA KA AA
+#define BCCASE(I, EXPR)                                                                                    \
+    case U_BC + 5 * (I) + BC_SS: LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BC + 5 * (I) + BC_SK: LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BC + 5 * (I) + BC_SA: LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BC + 5 * (I) + BC_KA: { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BC + 5 * (I) + BC_AA: SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break;
+// ordered binary: SS SK KS SA AS KA AK AA
+#define BNCASE(I, EXPR)                                                                                    \
+    case U_BN + 8 * (I) + BN_SS: LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BN + 8 * (I) + BN_SK: LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BN + 8 * (I) + BN_KS: LS(b, fb) { const double x = konst(fa); SAF_FOR_P { const double y = b.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BN + 8 * (I) + BN_SA: LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BN + 8 * (I) + BN_AS: LS(b, fb) SAF_FOR_P { const double x = acc.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BN + 8 * (I) + BN_KA: { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BN + 8 * (I) + BN_AK: { const double y = konst(fb); SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BN + 8 * (I) + BN_AA: SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break;
+// fused multiply-add family: x * y (+/-) z
+#define TCASE(T, EXPR)                                                                                     \
+    case U_T + 10 * (T) + T_SSS: { const uint32_t fc = FC; LS(a, fa) LS(b, fb) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SSK: { const uint32_t fc = FC; LS(a, fa) LS(b, fb) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SSA: { LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SKS: { const uint32_t fc = FC; LS(a, fa) LS(c, fc) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SKK: { const uint32_t fc = FC; LS(a, fa) const double y = konst(fb), z = konst(fc); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SKA: { LS(a, fa) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SAS: { const uint32_t fc = FC; LS(a, fa) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SAK: { const uint32_t fc = FC; LS(a, fa) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_KAS: { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_KAK: { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break;
+
+                // run-time operand fetch of the generic micro-ops
+                auto any = [&](uint32_t kind, uint32_t f, Pt<P> &o) {
                     if (kind == KIND_S) {
                         RF::load(my, f, o);
                     } else if (kind == KIND_K) {
@@ -197,149 +245,111 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
                         o = acc;
                     }
                 };
-                // operand of a heavy unary opcode, with the optional affine prefix (saf_isa.h)
-                auto unary_arg = [&](Pt<P> &o) {
-                    any(fa, o);
-                    const uint32_t mode = (w.x >> 8) & 0xffu;
-                    if (mode != PREFIX_NONE) {
-                        const uint32_t ki = fb >> KIND_BITS;
-                        const double k1 = konst_at(ki);
-                        if (mode == PREFIX_MUL) {
-                            SAF_FOR_P o.v[p] = __dmul_rn(o.v[p], k1);
-                        } else {
-                            const double k2 = konst_at(ki + 1);
-                            SAF_FOR_P o.v[p] = __fma_rn(o.v[p], k1, k2);
-                        }
+
+                switch (uop) {
+                case U_END: goto program_end;
+                case U_LOADK: { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } break;
+
+                U1CASE(D_COPY, x)
+                U1CASE(D_NEG, -x)
+                U1CASE(D_SQUARE, __dmul_rn(x, x))
+                U1CASE(D_CUBE, __dmul_rn(__dmul_rn(x, x), x))
+                U1CASE(D_POW4, __dmul_rn(__dmul_rn(x, x), __dmul_rn(x, x)))
+                U1CASE(D_POW3_2, __dmul_rn(x, __dsqrt_rn(x)))
+                U1CASE(D_INVPOW3_2, __ddiv_rn(1.0, __dmul_rn(x, __dsqrt_rn(x))))
+                U1CASE(D_INVSQRT, __ddiv_rn(1.0, __dsqrt_rn(x)))
+                U1CASE(D_INVSQUARE, __ddiv_rn(1.0, __dmul_rn(x, x)))
+                U1CASE(D_INVCUBE, __ddiv_rn(1.0, __dmul_rn(__dmul_rn(x, x), x)))
+                U1CASE(D_RECIP, __ddiv_rn(1.0, x))
+                U1CASE(D_SQRT, __dsqrt_rn(x))
+
+                H1CASE(H1_SIN, lm::sin_n<P>(a.v, acc.v);)
+                H1CASE(H1_COS, lm::cos_n<P>(a.v, acc.v);)
+                H1CASE(H1_EXP, lm::exp_n<P>(a.v, acc.v);)
+                H1CASE(H1_LN, SAF_FOR_P acc.v[p] = log(a.v[p]);)
+                H1CASE(H1_RECIPEXPM1, SAF_FOR_P acc.v[p] = __ddiv_rn(1.0, expm1(a.v[p]));)
+                H1CASE(H1_EXPSQR, SAF_FOR_P a.v[p] = __dmul_rn(a.v[p], a.v[p]); lm::exp_n<P>(a.v, acc.v);)
+                H1CASE(H1_EXPSQRNEG, SAF_FOR_P a.v[p] = -__dmul_rn(a.v[p], a.v[p]); lm::exp_n<P>(a.v, acc.v);)
+                H1CASE(H1_EXPNEG, SAF_FOR_P a.v[p] = -a.v[p]; lm::exp_n<P>(a.v, acc.v);)
+                H1CASE(H1_SINCOS, {
+                    const int32_t fc = (int32_t)FC;
+                    lm::sincos_n<P>(a.v, acc.v, c.v);
+                    if (fc >= 0) RF::store(my, (uint32_t)fc, c);
+                })
+
+                BCCASE(BC_ADD, __dadd_rn(x, y))
+                BCCASE(BC_MUL, __dmul_rn(x, y))
+                BCCASE(BC_NEGMUL, -__dmul_rn(x, y))
+                BNCASE(BN_SUB, __dsub_rn(x, y))
+                BNCASE(BN_DIV, __ddiv_rn(x, y))
+
+                TCASE(T_FMA, __fma_rn(x, y, z))
+                TCASE(T_FMS, __fma_rn(x, y, -z))
+                TCASE(T_FNMA, __fma_rn(-x, y, z))
+                TCASE(T_FNMS, __fma_rn(-x, y, -z))
+
+                // ---- generic micro-ops (operand kinds decoded at run time) ----
+                case U_G + G_POW: {
+                    const uint32_t k = KINDS;
+                    any(k & 3u, fa, a); any((k >> 2) & 3u, fb, b);
+                    SAF_FOR_P acc.v[p] = pow(a.v[p], b.v[p]);
+                } break;
+                case U_G + G_DIV: {
+                    const uint32_t k = KINDS;
+                    any(k & 3u, fa, a); any((k >> 2) & 3u, fb, b);
+                    SAF_FOR_P acc.v[p] = __ddiv_rn(a.v[p], b.v[p]);
+                } break;
+                case U_G + G_POWI: {
+                    const uint32_t k = KINDS;
+                    const int n = (int)IMM;
+                    any(k & 3u, fa, a);
+                    SAF_FOR_P acc.v[p] = dm::powi(a.v[p], n).v;
+                } break;
+                case U_G + G_BUILTIN1: {
+                    const uint32_t k = KINDS, fn = IMM;
+                    any(k & 3u, fa, a);
+                    SAF_FOR_P acc.v[p] = dm::builtin1(fn, a.v[p]).v;
+                } break;
+                case U_G + G_BUILTIN2: {
+                    const uint32_t k = KINDS, fn = IMM;
+                    any(k & 3u, fa, a); any((k >> 2) & 3u, fb, b);
+                    SAF_FOR_P acc.v[p] = dm::builtin2(fn, a.v[p], b.v[p]).v;
+                } break;
+                case U_G + G_BUILTIN3: {
+                    const uint32_t k = KINDS, fn = IMM;
+                    any(k & 3u, fa, a);
+                    Pt<P> x0;
+                    RF::load(my, (uint32_t)d.x0_off, x0);
+                    RF::load(my, (uint32_t)d.x1_off, c);
+                    SAF_FOR_P acc.v[p] = dm::builtin3(fn, x0.v[p], c.v[p], a.v[p]).v;
+                } break;
+                case U_G + G_BUILTIN4: {
+                    const uint32_t k = KINDS, fn = IMM;
+                    any(k & 3u, fa, a); any((k >> 2) & 3u, fb, b);
+                    Pt<P> x0;
+                    RF::load(my, (uint32_t)d.x0_off, x0);
+                    RF::load(my, (uint32_t)d.x1_off, c);
+                    SAF_FOR_P acc.v[p] = dm::builtin4(fn, x0.v[p], c.v[p], a.v[p], b.v[p]).v;
+                } break;
+                case U_G + G_ARG2: { // stages two operands for the next Builtin3/4: ACC untouched
+                    const uint32_t k = KINDS;
+                    any(k & 3u, fa, a); any((k >> 2) & 3u, fb, b);
+                    RF::store(my, (uint32_t)d.x0_off, a);
+                    RF::store(my, (uint32_t)d.x1_off, b);
+                } break;
+                case U_G + G_FMA: case U_G + G_FMS: case U_G + G_FNMA: case U_G + G_FNMS: {
+                    const uint32_t k = KINDS, fc = FC;
+                    any(k & 3u, fa, a); any((k >> 2) & 3u, fb, b); any((k >> 4) & 3u, fc, c);
+                    const uint32_t t = uop - (U_G + G_FMA);
+                    SAF_FOR_P {
+                        const double x = (t & 2u) ? -a.v[p] : a.v[p];
+                        const double z = (t & 1u) ? -c.v[p] : c.v[p];
+                        acc.v[p] = __fma_rn(x, b.v[p], z);
                     }
-                };
-
-                Pt<P> a, b, r;
-
-#define SAF_A_S RF::load(my, fa, a);
-#define SAF_A_K { const double k_ = konst(fa); SAF_FOR_P a.v[p] = k_; }
-#define SAF_A_A a = acc;
-#define SAF_B_S RF::load(my, fb, b);
-#define SAF_B_K { const double k_ = konst(fb); SAF_FOR_P b.v[p] = k_; }
-#define SAF_B_A b = acc;
-// light unary: two forms (a from a slot / from ACC)
-#define SAF_ULIGHT(OP, EXPR)                                                                       \
-    case X_ULIGHT + 2 * ((OP) - D_FIRST_LIGHT_UNARY): SAF_A_S SAF_FOR_P { EXPR; } break;           \
-    case X_ULIGHT + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_A_A SAF_FOR_P { EXPR; } break;
-// light binary: eight forms (K,K is never emitted)
-#define SAF_BCASE(OP, KA, KB, LA, LB, EXPR)                                                        \
-    case X_BLIGHT + 9 * ((OP) - D_FIRST_LIGHT_BINARY) + 3 * (KA) + (KB): LA LB SAF_FOR_P { EXPR; } break;
-#define SAF_BLIGHT(OP, EXPR)                                                                       \
-    SAF_BCASE(OP, KIND_S, KIND_S, SAF_A_S, SAF_B_S, EXPR)                                          \
-    SAF_BCASE(OP, KIND_S, KIND_K, SAF_A_S, SAF_B_K, EXPR)                                          \
-    SAF_BCASE(OP, KIND_S, KIND_ACC, SAF_A_S, SAF_B_A, EXPR)                                        \
-    SAF_BCASE(OP, KIND_K, KIND_S, SAF_A_K, SAF_B_S, EXPR)                                          \
-    SAF_BCASE(OP, KIND_K, KIND_ACC, SAF_A_K, SAF_B_A, EXPR)                                        \
-    SAF_BCASE(OP, KIND_ACC, KIND_S, SAF_A_A, SAF_B_S, EXPR)                                        \
-    SAF_BCASE(OP, KIND_ACC, KIND_K, SAF_A_A, SAF_B_K, EXPR)                                        \
-    SAF_BCASE(OP, KIND_ACC, KIND_ACC, SAF_A_A, SAF_B_A, EXPR)
-#define SAF_UHEAVY(OP, EXPR)                                                                       \
-    case X_UHEAVY + ((OP) - D_FIRST_HEAVY_UNARY): unary_arg(a); SAF_FOR_P { EXPR; } break;
-#define SAF_BHEAVY(OP, EXPR)                                                                       \
-    case X_BHEAVY + ((OP) - D_FIRST_HEAVY_BINARY): any(fa, a); any(fb, b); SAF_FOR_P { EXPR; } break;
-#define SAF_TERN(OP, EXPR)                                                                         \
-    case X_TERN + ((OP) - D_FIRST_TERNARY): {                                                      \
-        const uint2 h = fetch_word(pc++);                                                          \
-        Pt<P> c;                                                                                   \
-        any(fa, a); any(fb, b); any(h.x & 0xffffu, c);                                             \
-        SAF_FOR_P { EXPR; }                                                                        \
-    } break;
-
-                switch (xop) {
-                case X_END: goto program_end;
-                case X_LOADK: SAF_A_K r = a; break;
-
-                SAF_ULIGHT(D_COPY, r.v[p] = a.v[p])
-                SAF_ULIGHT(D_NEG, r.v[p] = -a.v[p])
-                SAF_ULIGHT(D_SQUARE, r.v[p] = __dmul_rn(a.v[p], a.v[p]))
-                SAF_ULIGHT(D_CUBE, r.v[p] = __dmul_rn(__dmul_rn(a.v[p], a.v[p]), a.v[p]))
-                SAF_ULIGHT(D_POW4, double t_ = __dmul_rn(a.v[p], a.v[p]); r.v[p] = __dmul_rn(t_, t_))
-                SAF_ULIGHT(D_POW3_2, r.v[p] = __dmul_rn(a.v[p], __dsqrt_rn(a.v[p])))
-                SAF_ULIGHT(D_INVPOW3_2, r.v[p] = __ddiv_rn(1.0, __dmul_rn(a.v[p], __dsqrt_rn(a.v[p]))))
-                SAF_ULIGHT(D_INVSQRT, r.v[p] = __ddiv_rn(1.0, __dsqrt_rn(a.v[p])))
-                SAF_ULIGHT(D_INVSQUARE, r.v[p] = __ddiv_rn(1.0, __dmul_rn(a.v[p], a.v[p])))
-                SAF_ULIGHT(D_INVCUBE, r.v[p] = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(a.v[p], a.v[p]), a.v[p])))
-                SAF_ULIGHT(D_RECIP, r.v[p] = __ddiv_rn(1.0, a.v[p]))
-                SAF_ULIGHT(D_SQRT, r.v[p] = __dsqrt_rn(a.v[p]))
-
-                case X_UHEAVY + (D_SIN - D_FIRST_HEAVY_UNARY): unary_arg(a); lm::sin_n<P>(a.v, r.v, trig_tab); break;
-                case X_UHEAVY + (D_COS - D_FIRST_HEAVY_UNARY): unary_arg(a); lm::cos_n<P>(a.v, r.v, trig_tab); break;
-                case X_UHEAVY + (D_EXP - D_FIRST_HEAVY_UNARY): unary_arg(a); lm::exp_n<P>(a.v, r.v); break;
-                SAF_UHEAVY(D_LN, r.v[p] = log(a.v[p]))
-                SAF_UHEAVY(D_RECIPEXPM1, r.v[p] = __ddiv_rn(1.0, expm1(a.v[p])))
-                case X_UHEAVY + (D_EXPSQR - D_FIRST_HEAVY_UNARY):
-                    unary_arg(a);
-                    SAF_FOR_P a.v[p] = __dmul_rn(a.v[p], a.v[p]);
-                    lm::exp_n<P>(a.v, r.v);
-                    break;
-                case X_UHEAVY + (D_EXPSQRNEG - D_FIRST_HEAVY_UNARY):
-                    unary_arg(a);
-                    SAF_FOR_P a.v[p] = -__dmul_rn(a.v[p], a.v[p]);
-                    lm::exp_n<P>(a.v, r.v);
-                    break;
-                case X_UHEAVY + (D_EXPNEG - D_FIRST_HEAVY_UNARY):
-                    unary_arg(a);
-                    SAF_FOR_P a.v[p] = -a.v[p];
-                    lm::exp_n<P>(a.v, r.v);
-                    break;
-                case X_UHEAVY + (D_SINCOS - D_FIRST_HEAVY_UNARY): {
-                    const uint2 h = fetch_word(pc++);
-                    unary_arg(a);
-                    Pt<P> cs;
-                    lm::sincos_n<P>(a.v, r.v, cs.v, trig_tab);
-                    if ((h.x & KIND_MASK) == KIND_S) RF::store(my, h.x & 0xffffu, cs);
                 } break;
-                case X_UHEAVY + (D_BUILTIN1 - D_FIRST_HEAVY_UNARY): {
-                    const uint2 h = fetch_word(pc++);
-                    any(fa, a);
-                    SAF_FOR_P r.v[p] = dm::builtin1(h.y, a.v[p]).v;
-                } break;
-                case X_UHEAVY + (D_BUILTIN3 - D_FIRST_HEAVY_UNARY): {
-                    const uint2 h = fetch_word(pc++);
-                    any(fa, a);
-                    SAF_FOR_P r.v[p] = dm::builtin3(h.y, x0.v[p], x1.v[p], a.v[p]).v;
-                } break;
-
-                SAF_BLIGHT(D_ADD, r.v[p] = __dadd_rn(a.v[p], b.v[p]))
-                SAF_BLIGHT(D_SUB, r.v[p] = __dsub_rn(a.v[p], b.v[p]))
-                SAF_BLIGHT(D_MUL, r.v[p] = __dmul_rn(a.v[p], b.v[p]))
-                SAF_BLIGHT(D_NEGMUL, r.v[p] = -__dmul_rn(a.v[p], b.v[p]))
-
-                SAF_BHEAVY(D_DIV, r.v[p] = __ddiv_rn(a.v[p], b.v[p]))
-                SAF_BHEAVY(D_POW, r.v[p] = pow(a.v[p], b.v[p]))
-                case X_BHEAVY + (D_POWI - D_FIRST_HEAVY_BINARY): {
-                    const uint2 h = fetch_word(pc++);
-                    any(fa, a);
-                    const int n = (int)h.y;
-                    SAF_FOR_P r.v[p] = dm::powi(a.v[p], n).v;
-                } break;
-                case X_BHEAVY + (D_BUILTIN2 - D_FIRST_HEAVY_BINARY): {
-                    const uint2 h = fetch_word(pc++);
-                    any(fa, a); any(fb, b);
-                    SAF_FOR_P r.v[p] = dm::builtin2(h.y, a.v[p], b.v[p]).v;
-                } break;
-                case X_BHEAVY + (D_BUILTIN4 - D_FIRST_HEAVY_BINARY): {
-                    const uint2 h = fetch_word(pc++);
-                    any(fa, a); any(fb, b);
-                    SAF_FOR_P r.v[p] = dm::builtin4(h.y, x0.v[p], x1.v[p], a.v[p], b.v[p]).v;
-                } break;
-                case X_BHEAVY + (D_ARG2 - D_FIRST_HEAVY_BINARY):
-                    any(fa, x0);
-                    any(fb, x1);
-                    continue; // stages operands only: ACC and slots untouched
-
-                SAF_TERN(D_FMA, r.v[p] = __fma_rn(a.v[p], b.v[p], c.v[p]))
-                SAF_TERN(D_FMS, r.v[p] = __fma_rn(a.v[p], b.v[p], -c.v[p]))
-                SAF_TERN(D_FNMA, r.v[p] = __fma_rn(-a.v[p], b.v[p], c.v[p]))
-                SAF_TERN(D_FNMS, r.v[p] = __fma_rn(-a.v[p], b.v[p], -c.v[p]))
-                default: SAF_FOR_P r.v[p] = dm::nan_(); break;
+                default: SAF_FOR_P acc.v[p] = dm::nan_(); break;
                 }
-                acc = r;
-                if ((fd & KIND_MASK) == KIND_S) RF::store(my, fd, r);
+                if (fd >= 0) RF::store(my, (uint32_t)fd, acc);
             }
         program_end:
 
@@ -347,29 +357,27 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d, const __grid_constant__ 
             // ---- in-kernel feedback: parameter j <- result j (result slots never alias parameter
             // slots, lower.cpp), state stays on chip between iterations ----
             for (uint32_t j = 0; j < d.n_params; ++j) {
-                const uint32_t s = d.param_slot[j];
-                if (s == 0xffffu) continue;
-                const uint32_t f = d.result_field[j];
+                const int32_t s = d.param_off[j];
+                if (s < 0) continue;
                 Pt<P> v;
-                if ((f & KIND_MASK) == KIND_S) {
-                    RF::load(my, f, v);
-                } else {
-                    const double k = konst(f);
+                if ((d.result_k_mask >> j) & 1u) {
+                    const double k = konst((uint32_t)d.result_off[j]);
                     SAF_FOR_P v.v[p] = k;
+                } else {
+                    RF::load(my, (uint32_t)d.result_off[j], v);
                 }
-                RF::store(my, s << KIND_BITS, v);
+                RF::store(my, (uint32_t)s, v);
             }
         }
 
         // ---- epilogue: result slots -> output columns ----
         for (uint32_t k = 0; k < d.n_results; ++k) {
-            const uint32_t f = d.result_field[k];
             Pt<P> v;
-            if ((f & KIND_MASK) == KIND_S) {
-                RF::load(my, f, v);
-            } else {
-                const double kv = konst(f);
+            if ((d.result_k_mask >> k) & 1u) {
+                const double kv = konst((uint32_t)d.result_off[k]);
                 SAF_FOR_P v.v[p] = kv;
+            } else {
+                RF::load(my, (uint32_t)d.result_off[k], v);
             }
             double *out = d.outs[k];
             if constexpr (P == 1) {
@@ -417,10 +425,10 @@ cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t s
 
 // ---- host side -------------------------------------------------------------------------------------
 
-template <int P, int WORDS, bool CODE_IN_BLOB, bool K_IN_BLOB>
-static cudaError_t launch_one(const LaunchDesc &desc, const uint64_t *words, size_t n_words,
-                              const LaunchShape &shape, cudaStream_t stream) {
-    auto kern = saf_interp_kernel<P, WORDS, CODE_IN_BLOB, K_IN_BLOB>;
+template <int P, int WORDS, bool IN_BLOB>
+static cudaError_t launch_one(const LaunchDesc &desc, const uint64_t *image, size_t n_words, const LaunchShape &shape,
+                              cudaStream_t stream) {
+    auto kern = saf_interp_kernel<P, WORDS, IN_BLOB>;
     // opt in once per (instantiation, device) to the full dynamic shared-memory carve-out
     static bool configured[64] = {};
     int dev = 0;
@@ -435,76 +443,86 @@ static cudaError_t launch_one(const LaunchDesc &desc, const uint64_t *words, siz
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     ConstBlob<WORDS> blob;
-    if (CODE_IN_BLOB) {
-        for (size_t i = 0; i < n_words; ++i) blob.w[i] = words[i];
+    if (IN_BLOB) {
+        for (size_t i = 0; i < n_words; ++i) blob.w[i] = image[i];
+        for (size_t i = n_words; i < (size_t)WORDS; ++i) blob.w[i] = 0;
+    } else {
+        blob.w[0] = 0;
     }
     kern<<<shape.grid, shape.block, shape.smem_bytes, stream>>>(desc, blob);
     return cudaGetLastError();
 }
 
 template <int P>
-static cudaError_t launch_p(const LaunchDesc &desc, const uint64_t *words, size_t n_words, bool consts_in_blob,
-                            const LaunchShape &shape, cudaStream_t stream) {
-    if (words == nullptr || n_words > (size_t)BLOB_LARGE)
-        return launch_one<P, 1, false, false>(desc, nullptr, 0, shape, stream);
-    if (!consts_in_blob) return launch_one<P, BLOB_LARGE, true, false>(desc, words, n_words, shape, stream);
-    if (n_words <= (size_t)BLOB_SMALL) return launch_one<P, BLOB_SMALL, true, true>(desc, words, n_words, shape, stream);
-    return launch_one<P, BLOB_LARGE, true, true>(desc, words, n_words, shape, stream);
+static cudaError_t launch_p(const LaunchDesc &desc, const uint64_t *image, size_t n_words, const LaunchShape &shape,
+                            cudaStream_t stream) {
+    if (image == nullptr || n_words > (size_t)BLOB_LARGE) return launch_one<P, 1, false>(desc, nullptr, 0, shape, stream);
+    if (n_words <= (size_t)BLOB_SMALL) return launch_one<P, BLOB_SMALL, true>(desc, image, n_words, shape, stream);
+    return launch_one<P, BLOB_LARGE, true>(desc, image, n_words, shape, stream);
 }
 
-cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *blob_words, size_t n_blob_words,
-                               bool consts_in_blob, const LaunchShape &shape, cudaStream_t stream) {
+cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *image, size_t n_image_words,
+                               const LaunchShape &shape, cudaStream_t stream) {
     switch (shape.points_per_thread) {
-    case 4: return launch_p<4>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
-    case 2: return launch_p<2>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
-    default: return launch_p<1>(desc, blob_words, n_blob_words, consts_in_blob, shape, stream);
+    case 4: return launch_p<4>(desc, image, n_image_words, shape, stream);
+    case 2: return launch_p<2>(desc, image, n_image_words, shape, stream);
+    default: return launch_p<1>(desc, image, n_image_words, shape, stream);
     }
 }
 
 size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread) {
-    return (size_t)n_slots * (size_t)BLOCK_THREADS * (size_t)points_per_thread * 8 + 128; // + trig table
+    return (size_t)n_slots * (size_t)BLOCK_THREADS * (size_t)points_per_thread * 8;
 }
 
-cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
-                         int force_points_per_thread, LaunchShape *shape) {
+static int resident_blocks_for(int P) { return P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1; }
+
+cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
+                                     int force_points_per_thread, int *points_per_thread) {
     int sms = 0, smem_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
     const size_t smem_sm = (size_t)smem_optin; // per-block opt-in limit ~= per-SM capacity minus 1 KB
-    const int block = BLOCK_THREADS;
-
     // More points per thread amortise the dispatch; they need (a) 16-byte aligned columns, (b) enough
     // points to still give every SM several blocks, (c) a register file that leaves >= 2 blocks per SM.
+    // n_slots + 2: room for the staging slots the packer may add.
     auto fits = [&](int p, int min_blocks) {
-        return interpreter_smem_bytes(n_slots, p) * (size_t)min_blocks <= smem_sm;
+        return (interpreter_smem_bytes(n_slots + 2, p) + 1024) * (size_t)min_blocks <= smem_sm + 1024;
     };
     auto enough = [&](int p) {
-        return n_points >= (unsigned long long)sms * 3ull * (unsigned long long)block * (unsigned long long)p;
+        return n_points >= (unsigned long long)sms * 3ull * (unsigned long long)BLOCK_THREADS * (unsigned long long)p;
     };
     int P = 1;
     if (aligned16 && enough(4) && fits(4, 2)) P = 4;
     else if (aligned16 && enough(2) && fits(2, 2)) P = 2;
     if (force_points_per_thread == 1 || (aligned16 && (force_points_per_thread == 2 || force_points_per_thread == 4)))
         P = force_points_per_thread;
-    if (!fits(P, 1)) {
-        P = 1;
-        if (!fits(1, 1)) return cudaErrorInvalidConfiguration;
-    }
+    while (P > 1 && !fits(P, 1)) P >>= 1;
+    if (!fits(P, 1)) return cudaErrorInvalidConfiguration;
+    *points_per_thread = P;
+    return cudaSuccess;
+}
 
+cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, int P, LaunchShape *shape) {
+    int sms = 0, smem_optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return e;
     const size_t smem = interpreter_smem_bytes(n_slots, P);
-    size_t resident = (P == 4) ? SAF_MINB_P4 : (P == 2) ? SAF_MINB_P2 : SAF_MINB_P1; // __launch_bounds__ budget
-    size_t by_smem = (smem_sm + 1024) / (smem + 1024);
+    if (smem > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
+    size_t resident = (size_t)resident_blocks_for(P); // __launch_bounds__ register budget
+    const size_t by_smem = ((size_t)smem_optin + 1024) / (smem + 1024);
     if (by_smem < resident) resident = by_smem;
     if (resident < 1) resident = 1;
-    const unsigned long long tile = (unsigned long long)block * P;
+    const unsigned long long tile = (unsigned long long)BLOCK_THREADS * P;
     const unsigned long long n_tiles = (n_points + tile - 1) / tile;
     unsigned long long grid = (unsigned long long)sms * resident;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     shape->points_per_thread = P;
-    shape->block = block;
+    shape->block = BLOCK_THREADS;
     shape->grid = (int)grid;
     shape->smem_bytes = smem;
     return cudaSuccess;

@@ -4,37 +4,39 @@
 #include <cuda_runtime.h>
 
 #include "saf_isa.h"
+#include "uop.h"
 
 namespace saf {
 
-// Everything the kernel needs besides the program words, passed by value in the kernel parameter
-// (constant) bank.
+// Everything the kernel needs besides the program image, passed by value in the kernel parameter
+// (constant) bank.  Offsets are BYTES: register-file offsets are relative to the block's shared
+// memory, image offsets relative to the start of the packed image (pack.h).
 struct LaunchDesc {
     unsigned long long n_points;
     unsigned long long iters;            // >= 1; > 1 only for saf_iterate_*
-    const uint64_t *code_global;         // device words in global memory (used when the program does
-    const double *consts_global;         //   not fit the constant-bank blob)
-    uint32_t n_code;                     // device words including D_END
-    uint32_t n_consts;
-    uint32_t n_slots;
+    const unsigned char *image_global;   // packed image in global memory (programs that do not fit the blob)
+    uint32_t code_off;                   // first micro-instruction in the image
+    uint32_t n_slots;                    // register-file slots (incl. staging slots)
     uint32_t n_params;                   // columns the program can read (param_count)
     uint32_t n_results;
     uint32_t flags;                      // SAF_EVAL_BROADCAST
+    uint32_t result_k_mask;              // bit k: result k is a constant (result_off = image offset)
+    int32_t x0_off, x1_off;              // staging slots of Builtin3/4 operands
     const double *cols[MAX_COLS];        // device column base pointers (nullptr = missing -> 0.0)
     unsigned long long col_len[MAX_COLS];
     double *outs[MAX_OUTS];
-    uint16_t param_slot[MAX_COLS];       // slot of each parameter (0xffff = never read)
-    uint16_t result_field[MAX_OUTS];     // S / K field of each result
+    int32_t param_off[MAX_COLS];         // register-file offset of each parameter (-1 = never read)
+    int32_t result_off[MAX_OUTS];
 };
 
-// Program words + constants staged in the kernel parameter space, i.e. the constant bank: fetched
-// through the constant cache with warp-uniform addresses, off the shared-memory / L1 data path.
+// Packed image staged in the kernel parameter space, i.e. the constant bank: fetched through the
+// constant cache with warp-uniform addresses, off the shared-memory / L1 data path.
 template <int WORDS>
 struct ConstBlob {
-    uint64_t w[WORDS]; // [0, n_code) device words, then n_consts f64 bit patterns
+    uint64_t w[WORDS];
 };
 
-// Blob size classes (8-byte words).  With LaunchDesc (< 1 KB) the largest stays under the 32764-byte
+// Blob size classes (8-byte words).  With LaunchDesc (~1.1 KB) the largest stays under the 32764-byte
 // kernel parameter limit of CUDA 12.1+.
 constexpr int BLOB_SMALL = 448;
 constexpr int BLOB_LARGE = 3840;
@@ -46,16 +48,18 @@ struct LaunchShape {
     size_t smem_bytes;
 };
 
-// Launches the interpreter.  `blob_words` holds the code words (followed by the constants when
-// `consts_in_blob`) if they fit BLOB_LARGE; otherwise pass nullptr and the kernel reads
-// desc.code_global / desc.consts_global.
-cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *blob_words, size_t n_blob_words,
-                               bool consts_in_blob, const LaunchShape &shape, cudaStream_t stream);
+// Launches the interpreter.  `image` (host) is copied into the constant-bank blob when it fits BLOB_LARGE
+// words; otherwise desc.image_global must point at a device copy.
+cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *image, size_t n_image_words,
+                               const LaunchShape &shape, cudaStream_t stream);
 
-// Picks points-per-thread / grid for a program with n_slots live values on `device`.
+// Points per thread for a program with n_slots live values (before staging slots) on `device`.
 // force_points_per_thread: 0 = automatic, 1 / 2 / 4 = tuning override (SAF_POINTS_PER_THREAD).
-cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
-                         int force_points_per_thread, LaunchShape *shape);
+cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
+                                     int force_points_per_thread, int *points_per_thread);
+// Grid / shared memory for the packed program's n_slots.
+cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, int points_per_thread,
+                         LaunchShape *shape);
 size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread);
 
 // FP64-pipe peak probe: blocks x 256 threads, each `iters` x 64 dependent-chain DFMAs.

@@ -1,77 +1,83 @@
 // leanmath.cuh -- issue-lean f64 sin / cos / sincos / exp for the interpreter's hottest opcodes.
 //
 // Why not libdevice here: the FP64 pipe of an SM accepts one warp instruction every two cycles, so a
-// kernel is FP64-bound only while (all instructions) <= 2 x (FP64 instructions).  libdevice's sin
-// executes ~52 instructions per point for 15 FP64 ones (constant materialisation through UMOV pairs,
-// 64-bit table addressing + 3 global loads, FSEL selects, special-case plumbing; ncu source view in
-// profiles/r01_a_*).  The kernels below do the same mathematics -- 3-term Cody-Waite reduction by
-// pi/2, fdlibm-grade minimax kernels on [-pi/4, pi/4], coefficient choice by quadrant parity -- in
-// ~30 instructions: coefficients come from a 128-byte shared-memory table (one conflict-free LDS.64
-// per coefficient: the sin and cos entries of a term sit in different banks), the sign is an XOR.
+// kernel is FP64-bound only while (all instructions) <= 2 x (FP64 instructions), and the integer/select
+// pipe is just as narrow.  libdevice's sin executes ~52 instructions per point for 15 FP64 ones
+// (constant materialisation, table addressing + 3 loads, FSEL selects, special-case plumbing; ncu source
+// view in profiles/r01_a_*); a quadrant-selecting kernel needs two selects per coefficient.  The kernels
+// below contain NO loads, selects or conversions -- FP64 instructions with constant-bank coefficients plus
+// three integer instructions per point:
 //
-// Accuracy (tools/leanmath_check.c, 4M points per decade, vs glibc): sin <= 1 ulp, cos <= 2 ulp for
-// |x| <= 1e6, exp <= 1 ulp on [-700, 700].  Outside the fast range (|x| >= 2^20, zeros/denormals for
-// sin so that sin(-0.0) = -0.0, |x| > 700 for exp, NaN/Inf) the CUDA math library is called, so
-// special-value behaviour is exactly libdevice's.
+//   sin(x) = (-1)^k sin(r),      k = rint(x / pi),          r = x - k pi           |r| <= pi/2
+//   cos(x) = (-1)^(k+1) sin(r),  k = rint(x / pi - 1/2),    r = x - (k + 1/2) pi
+//   rint by the 1.5 * 2^52 trick (k sits in the low word of the biased sum), three-term Cody-Waite
+//   reduction with FMAs (pi split into three POSITIVE parts so that -0 survives: sin(-0) = -0),
+//   sin(r) = r + r z P(z), z = r^2, P = degree-7 fit of (sin r - r) / r^3 on |r| <= 1.0002 pi/2
+//   (Chebyshev nodes, 60-digit arithmetic: tools/fit_leanmath.py; |P error| z < 1e-18),
+//   sign of the result = sign of the (parity-flipped) reduced argument, so zeros keep their sign.
+//   exp(x) = 2^k (1 + r + r^2 Q(r)),  k = rint(x log2 e),  r = x - k ln2 (hi + lo), Q degree 10.
+//
+// Accuracy (tools/leanmath_check.c replays the same operation sequences on the CPU with C99 fma, 4M points
+// per range, against 80-bit libm): sin <= 1.96 ulp, cos <= 2.04 ulp for |x| < 2^20, exp <= 0.86 ulp on
+// [-700, 700]; against glibc's double functions (what the reference calls): <= 2 / 2 / 1 ulp.  Zero,
+// denormal and -0 arguments go through the fast path with the exact libm result.  Outside the fast range
+// (|x| >= 2^20, |x| >= 700 for exp, Inf, NaN) the CUDA math library is called, so special-value
+// behaviour there is exactly libdevice's.
 #pragma once
 #include <cstdint>
 
 namespace saf {
 namespace lm {
 
-// [term j][0 = sin kernel, 1 = cos kernel], highest degree first; the sin kernel has one term fewer.
-// sin(r) = r + (z r) * Ps(z),  cos(r) = 1 + z * Pc(z),  z = r^2   (fdlibm k_sin.c / k_cos.c coefficients)
-__device__ __constant__ double kTrigTable[7][2] = {
-    {0.0, -1.13596475577881948265e-11},
-    {1.58969099521155010221e-10, 2.08757232129817482790e-09},
-    {-2.50507602534068634195e-08, -2.75573143513906633035e-07},
-    {2.75573137070700676789e-06, 2.48015872894767294178e-05},
-    {-1.98412698298579493134e-04, -1.38888888888741095749e-03},
-    {8.33333333332248946124e-03, 4.16666666666666019037e-02},
-    {-1.66666666666666324348e-01, -0.5},
-};
-constexpr int kTrigTableBytes = 7 * 2 * 8;
+constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52
+constexpr double kInvPi = 3.18309886183790691e-01;
+constexpr double kPiA = 3.14159265358979312e+00;
+constexpr double kPiB = 1.22464679914735296e-16; // rounded DOWN: every part of the split is positive
+constexpr double kPiC = 2.16571334784382806e-32;
 
-constexpr double kTwoOverPi = 6.36619772367581382433e-01;
-constexpr double kPio2_1 = 1.57079632679489655800e+00;
-constexpr double kPio2_2 = 6.12323399573676603587e-17;
-constexpr double kPio2_3 = -1.49738490485916983249e-33;
+constexpr double kS0 = -1.66666666666666657e-01, kS1 = 8.33333333333331587e-03, kS2 = -1.98412698412549389e-04,
+                 kS3 = 2.75573192191536246e-06, kS4 = -2.50521076157725835e-08, kS5 = 1.60589772331473175e-10,
+                 kS6 = -7.64396776493426846e-13, kS7 = 2.73141320376900007e-15;
 
-// true when x is outside the fast range of the trig kernels: zero, denormal, |x| >= 2^20, Inf, NaN
+// |x| outside the fast range of the trig kernels: >= 2^20, Inf, NaN
 __device__ __forceinline__ bool trig_slow(double x) {
-    const uint32_t hi = (uint32_t)__double2hiint(x) & 0x7fffffffu;
-    return (hi - 0x00100000u) >= (0x41300000u - 0x00100000u);
+    return ((uint32_t)__double2hiint(x) & 0x7fffffffu) >= 0x41300000u;
 }
 
-// q = nearest integer to x*2/pi (low bits), r = x - q*pi/2
-__device__ __forceinline__ double trig_reduce(double x, int &q) {
-    q = __double2int_rn(__dmul_rn(x, kTwoOverPi));
-    const double kd = __int2double_rn(q);
-    double r = __fma_rn(kd, -kPio2_1, x);
-    r = __fma_rn(kd, -kPio2_2, r);
-    r = __fma_rn(kd, -kPio2_3, r);
-    return r;
-}
-
-// sin kernel if (q & 1) == 0, cos kernel otherwise; sign flipped when q & 2.  `tab` = shared-memory copy
-// of kTrigTable (generic pointer into shared memory).
-__device__ __forceinline__ double trig_eval(double r, int q, const double *tab) {
-    const double *t = tab + (q & 1);
+// (-1)^k sin(r) for |r| <= pi/2 (a little beyond is fine); k in the low bit of `k`
+__device__ __forceinline__ double sin_kernel(double r, uint32_t k) {
+    // sin is odd: fold the parity into the argument
+    const int rhi = __double2hiint(r) ^ (int)(k << 31);
+    r = __hiloint2double(rhi, __double2loint(r));
     const double z = __dmul_rn(r, r);
-    double p = t[0];
-    p = __fma_rn(p, z, t[2]);
-    p = __fma_rn(p, z, t[4]);
-    p = __fma_rn(p, z, t[6]);
-    p = __fma_rn(p, z, t[8]);
-    p = __fma_rn(p, z, t[10]);
-    p = __fma_rn(p, z, t[12]);
-    const bool odd = q & 1;
-    const double m = odd ? z : __dmul_rn(z, r);
-    const double c = odd ? 1.0 : r;
-    const double v = __fma_rn(p, m, c);
-    // sign: flip when bit 1 of q is set
-    const int hi = __double2hiint(v) ^ ((q & 2) << 30);
-    return __hiloint2double(hi, __double2loint(v));
+    double p = kS7;
+    p = __fma_rn(p, z, kS6);
+    p = __fma_rn(p, z, kS5);
+    p = __fma_rn(p, z, kS4);
+    p = __fma_rn(p, z, kS3);
+    p = __fma_rn(p, z, kS2);
+    p = __fma_rn(p, z, kS1);
+    p = __fma_rn(p, z, kS0);
+    const double v = __fma_rn(__dmul_rn(r, z), p, r);
+    // the result carries the sign of r; only differs from v for r = -0, where the fma yields +0
+    return __hiloint2double(__double2hiint(v) | (rhi & (int)0x80000000), __double2loint(v));
+}
+
+__device__ __forceinline__ double sin_fast(double x) {
+    const double t = __fma_rn(x, kInvPi, kMagic);
+    const double kd = __dsub_rn(t, kMagic);
+    double r = __fma_rn(kd, -kPiA, x);
+    r = __fma_rn(kd, -kPiB, r);
+    r = __fma_rn(kd, -kPiC, r);
+    return sin_kernel(r, (uint32_t)__double2loint(t));
+}
+__device__ __forceinline__ double cos_fast(double x) {
+    const double t = __dadd_rn(__fma_rn(x, kInvPi, -0.5), kMagic);
+    const double hd = __dadd_rn(__dsub_rn(t, kMagic), 0.5);
+    double r = __fma_rn(hd, -kPiA, x);
+    r = __fma_rn(hd, -kPiB, r);
+    r = __fma_rn(hd, -kPiC, r);
+    return sin_kernel(r, (uint32_t)__double2loint(t) + 1u);
 }
 
 // ---- P-wide entry points -------------------------------------------------------------------------
@@ -80,70 +86,95 @@ __device__ __forceinline__ double trig_eval(double r, int q, const double *tab) 
 // range are then recomputed one by one with the CUDA math library.  Every point's result depends only
 // on its own input -- never on which other points share the thread.
 template <int P>
-__device__ __forceinline__ void sin_n(const double (&x)[P], double (&out)[P], const double *tab) {
+__device__ __forceinline__ void sin_n(const double (&x)[P], double (&out)[P]) {
+    bool slow = false;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        int q;
-        const double r = trig_reduce(x[p], q);
-        out[p] = trig_eval(r, q, tab);
+        out[p] = sin_fast(x[p]);
+        slow |= trig_slow(x[p]);
     }
+    if (slow) {
 #pragma unroll
-    for (int p = 0; p < P; ++p)
-        if (trig_slow(x[p])) out[p] = ::sin(x[p]);
+        for (int p = 0; p < P; ++p)
+            if (trig_slow(x[p])) out[p] = ::sin(x[p]);
+    }
 }
 template <int P>
-__device__ __forceinline__ void cos_n(const double (&x)[P], double (&out)[P], const double *tab) {
+__device__ __forceinline__ void cos_n(const double (&x)[P], double (&out)[P]) {
+    bool slow = false;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        int q;
-        const double r = trig_reduce(x[p], q);
-        out[p] = trig_eval(r, q + 1, tab);
+        out[p] = cos_fast(x[p]);
+        slow |= trig_slow(x[p]);
     }
+    if (slow) {
 #pragma unroll
-    for (int p = 0; p < P; ++p)
-        if (trig_slow(x[p])) out[p] = ::cos(x[p]);
+        for (int p = 0; p < P; ++p)
+            if (trig_slow(x[p])) out[p] = ::cos(x[p]);
+    }
 }
 template <int P>
-__device__ __forceinline__ void sincos_n(const double (&x)[P], double (&s)[P], double (&c)[P], const double *tab) {
+__device__ __forceinline__ void sincos_n(const double (&x)[P], double (&s)[P], double (&c)[P]) {
+    bool slow = false;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        int q;
-        const double r = trig_reduce(x[p], q);
-        s[p] = trig_eval(r, q, tab);
-        c[p] = trig_eval(r, q + 1, tab);
+        s[p] = sin_fast(x[p]);
+        c[p] = cos_fast(x[p]);
+        slow |= trig_slow(x[p]);
     }
+    if (slow) {
 #pragma unroll
-    for (int p = 0; p < P; ++p)
-        if (trig_slow(x[p])) ::sincos(x[p], &s[p], &c[p]);
+        for (int p = 0; p < P; ++p)
+            if (trig_slow(x[p])) ::sincos(x[p], &s[p], &c[p]);
+    }
 }
 
-// exp: k = rint(x log2 e), r = x - k ln2 (hi + lo), degree-13 Taylor kernel (remainder < 2^-57 on
-// |r| <= ln2/2), result scaled by 2^k through the exponent field (results stay normal for |x| < 700).
+// exp
 constexpr double kLog2e = 1.44269504088896338700e+00;
 constexpr double kLn2Hi = 6.93147180369123816490e-01;
 constexpr double kLn2Lo = 1.90821492927058770002e-10;
-__device__ __constant__ double kExpTaylor[14] = {
-    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
-    1.0 / 5040.0,       1.0 / 720.0,       1.0 / 120.0,      1.0 / 24.0,      1.0 / 6.0,      0.5,
-    1.0,                1.0};
+constexpr double kE0 = 5.00000000000000000e-01, kE1 = 1.66666666666666713e-01, kE2 = 4.16666666666666713e-02,
+                 kE3 = 8.33333333332612891e-03, kE4 = 1.38888888888837438e-03, kE5 = 1.98412698748407683e-04,
+                 kE6 = 2.48015873255621253e-05, kE7 = 2.75572553746587440e-06, kE8 = 2.75572736248664783e-07,
+                 kE9 = 2.51052276365517599e-08, kE10 = 2.09146945603515922e-09;
 
 __device__ __forceinline__ double exp_fast(double x) {
-    const int k = __double2int_rn(__dmul_rn(x, kLog2e));
-    const double kd = __int2double_rn(k);
+    const double t = __fma_rn(x, kLog2e, kMagic);
+    const double kd = __dsub_rn(t, kMagic);
     double r = __fma_rn(kd, -kLn2Hi, x);
     r = __fma_rn(kd, -kLn2Lo, r);
-    double p = kExpTaylor[0];
-#pragma unroll
-    for (int i = 1; i < 14; ++i) p = __fma_rn(p, r, kExpTaylor[i]);
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    double p = kE10;
+    p = __fma_rn(p, r, kE9);
+    p = __fma_rn(p, r, kE8);
+    p = __fma_rn(p, r, kE7);
+    p = __fma_rn(p, r, kE6);
+    p = __fma_rn(p, r, kE5);
+    p = __fma_rn(p, r, kE4);
+    p = __fma_rn(p, r, kE3);
+    p = __fma_rn(p, r, kE2);
+    p = __fma_rn(p, r, kE1);
+    p = __fma_rn(p, r, kE0);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    // scale by 2^k through the exponent field (results stay normal for |x| < 700)
+    return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
+}
+__device__ __forceinline__ bool exp_slow(double x) {
+    return ((uint32_t)__double2hiint(x) & 0x7fffffffu) >= 0x4085e000u; // |x| >= 700, Inf, NaN
 }
 template <int P>
 __device__ __forceinline__ void exp_n(const double (&x)[P], double (&out)[P]) {
+    bool slow = false;
 #pragma unroll
-    for (int p = 0; p < P; ++p) out[p] = exp_fast(x[p]);
+    for (int p = 0; p < P; ++p) {
+        out[p] = exp_fast(x[p]);
+        slow |= exp_slow(x[p]);
+    }
+    if (slow) {
 #pragma unroll
-    for (int p = 0; p < P; ++p)
-        if (!(fabs(x[p]) < 700.0)) out[p] = ::exp(x[p]);
+        for (int p = 0; p < P; ++p)
+            if (exp_slow(x[p])) out[p] = ::exp(x[p]);
+    }
 }
 
 } // namespace lm

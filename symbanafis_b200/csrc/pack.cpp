@@ -1,0 +1,254 @@
+// pack.cpp -- device program (indices, run-time kinds) -> micro-instruction image (byte offsets,
+// kind-specialised micro-ops).  Pure re-encoding: the same operations run on the same values in the
+// same order; commutative operands may swap places (IEEE add/mul commute bit for bit).
+#include "pack.h"
+
+#include <cstring>
+#include <map>
+#include <sstream>
+
+#include "../../include/saf_b200.h"
+
+namespace saf {
+
+namespace {
+
+struct Dec { // one decoded device instruction
+    uint32_t op, prefix, fd, fa, fb, fc, imm;
+};
+
+struct UI {
+    uint32_t uop = U_END;
+    int32_t d = NO_DEST;
+    uint32_t a = 0, b = 0, c = 0, imm = 0, kinds = 0;
+};
+
+} // namespace
+
+int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string &err) {
+    out = PackedProgram();
+    out.points_per_thread = P;
+    const uint32_t SB = slot_bytes(P);
+
+    // ---- decode ----
+    std::vector<Dec> code;
+    bool needs_staging = false;
+    for (size_t i = 0; i < dp.code.size();) {
+        const uint64_t lo = dp.code[i++];
+        const uint32_t x = (uint32_t)(lo & 0xffu);
+        uint32_t op, ka, kb;
+        decode_xop(x, &op, &ka, &kb);
+        Dec d{op, (uint32_t)((lo >> 8) & 0xffu), (uint32_t)((lo >> 16) & 0xffffu), (uint32_t)((lo >> 32) & 0xffffu),
+              (uint32_t)(lo >> 48), FIELD_NONE, 0};
+        if (xop_has_hi(x)) {
+            if (i >= dp.code.size()) {
+                err = "internal: truncated device program";
+                return SAF_ERR_INVALID_PROGRAM;
+            }
+            const uint64_t hi = dp.code[i++];
+            d.fc = (uint32_t)(hi & 0xffffu);
+            d.imm = (uint32_t)(hi >> 32);
+        }
+        if (op == D_BUILTIN3 || op == D_BUILTIN4 || op == D_ARG2) needs_staging = true;
+        code.push_back(d);
+        if (op == D_END) break;
+    }
+
+    // ---- register file and constant table ----
+    uint32_t n_slots = dp.n_slots;
+    if (needs_staging) {
+        out.x0_off = (int32_t)(n_slots * SB);
+        out.x1_off = (int32_t)((n_slots + 1) * SB);
+        n_slots += 2;
+    }
+    out.n_slots = n_slots;
+    if ((uint64_t)n_slots * SB >= 0x7fffffffull) {
+        err = "register file offset overflow";
+        return SAF_ERR_UNSUPPORTED;
+    }
+    std::vector<double> K(dp.consts.begin(), dp.consts.end());
+    std::map<uint64_t, uint32_t> mul_pair; // bits(k1) -> byte offset of the pair {k1, -0.0}
+    auto soff = [&](uint32_t f) { return field_index(f) * SB; };
+    auto koff = [&](uint32_t f) { return field_index(f) * 8u; };
+    auto off_of = [&](uint32_t f) -> uint32_t {
+        switch (field_kind(f)) {
+        case KIND_S: return soff(f);
+        case KIND_K: return koff(f);
+        default: return 0;
+        }
+    };
+    auto dest_of = [&](uint32_t f) -> int32_t { return field_kind(f) == KIND_S ? (int32_t)soff(f) : NO_DEST; };
+
+    std::vector<UI> U;
+    auto kinds3 = [](uint32_t fa, uint32_t fb, uint32_t fc) {
+        return field_kind(fa) | (field_kind(fb) << 2) | (field_kind(fc) << 4);
+    };
+
+    for (const Dec &d : code) {
+        UI u;
+        u.d = dest_of(d.fd);
+        const uint32_t ka = field_kind(d.fa), kb = field_kind(d.fb), kc = field_kind(d.fc);
+        const uint32_t op = d.op;
+        if (op == D_END) {
+            u.uop = U_END;
+        } else if (op == D_LOADK) {
+            u.uop = U_LOADK;
+            u.a = koff(d.fa);
+        } else if (op >= D_FIRST_LIGHT_UNARY && op < D_FIRST_LIGHT_UNARY + D_N_LIGHT_UNARY) {
+            if (ka == KIND_K) { // not produced by the lowering; keep the packer total anyway
+                UI l;
+                l.uop = U_LOADK;
+                l.a = koff(d.fa);
+                U.push_back(l);
+            }
+            u.uop = U_U1 + 2 * (op - D_FIRST_LIGHT_UNARY) + (ka == KIND_S ? 0u : 1u);
+            u.a = off_of(d.fa);
+        } else if (op == D_SIN || op == D_COS || op == D_EXP || op == D_LN || op == D_RECIPEXPM1 || op == D_EXPSQR ||
+                   op == D_EXPSQRNEG || op == D_EXPNEG || op == D_SINCOS) {
+            static const uint32_t H[] = {H1_SIN, H1_COS, H1_EXP, H1_LN, H1_RECIPEXPM1, H1_EXPSQR, H1_EXPSQRNEG, H1_EXPNEG, H1_SINCOS};
+            const uint32_t h = H[op - D_SIN];
+            if (ka == KIND_K) { // a constant argument: materialise it in ACC first (unary: ACC is free)
+                UI l;
+                l.uop = U_LOADK;
+                l.a = koff(d.fa);
+                U.push_back(l);
+            }
+            uint32_t prefixed = 0;
+            if (d.prefix == PREFIX_FMA) {
+                prefixed = 1;
+                u.b = koff(d.fb); // K[b], K[b+1] are adjacent in the device constant table
+            } else if (d.prefix == PREFIX_MUL) {
+                prefixed = 1;
+                const double k1 = dp.consts[field_index(d.fb)];
+                uint64_t bits;
+                std::memcpy(&bits, &k1, 8);
+                auto it = mul_pair.find(bits);
+                if (it == mul_pair.end()) {
+                    const uint32_t o = (uint32_t)K.size() * 8u;
+                    K.push_back(k1);
+                    K.push_back(-0.0); // fma(x, k1, -0.0) == x * k1 for every x, zeros and NaN included
+                    it = mul_pair.emplace(bits, o).first;
+                }
+                u.b = it->second;
+            }
+            u.uop = U_H1 + 4 * h + 2 * prefixed + (ka == KIND_S ? 0u : 1u);
+            u.a = off_of(d.fa);
+            if (op == D_SINCOS) u.c = (uint32_t)dest_of(d.fc);
+        } else if (op == D_ADD || op == D_MUL || op == D_NEGMUL) {
+            const uint32_t i = op == D_ADD ? BC_ADD : op == D_MUL ? BC_MUL : BC_NEGMUL;
+            uint32_t fa = d.fa, fb = d.fb;
+            auto rank = [](uint32_t k) { return k == KIND_S ? 0 : k == KIND_K ? 1 : 2; };
+            if (rank(field_kind(fa)) > rank(field_kind(fb))) std::swap(fa, fb);
+            const uint32_t a_ = field_kind(fa), b_ = field_kind(fb);
+            uint32_t v;
+            if (a_ == KIND_S && b_ == KIND_S) v = BC_SS;
+            else if (a_ == KIND_S && b_ == KIND_K) v = BC_SK;
+            else if (a_ == KIND_S && b_ == KIND_ACC) v = BC_SA;
+            else if (a_ == KIND_K && b_ == KIND_ACC) v = BC_KA;
+            else if (a_ == KIND_ACC && b_ == KIND_ACC) v = BC_AA;
+            else {
+                err = "internal: constant-constant light binary operation in the device program";
+                return SAF_ERR_INVALID_PROGRAM;
+            }
+            u.uop = U_BC + 5 * i + v;
+            u.a = off_of(fa);
+            u.b = off_of(fb);
+        } else if (op == D_SUB || op == D_DIV) {
+            const uint32_t i = op == D_SUB ? BN_SUB : BN_DIV;
+            int v = -1;
+            if (ka == KIND_S && kb == KIND_S) v = BN_SS;
+            else if (ka == KIND_S && kb == KIND_K) v = BN_SK;
+            else if (ka == KIND_K && kb == KIND_S) v = BN_KS;
+            else if (ka == KIND_S && kb == KIND_ACC) v = BN_SA;
+            else if (ka == KIND_ACC && kb == KIND_S) v = BN_AS;
+            else if (ka == KIND_K && kb == KIND_ACC) v = BN_KA;
+            else if (ka == KIND_ACC && kb == KIND_K) v = BN_AK;
+            else if (ka == KIND_ACC && kb == KIND_ACC) v = BN_AA;
+            if (v >= 0) {
+                u.uop = U_BN + 8 * i + (uint32_t)v;
+            } else if (op == D_DIV) {
+                u.uop = U_G + G_DIV;
+                u.kinds = kinds3(d.fa, d.fb, FIELD_NONE);
+            } else {
+                err = "internal: constant-constant subtraction in the device program";
+                return SAF_ERR_INVALID_PROGRAM;
+            }
+            u.a = off_of(d.fa);
+            u.b = off_of(d.fb);
+        } else if (op >= D_FIRST_TERNARY && op < D_FIRST_TERNARY + D_N_TERNARY) {
+            const uint32_t t = op - D_FIRST_TERNARY;
+            uint32_t fa = d.fa, fb = d.fb;
+            auto rank = [](uint32_t k) { return k == KIND_S ? 0 : k == KIND_K ? 1 : 2; };
+            if (rank(field_kind(fa)) > rank(field_kind(fb))) std::swap(fa, fb); // a * b commutes
+            const uint32_t a_ = field_kind(fa), b_ = field_kind(fb);
+            int v = -1;
+            if (a_ == KIND_S && b_ == KIND_S) v = kc == KIND_S ? (int)T_SSS : kc == KIND_K ? (int)T_SSK : (int)T_SSA;
+            else if (a_ == KIND_S && b_ == KIND_K) v = kc == KIND_S ? (int)T_SKS : kc == KIND_K ? (int)T_SKK : (int)T_SKA;
+            else if (a_ == KIND_S && b_ == KIND_ACC && kc != KIND_ACC) v = kc == KIND_S ? (int)T_SAS : (int)T_SAK;
+            else if (a_ == KIND_K && b_ == KIND_ACC && kc != KIND_ACC) v = kc == KIND_S ? (int)T_KAS : (int)T_KAK;
+            if (v >= 0) {
+                u.uop = U_T + 10 * t + (uint32_t)v;
+                u.a = off_of(fa);
+                u.b = off_of(fb);
+                u.c = off_of(d.fc);
+            } else {
+                u.uop = U_G + G_FMA + t;
+                u.a = off_of(d.fa);
+                u.b = off_of(d.fb);
+                u.c = off_of(d.fc);
+                u.kinds = kinds3(d.fa, d.fb, d.fc);
+            }
+        } else {
+            // generic micro-ops: kinds decoded at run time
+            u.a = off_of(d.fa);
+            u.b = off_of(d.fb);
+            u.imm = d.imm;
+            u.kinds = kinds3(d.fa, d.fb, FIELD_NONE);
+            switch (op) {
+            case D_POW: u.uop = U_G + G_POW; break;
+            case D_POWI: u.uop = U_G + G_POWI; break;
+            case D_BUILTIN1: u.uop = U_G + G_BUILTIN1; break;
+            case D_BUILTIN2: u.uop = U_G + G_BUILTIN2; break;
+            case D_BUILTIN3: u.uop = U_G + G_BUILTIN3; break;
+            case D_BUILTIN4: u.uop = U_G + G_BUILTIN4; break;
+            case D_ARG2: u.uop = U_G + G_ARG2; u.d = NO_DEST; break;
+            default: {
+                std::ostringstream os;
+                os << "internal: device op " << op << " has no micro-op";
+                err = os.str();
+                return SAF_ERR_INVALID_PROGRAM;
+            }
+            }
+        }
+        U.push_back(u);
+    }
+    // one padding instruction: the kernel prefetches the instruction after U_END
+    U.push_back(UI());
+
+    // ---- image: [constants, padded to 32 bytes][micro-instructions] ----
+    const size_t k_words = (K.size() + 3) & ~(size_t)3;
+    out.image.assign(k_words + U.size() * UINSTR_WORDS, 0);
+    for (size_t i = 0; i < K.size(); ++i) std::memcpy(&out.image[i], &K[i], 8);
+    for (size_t i = 0; i < U.size(); ++i) {
+        const UI &u = U[i];
+        uint64_t *w = &out.image[k_words + i * UINSTR_WORDS];
+        w[0] = (uint64_t)u.uop | ((uint64_t)(uint32_t)u.d << 32);
+        w[1] = (uint64_t)u.a | ((uint64_t)u.b << 32);
+        w[2] = (uint64_t)u.c | ((uint64_t)u.imm << 32);
+        w[3] = (uint64_t)u.kinds;
+    }
+    out.n_instr = (uint32_t)U.size();
+    out.code_off = (uint32_t)(k_words * 8);
+
+    out.param_off.assign(dp.param_count, -1);
+    for (uint32_t j = 0; j < dp.param_count; ++j)
+        if (dp.param_slot[j] != NO_SLOT) out.param_off[j] = (int32_t)((uint32_t)dp.param_slot[j] * SB);
+    for (uint32_t f : dp.result_field) {
+        const bool is_k = field_kind(f) == KIND_K;
+        out.result_is_k.push_back(is_k ? 1 : 0);
+        out.result_off.push_back((int32_t)(is_k ? koff(f) : soff(f)));
+    }
+    return SAF_OK;
+}
+
+} // namespace saf

@@ -1,0 +1,33 @@
+// pack.h -- packs a device program (saf_isa.h) into the kernel's micro-instruction image (uop.h) for
+// one register-file layout.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "lower.h"
+#include "uop.h"
+
+namespace saf {
+
+struct PackedProgram {
+    int points_per_thread = 0;
+    // image = constant table (padded to 32 bytes), then n_instr micro-instructions (incl. U_END and one
+    // padding instruction for the prefetch); every K operand is a byte offset into this image
+    std::vector<uint64_t> image;
+    uint32_t code_off = 0;             // byte offset of the first micro-instruction in the image
+    uint32_t n_instr = 0;
+    uint32_t n_slots = 0;              // register-file slots incl. staging slots for Builtin3/4 operands
+    int32_t x0_off = -1, x1_off = -1;  // staging slots (byte offsets), -1 when unused
+    std::vector<int32_t> param_off;    // per parameter: register-file byte offset, -1 = never read
+    std::vector<int32_t> result_off;   // per result: byte offset (register file or image)
+    std::vector<uint8_t> result_is_k;  // per result: 1 = constant (offset into the image)
+};
+
+// Byte stride of one slot for P points per thread.
+constexpr uint32_t slot_bytes(int points_per_thread) { return (uint32_t)BLOCK_THREADS * 8u * (uint32_t)points_per_thread; }
+
+// Returns 0 or SAF_ERR_UNSUPPORTED (err filled).
+int pack_program(const DeviceProgram &dp, int points_per_thread, PackedProgram &out, std::string &err);
+
+} // namespace saf

@@ -1,0 +1,58 @@
+// uop.h -- the interpreter kernel's PACKED instruction format (host + device).
+//
+// The device program of saf_isa.h (what saf_program_export returns and tests/dev_emulator.py runs) is
+// layout-independent: fields are slot / constant INDICES.  Before a launch the host packs it for one
+// register-file layout (points per thread P) into fixed-size 32-byte micro-instructions whose operands
+// are ready-to-use BYTE OFFSETS, and whose opcode says where every operand comes from, so that a handler
+// is: one integer add per shared-memory operand, one constant-bank load per constant operand, the FP64
+// instructions, and a sign-tested store.  No operand-kind decoding, shifting or masking happens in the
+// hot handlers.
+//
+//   word 0: [31:0] uop            [63:32] d   destination byte offset in the register file, < 0 = ACC only
+//   word 1: [31:0] a              [63:32] b   S operands: byte offset of the slot in the register file
+//   word 2: [31:0] c              [63:32] imm K operands: byte offset of the constant in the blob
+//   word 3: [31:0] kinds (generic ops: kind(a) | kind(b) << 2 | kind(c) << 4)
+//
+// Operand kinds S (register-file slot), K (constant table), A (accumulator = previous result), see
+// saf_isa.h.  Specialised micro-op families (operand kinds fixed by the opcode):
+//   U1   light unary        x {S, A}
+//   H1   heavy unary        x {S, A} x {plain, affine prefix arg = fma(a, K[b], K[b+8])}
+//   BC   commutative binary (add, mul, negmul), operands ordered S < K < A:   SS SK SA KA AA
+//   BN   ordered binary (sub, div):                                 SS SK KS SA AS KA AK AA
+//   T    fused multiply-add family, product operands ordered S < K < A, at most one A:
+//                                                      SSS SSK SSA SKS SKK SKA SAS SAK KAS KAK
+// Everything else (pow, powi, builtins, operand staging, the rare kind combinations above) runs through
+// generic micro-ops that decode `kinds` at run time.
+#pragma once
+#include <stdint.h>
+
+#include "saf_isa.h"
+
+namespace saf {
+
+constexpr int UINSTR_BYTES = 32;
+constexpr int UINSTR_WORDS = 4; // 64-bit words
+
+constexpr uint32_t U_END = 0, U_LOADK = 1;
+constexpr uint32_t U_U1 = 2;                                  // + 2 * u + (a is A)
+constexpr uint32_t U_H1 = U_U1 + 2 * D_N_LIGHT_UNARY;         // + 4 * h + 2 * prefixed + (a is A)
+constexpr uint32_t H1_SIN = 0, H1_COS = 1, H1_EXP = 2, H1_LN = 3, H1_RECIPEXPM1 = 4, H1_EXPSQR = 5,
+                   H1_EXPSQRNEG = 6, H1_EXPNEG = 7, H1_SINCOS = 8, H1_COUNT = 9;
+constexpr uint32_t U_BC = U_H1 + 4 * H1_COUNT;                // + 5 * i + variant
+constexpr uint32_t BC_ADD = 0, BC_MUL = 1, BC_NEGMUL = 2, BC_COUNT = 3;
+constexpr uint32_t BC_SS = 0, BC_SK = 1, BC_SA = 2, BC_KA = 3, BC_AA = 4;
+constexpr uint32_t U_BN = U_BC + 5 * BC_COUNT;                // + 8 * i + variant
+constexpr uint32_t BN_SUB = 0, BN_DIV = 1, BN_COUNT = 2;
+constexpr uint32_t BN_SS = 0, BN_SK = 1, BN_KS = 2, BN_SA = 3, BN_AS = 4, BN_KA = 5, BN_AK = 6, BN_AA = 7;
+constexpr uint32_t U_T = U_BN + 8 * BN_COUNT;                 // + 10 * t + variant
+constexpr uint32_t T_FMA = 0, T_FMS = 1, T_FNMA = 2, T_FNMS = 3, T_COUNT = 4;
+constexpr uint32_t T_SSS = 0, T_SSK = 1, T_SSA = 2, T_SKS = 3, T_SKK = 4, T_SKA = 5, T_SAS = 6, T_SAK = 7,
+                   T_KAS = 8, T_KAK = 9;
+constexpr uint32_t U_G = U_T + 10 * T_COUNT;                  // generic micro-ops
+constexpr uint32_t G_POW = 0, G_POWI = 1, G_BUILTIN1 = 2, G_BUILTIN2 = 3, G_BUILTIN3 = 4, G_BUILTIN4 = 5,
+                   G_ARG2 = 6, G_FMA = 7, G_FMS = 8, G_FNMA = 9, G_FNMS = 10, G_DIV = 11, G_COUNT = 12;
+constexpr uint32_t U_COUNT = U_G + G_COUNT;
+
+constexpr int32_t NO_DEST = -1;
+
+} // namespace saf

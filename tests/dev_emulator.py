@@ -181,3 +181,153 @@ def run_device_program(code: Sequence[int], consts: np.ndarray, param_slot: Sequ
                 if s != 0xFFFF:
                     S[int(s)] = result_value(int(result_field[j]))
     return [result_value(int(f)) for f in result_field]
+
+
+# ---- packed micro-instruction image (symbanafis_b200/csrc/uop.h, produced by pack.cpp) -------------------
+N_H1 = 9
+U_END, U_LOADK, U_U1 = 0, 1, 2
+U_H1 = U_U1 + 2 * N_LIGHT_UNARY
+U_BC = U_H1 + 4 * N_H1
+U_BN = U_BC + 5 * 3
+U_T = U_BN + 8 * 2
+U_G = U_T + 10 * 4
+H1_NAMES = ["sin", "cos", "exp", "ln", "recipexpm1", "expsqr", "expsqrneg", "expneg", "sincos"]
+BC_NAMES = ["add", "mul", "negmul"]
+BC_KINDS = ["SS", "SK", "SA", "KA", "AA"]
+BN_NAMES = ["sub", "div"]
+BN_KINDS = ["SS", "SK", "KS", "SA", "AS", "KA", "AK", "AA"]
+T_NAMES = ["fma", "fms", "fnma", "fnms"]
+T_KINDS = ["SSS", "SSK", "SSA", "SKS", "SKK", "SKA", "SAS", "SAK", "KAS", "KAK"]
+G_NAMES = ["pow", "powi", "builtin1", "builtin2", "builtin3", "builtin4", "arg2", "fma", "fms", "fnma", "fnms", "div"]
+
+
+def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iters: int = 1) -> List[np.ndarray]:
+    """Executes the packed image exactly as kernel.cu does (register file addressed by byte offset, constants
+    read from the image, accumulator, sign-tested destination store), leaf math delegated to the oracle."""
+    image = np.asarray(pk["image"], dtype=np.uint64)
+    kview = image.view(np.float64)
+    P = int(pk["points_per_thread"])
+    slot_bytes = 128 * 8 * P
+    rf_bytes = int(pk["n_slots"]) * slot_bytes
+    RF: Dict[int, np.ndarray] = {}
+
+    def K(off: int) -> np.ndarray:
+        assert off % 8 == 0 and off < int(pk["code_off"]), "constant operand outside the constant table"
+        return np.full(n_points, kview[off // 8])
+
+    def S(off: int) -> np.ndarray:
+        assert off % slot_bytes == 0 and 0 <= off < rf_bytes, "slot operand outside the register file"
+        return RF[off]  # KeyError = slot read before it was written
+
+    def store(off: int, v: np.ndarray):
+        assert off % slot_bytes == 0 and 0 <= off < rf_bytes, "slot store outside the register file"
+        RF[off] = v.copy()
+
+    for j, off in enumerate(pk["param_off"]):
+        off = int(off)
+        if off < 0:
+            continue
+        if j < len(cols):
+            c = np.asarray(cols[j], dtype=np.float64)
+            store(off, c[np.minimum(np.arange(n_points), len(c) - 1)])
+        else:
+            store(off, np.zeros(n_points))
+    acc = np.zeros(n_points)
+
+    def by_letter(letter: str, off: int) -> np.ndarray:
+        return S(off) if letter == "S" else K(off) if letter == "K" else acc
+
+    def by_kind(kind: int, off: int) -> np.ndarray:
+        return S(off) if kind == KIND_S else K(off) if kind == KIND_K else acc
+
+    def ref1(name, x):
+        return _leaf((name, 1, 0), 1).eval_batch([x], n_points)[0]
+
+    def ref2(name, x, y):
+        return _leaf((name, 2, 0, 1), 2).eval_batch([x, y], n_points)[0]
+
+    def ref3(name, x, y, z):
+        return _leaf((name, 3, 0, 1, 2), 3).eval_batch([x, y, z], n_points)[0]
+
+    def result_value(k: int) -> np.ndarray:
+        off = int(pk["result_off"][k])
+        return K(off) if pk["result_is_k"][k] else S(off).copy()
+
+    i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
+    for it in range(iters):
+        pc = int(pk["code_off"]) // 8
+        while True:
+            w0, w1, w2, w3 = (int(x) for x in image[pc:pc + 4])
+            pc += 4
+            uop, fd = w0 & 0xFFFFFFFF, i32(w0 >> 32)
+            fa, fb, fc, imm, kinds = w1 & 0xFFFFFFFF, w1 >> 32, w2 & 0xFFFFFFFF, w2 >> 32, w3 & 0xFFFFFFFF
+            if uop == U_END:
+                break
+            keep_acc = False
+            if uop == U_LOADK:
+                r = K(fa)
+            elif uop < U_H1:
+                u, is_a = divmod(uop - U_U1, 2)
+                name = DEV_OPS[D["copy"] + u]
+                x = acc if is_a else S(fa)
+                r = x.copy() if name == "copy" else ref1(_UNARY_REF[name], x)
+            elif uop < U_BC:
+                h, v = divmod(uop - U_H1, 4)
+                x = acc if (v & 1) else S(fa)
+                if v & 2:
+                    x = ref3("MulAdd", x, K(fb), K(fb + 8))
+                name = H1_NAMES[h]
+                if name == "expneg":
+                    r = _leaf(("Builtin1", 1, "exp_neg", 0), 1).eval_batch([x], n_points)[0]
+                elif name == "sincos":
+                    r, c_ = _leaf(("SinCos", 1, 2, 0), 1, 2).eval_batch([x], n_points)
+                    if i32(fc) >= 0:
+                        store(fc, c_)
+                else:
+                    r = ref1(_UNARY_REF[name], x)
+            elif uop < U_BN:
+                i, v = divmod(uop - U_BC, 5)
+                kk = BC_KINDS[v]
+                r = ref2(_BINARY_REF[BC_NAMES[i]], by_letter(kk[0], fa), by_letter(kk[1], fb))
+            elif uop < U_T:
+                i, v = divmod(uop - U_BN, 8)
+                kk = BN_KINDS[v]
+                r = ref2(_BINARY_REF[BN_NAMES[i]], by_letter(kk[0], fa), by_letter(kk[1], fb))
+            elif uop < U_G:
+                t, v = divmod(uop - U_T, 10)
+                kk = T_KINDS[v]
+                r = ref3(_TERNARY_REF[T_NAMES[t]], by_letter(kk[0], fa), by_letter(kk[1], fb), by_letter(kk[2], fc))
+            else:
+                name = G_NAMES[uop - U_G]
+                ka, kb, kc = kinds & 3, (kinds >> 2) & 3, (kinds >> 4) & 3
+                if name in ("pow", "div"):
+                    r = ref2(_BINARY_REF[name], by_kind(ka, fa), by_kind(kb, fb))
+                elif name == "powi":
+                    r = _leaf(("Powi", 1, 0, i32(imm)), 1).eval_batch([by_kind(ka, fa)], n_points)[0]
+                elif name == "builtin1":
+                    r = _leaf(("Builtin1", 1, imm, 0), 1).eval_batch([by_kind(ka, fa)], n_points)[0]
+                elif name == "builtin2":
+                    r = _leaf(("Builtin2", 2, imm, 0, 1), 2).eval_batch([by_kind(ka, fa), by_kind(kb, fb)], n_points)[0]
+                elif name == "builtin3":
+                    r = _leaf(("Builtin3", 3, imm, 0, 1, 2), 3).eval_batch(
+                        [S(int(pk["x_off"][0])), S(int(pk["x_off"][1])), by_kind(ka, fa)], n_points)[0]
+                elif name == "builtin4":
+                    r = _leaf(("Builtin4", 4, imm, 0, 1, 2, 3), 4).eval_batch(
+                        [S(int(pk["x_off"][0])), S(int(pk["x_off"][1])), by_kind(ka, fa), by_kind(kb, fb)], n_points)[0]
+                elif name == "arg2":
+                    x0, x1 = by_kind(ka, fa).copy(), by_kind(kb, fb).copy()
+                    store(int(pk["x_off"][0]), x0)
+                    store(int(pk["x_off"][1]), x1)
+                    keep_acc = True
+                    r = acc
+                else:
+                    r = ref3(_TERNARY_REF[name], by_kind(ka, fa), by_kind(kb, fb), by_kind(kc, fc))
+            if not keep_acc:
+                acc = r
+            if fd >= 0:
+                store(fd, acc)
+        if it + 1 < iters:
+            for j, off in enumerate(pk["param_off"]):  # sequential, exactly like the kernel's feedback loop
+                if int(off) >= 0:
+                    store(int(off), result_value(j))
+    return [result_value(k) for k in range(len(pk["result_off"]))]

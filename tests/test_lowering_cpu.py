@@ -6,7 +6,7 @@ leaf math) and compared with the oracle executing the original reference bytecod
 import numpy as np
 import pytest
 
-from dev_emulator import run_device_program
+from dev_emulator import run_device_program, run_packed_program
 from oracle import OracleProgram
 from symbanafis_b200 import workloads
 from symbanafis_b200._lib import DeviceProgramHandle, SafError
@@ -26,6 +26,11 @@ def _check(prog, cols, n, iters=1):
     got = run_device_program(code, consts, pslot, rfield, cols, n, iters)
     for k, (r, g) in enumerate(zip(ref, got)):
         assert bits_equal(g, r), f"result {k} differs"
+    # the packed micro-instruction image the kernel executes, for every register-file layout
+    for ppt in (1, 2, 4):
+        got = run_packed_program(h.export_packed(ppt), cols, n, iters)
+        for k, (r, g) in enumerate(zip(ref, got)):
+            assert bits_equal(g, r), f"packed image (P={ppt}): result {k} differs"
     return h
 
 
@@ -78,9 +83,10 @@ def test_fuse_matches_separate_programs():
     cols = w.make_inputs(50, 3)
     code, consts, pslot, rfield = fused.export()
     got = run_device_program(code, consts, pslot, rfield, cols, 50)
-    for p, g in zip(w.parts, got):
+    got4 = run_packed_program(fused.export_packed(4), cols, 50)
+    for p, g, g4 in zip(w.parts, got, got4):
         ref = OracleProgram.from_program(p).eval_batch(cols, 50)[0]
-        assert bits_equal(g, ref)
+        assert bits_equal(g, ref) and bits_equal(g4, ref)
 
 
 def test_validator_rejects_malformed_programs():
