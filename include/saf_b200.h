@@ -121,7 +121,7 @@ SAF_API int saf_program_export(const saf_program *prog, uint64_t *code, size_t c
  * Any pointer may be NULL; n_words always receives the full size. */
 SAF_API int saf_program_export_packed(const saf_program *prog, int points_per_thread,
                               uint64_t *image, size_t cap_words, size_t *n_words,
-                              uint32_t *code_off, uint32_t *n_slots, int32_t *x_off /* [2] */,
+                              uint32_t *code_off, uint32_t *n_slots, int32_t *x_off /* [3]: x0, x1, acc */,
                               int32_t *param_off, int32_t *result_off, uint8_t *result_is_k);
 
 /* ---- evaluation --------------------------------------------------------------------------- */

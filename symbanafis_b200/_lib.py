@@ -212,14 +212,14 @@ class DeviceProgramHandle:
 
     def export_packed(self, points_per_thread: int):
         """The packed micro-instruction image for one register-file layout (csrc/uop.h):
-        dict(image uint64[], code_off, n_slots, x_off int32[2], param_off int32[], result_off int32[],
+        dict(image uint64[], code_off, n_slots, x_off int32[3] = staging x0, x1 and the ACC slot, param_off int32[], result_off int32[],
         result_is_k uint8[])."""
         nw, co, ns = C.c_size_t(), C.c_uint32(), C.c_uint32()
         check(lib().saf_program_export_packed(self._h, points_per_thread, None, 0, C.byref(nw), C.byref(co),
                                               C.byref(ns), None, None, None, None))
         info = self.info()
         image = np.zeros(nw.value, dtype=np.uint64)
-        x_off = np.zeros(2, dtype=np.int32)
+        x_off = np.zeros(3, dtype=np.int32)  # x0, x1, acc
         poff = np.zeros(max(1, info.param_count), dtype=np.int32)
         roff = np.zeros(max(1, info.n_results), dtype=np.int32)
         rk = np.zeros(max(1, info.n_results), dtype=np.uint8)

@@ -238,6 +238,7 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     if (rc != SAF_OK) return rc;
     d.code_off = pk->code_off;
     d.n_slots = pk->n_slots;
+    d.acc_off = pk->acc_off;
     d.x0_off = pk->x0_off;
     d.x1_off = pk->x1_off;
     for (uint32_t j = 0; j < dp.param_count; ++j) d.param_off[j] = pk->param_off[j];
@@ -245,21 +246,15 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
         d.result_off[k] = pk->result_off[k];
         if (pk->result_is_k[k]) d.result_k_mask |= 1u << k;
     }
-    const uint64_t *image = nullptr;
-    size_t n_image = 0;
-    if (pk->image.size() <= (size_t)BLOB_LARGE) {
-        image = pk->image.data();
-        n_image = pk->image.size();
-    } else {
-        rc = ensure_device_image(const_cast<saf_program *>(prog), device, *pk, &d.image_global);
-        if (rc != SAF_OK) return rc;
-    }
+    rc = ensure_device_image(const_cast<saf_program *>(prog), device, *pk, &d.image_global);
+    if (rc != SAF_OK) return rc;
+    d.image_bytes = (uint32_t)(pk->image.size() * 8);
     LaunchShape shape;
-    e = choose_shape(device, pk->n_slots, n_points, P, &shape);
+    e = choose_shape(device, pk->n_slots, pk->image.size() * 8, n_points, P, &shape);
     if (e == cudaErrorInvalidConfiguration)
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_shape");
-    e = launch_interpreter(d, image, n_image, shape, stream);
+    e = launch_interpreter(d, shape, stream);
     if (e != cudaSuccess) return cuda_fail(e, "interpreter launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return SAF_OK;
@@ -281,6 +276,7 @@ extern "C" int saf_program_export_packed(const saf_program *p, int points_per_th
     if (x_off) {
         x_off[0] = pk->x0_off;
         x_off[1] = pk->x1_off;
+        x_off[2] = pk->acc_off;
     }
     if (param_off) std::copy(pk->param_off.begin(), pk->param_off.end(), param_off);
     if (result_off) std::copy(pk->result_off.begin(), pk->result_off.end(), result_off);

@@ -14,13 +14,15 @@ namespace saf {
 struct LaunchDesc {
     unsigned long long n_points;
     unsigned long long iters;            // >= 1; > 1 only for saf_iterate_*
-    const unsigned char *image_global;   // packed image in global memory (programs that do not fit the blob)
+    const unsigned char *image_global;   // packed image (pack.h) in global memory
+    uint32_t image_bytes;                // multiple of 16
     uint32_t code_off;                   // first micro-instruction in the image
     uint32_t n_slots;                    // register-file slots (incl. staging slots)
     uint32_t n_params;                   // columns the program can read (param_count)
     uint32_t n_results;
     uint32_t flags;                      // SAF_EVAL_BROADCAST
     uint32_t result_k_mask;              // bit k: result k is a constant (result_off = image offset)
+    int32_t acc_off;                     // reserved slot through which ACC is handed to the cold micro-ops
     int32_t x0_off, x1_off;              // staging slots of Builtin3/4 operands
     const double *cols[MAX_COLS];        // device column base pointers (nullptr = missing -> 0.0)
     unsigned long long col_len[MAX_COLS];
@@ -29,38 +31,29 @@ struct LaunchDesc {
     int32_t result_off[MAX_OUTS];
 };
 
-// Packed image staged in the kernel parameter space, i.e. the constant bank: fetched through the
-// constant cache with warp-uniform addresses, off the shared-memory / L1 data path.
-template <int WORDS>
-struct ConstBlob {
-    uint64_t w[WORDS];
-};
-
-// Blob size classes (8-byte words).  With LaunchDesc (~1.1 KB) the largest stays under the 32764-byte
-// kernel parameter limit of CUDA 12.1+.
-constexpr int BLOB_SMALL = 448;
-constexpr int BLOB_LARGE = 3840;
+// The image is staged in shared memory when it fits there without costing a resident block.
+constexpr size_t IMAGE_SMEM_ALWAYS = 4096;   // always staged up to this size
+constexpr size_t IMAGE_SMEM_MAX = 48 * 1024; // never staged above this size
 
 struct LaunchShape {
     int points_per_thread; // 1, 2 or 4
     int block;             // threads per block (always BLOCK_THREADS)
     int grid;
     size_t smem_bytes;
+    bool image_in_smem;    // the kernel copies the image into shared memory (else reads it from global memory)
 };
 
-// Launches the interpreter.  `image` (host) is copied into the constant-bank blob when it fits BLOB_LARGE
-// words; otherwise desc.image_global must point at a device copy.
-cudaError_t launch_interpreter(const LaunchDesc &desc, const uint64_t *image, size_t n_image_words,
-                               const LaunchShape &shape, cudaStream_t stream);
+// Launches the interpreter; desc.image_global must point at a device copy of the packed image.
+cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream);
 
-// Points per thread for a program with n_slots live values (before staging slots) on `device`.
+// Points per thread for a program with n_slots live values (before reserved slots) on `device`.
 // force_points_per_thread: 0 = automatic, 1 / 2 / 4 = tuning override (SAF_POINTS_PER_THREAD).
 cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
                                      int force_points_per_thread, int *points_per_thread);
-// Grid / shared memory for the packed program's n_slots.
-cudaError_t choose_shape(int device, uint32_t n_slots, unsigned long long n_points, int points_per_thread,
-                         LaunchShape *shape);
-size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread);
+// Grid / shared memory / image placement for the packed program.
+cudaError_t choose_shape(int device, uint32_t n_slots, size_t image_bytes, unsigned long long n_points,
+                         int points_per_thread, LaunchShape *shape);
+size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t image_bytes_in_smem);
 
 // FP64-pipe peak probe: blocks x 256 threads, each `iters` x 64 dependent-chain DFMAs.
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);

@@ -29,15 +29,29 @@
 namespace saf {
 namespace lm {
 
-constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52
-constexpr double kInvPi = 3.18309886183790691e-01;
-constexpr double kPiA = 3.14159265358979312e+00;
-constexpr double kPiB = 1.22464679914735296e-16; // rounded DOWN: every part of the split is positive
-constexpr double kPiC = 2.16571334784382806e-32;
+constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52 (low word zero: an instruction immediate)
 
-constexpr double kS0 = -1.66666666666666657e-01, kS1 = 8.33333333333331587e-03, kS2 = -1.98412698412549389e-04,
-                 kS3 = 2.75573192191536246e-06, kS4 = -2.50521076157725835e-08, kS5 = 1.60589772331473175e-10,
-                 kS6 = -7.64396776493426846e-13, kS7 = 2.73141320376900007e-15;
+// Coefficients live in the constant bank (an FP64 instruction takes a c[bank][offset] operand for free),
+// not in the instruction stream: a 64-bit immediate would cost two UMOV per use.
+__device__ __constant__ double kTrig[12] = {
+    3.18309886183790691e-01,  // [0] 1/pi
+    3.14159265358979312e+00,  // [1] pi, part A
+    1.22464679914735296e-16,  // [2] pi, part B -- rounded DOWN: every part of the split is positive
+    2.16571334784382806e-32,  // [3] pi, part C
+    -1.66666666666666657e-01, 8.33333333333331587e-03, -1.98412698412549389e-04, 2.75573192191536246e-06,   // [4..11] S0..S7
+    -2.50521076157725835e-08, 1.60589772331473175e-10, -7.64396776493426846e-13, 2.73141320376900007e-15};
+#define kInvPi kTrig[0]
+#define kPiA kTrig[1]
+#define kPiB kTrig[2]
+#define kPiC kTrig[3]
+#define kS0 kTrig[4]
+#define kS1 kTrig[5]
+#define kS2 kTrig[6]
+#define kS3 kTrig[7]
+#define kS4 kTrig[8]
+#define kS5 kTrig[9]
+#define kS6 kTrig[10]
+#define kS7 kTrig[11]
 
 // |x| outside the fast range of the trig kernels: >= 2^20, Inf, NaN
 __device__ __forceinline__ bool trig_slow(double x) {
@@ -130,13 +144,27 @@ __device__ __forceinline__ void sincos_n(const double (&x)[P], double (&s)[P], d
 }
 
 // exp
-constexpr double kLog2e = 1.44269504088896338700e+00;
-constexpr double kLn2Hi = 6.93147180369123816490e-01;
-constexpr double kLn2Lo = 1.90821492927058770002e-10;
-constexpr double kE0 = 5.00000000000000000e-01, kE1 = 1.66666666666666713e-01, kE2 = 4.16666666666666713e-02,
-                 kE3 = 8.33333333332612891e-03, kE4 = 1.38888888888837438e-03, kE5 = 1.98412698748407683e-04,
-                 kE6 = 2.48015873255621253e-05, kE7 = 2.75572553746587440e-06, kE8 = 2.75572736248664783e-07,
-                 kE9 = 2.51052276365517599e-08, kE10 = 2.09146945603515922e-09;
+__device__ __constant__ double kExp[14] = {
+    1.44269504088896338700e+00,  // [0] log2(e)
+    6.93147180369123816490e-01,  // [1] ln2 hi
+    1.90821492927058770002e-10,  // [2] ln2 lo
+    5.00000000000000000e-01, 1.66666666666666713e-01, 4.16666666666666713e-02, 8.33333333332612891e-03,   // [3..13] E0..E10
+    1.38888888888837438e-03, 1.98412698748407683e-04, 2.48015873255621253e-05, 2.75572553746587440e-06,
+    2.75572736248664783e-07, 2.51052276365517599e-08, 2.09146945603515922e-09};
+#define kLog2e kExp[0]
+#define kLn2Hi kExp[1]
+#define kLn2Lo kExp[2]
+#define kE0 kExp[3]
+#define kE1 kExp[4]
+#define kE2 kExp[5]
+#define kE3 kExp[6]
+#define kE4 kExp[7]
+#define kE5 kExp[8]
+#define kE6 kExp[9]
+#define kE7 kExp[10]
+#define kE8 kExp[11]
+#define kE9 kExp[12]
+#define kE10 kExp[13]
 
 __device__ __forceinline__ double exp_fast(double x) {
     const double t = __fma_rn(x, kLog2e, kMagic);

@@ -3,6 +3,7 @@
 // same order; commutative operands may swap places (IEEE add/mul commute bit for bit).
 #include "pack.h"
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <sstream>
@@ -56,6 +57,8 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
 
     // ---- register file and constant table ----
     uint32_t n_slots = dp.n_slots;
+    out.acc_off = (int32_t)(n_slots * SB);
+    n_slots += 1;
     if (needs_staging) {
         out.x0_off = (int32_t)(n_slots * SB);
         out.x1_off = (int32_t)((n_slots + 1) * SB);
@@ -105,20 +108,10 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
             u.a = off_of(d.fa);
         } else if (op == D_SIN || op == D_COS || op == D_EXP || op == D_LN || op == D_RECIPEXPM1 || op == D_EXPSQR ||
                    op == D_EXPSQRNEG || op == D_EXPNEG || op == D_SINCOS) {
-            static const uint32_t H[] = {H1_SIN, H1_COS, H1_EXP, H1_LN, H1_RECIPEXPM1, H1_EXPSQR, H1_EXPSQRNEG, H1_EXPNEG, H1_SINCOS};
-            const uint32_t h = H[op - D_SIN];
-            if (ka == KIND_K) { // a constant argument: materialise it in ACC first (unary: ACC is free)
-                UI l;
-                l.uop = U_LOADK;
-                l.a = koff(d.fa);
-                U.push_back(l);
-            }
-            uint32_t prefixed = 0;
+            uint32_t pre_off = NO_PREFIX;
             if (d.prefix == PREFIX_FMA) {
-                prefixed = 1;
-                u.b = koff(d.fb); // K[b], K[b+1] are adjacent in the device constant table
+                pre_off = koff(d.fb); // K[b], K[b+1] are adjacent in the device constant table
             } else if (d.prefix == PREFIX_MUL) {
-                prefixed = 1;
                 const double k1 = dp.consts[field_index(d.fb)];
                 uint64_t bits;
                 std::memcpy(&bits, &k1, 8);
@@ -129,11 +122,38 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
                     K.push_back(-0.0); // fma(x, k1, -0.0) == x * k1 for every x, zeros and NaN included
                     it = mul_pair.emplace(bits, o).first;
                 }
-                u.b = it->second;
+                pre_off = it->second;
             }
-            u.uop = U_H1 + 4 * h + 2 * prefixed + (ka == KIND_S ? 0u : 1u);
-            u.a = off_of(d.fa);
-            if (op == D_SINCOS) u.c = (uint32_t)dest_of(d.fc);
+            if (op == D_RECIPEXPM1) { // cold
+                u.uop = U_G + G_RECIPEXPM1;
+                u.a = off_of(d.fa);
+                u.b = pre_off;
+                u.kinds = kinds3(d.fa, FIELD_NONE, FIELD_NONE);
+            } else {
+                static const uint32_t H[] = {H1_SIN, H1_COS, H1_EXP, H1_LN, 0, H1_EXPSQR, H1_EXPSQRNEG, H1_EXPNEG, H1_SINCOS};
+                const uint32_t h = H[op - D_SIN];
+                // the hot heavy handlers read their operand from a slot only
+                if (ka == KIND_K) { // constant argument: materialise it through the reserved slot
+                    UI l;
+                    l.uop = U_LOADK;
+                    l.a = koff(d.fa);
+                    l.d = out.acc_off;
+                    U.push_back(l);
+                    u.a = (uint32_t)out.acc_off;
+                } else if (ka == KIND_ACC) { // the producer is the previous micro-op: make it store its result
+                    if (U.empty()) {
+                        err = "internal: accumulator operand without a producer";
+                        return SAF_ERR_INVALID_PROGRAM;
+                    }
+                    if (U.back().d == NO_DEST) U.back().d = out.acc_off;
+                    u.a = (uint32_t)U.back().d;
+                } else {
+                    u.a = off_of(d.fa);
+                }
+                u.uop = U_H1 + 2 * h + (pre_off != NO_PREFIX ? 1u : 0u);
+                u.b = pre_off;
+                if (op == D_SINCOS) u.c = (uint32_t)dest_of(d.fc);
+            }
         } else if (op == D_ADD || op == D_MUL || op == D_NEGMUL) {
             const uint32_t i = op == D_ADD ? BC_ADD : op == D_MUL ? BC_MUL : BC_NEGMUL;
             uint32_t fa = d.fa, fb = d.fb;
@@ -226,7 +246,8 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
     U.push_back(UI());
 
     // ---- image: [constants, padded to 32 bytes][micro-instructions] ----
-    const size_t k_words = (K.size() + 3) & ~(size_t)3;
+    // never empty: byte offset 0 is not a valid program counter (hot_run returns pc = 0 for "program finished")
+    const size_t k_words = std::max<size_t>(4, (K.size() + 3) & ~(size_t)3);
     out.image.assign(k_words + U.size() * UINSTR_WORDS, 0);
     for (size_t i = 0; i < K.size(); ++i) std::memcpy(&out.image[i], &K[i], 8);
     for (size_t i = 0; i < U.size(); ++i) {

@@ -17,8 +17,9 @@ struct PackedProgram {
     std::vector<uint64_t> image;
     uint32_t code_off = 0;             // byte offset of the first micro-instruction in the image
     uint32_t n_instr = 0;
-    uint32_t n_slots = 0;              // register-file slots incl. staging slots for Builtin3/4 operands
-    int32_t x0_off = -1, x1_off = -1;  // staging slots (byte offsets), -1 when unused
+    uint32_t n_slots = 0;              // register-file slots incl. the reserved ones below
+    int32_t acc_off = 0;               // reserved slot through which ACC is handed to cold micro-ops / heavy ops
+    int32_t x0_off = -1, x1_off = -1;  // staging slots of Builtin3/4 operands (byte offsets), -1 when unused
     std::vector<int32_t> param_off;    // per parameter: register-file byte offset, -1 = never read
     std::vector<int32_t> result_off;   // per result: byte offset (register file or image)
     std::vector<uint8_t> result_is_k;  // per result: 1 = constant (offset into the image)

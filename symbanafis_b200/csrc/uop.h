@@ -16,13 +16,17 @@
 // Operand kinds S (register-file slot), K (constant table), A (accumulator = previous result), see
 // saf_isa.h.  Specialised micro-op families (operand kinds fixed by the opcode):
 //   U1   light unary        x {S, A}
-//   H1   heavy unary        x {S, A} x {plain, affine prefix arg = fma(a, K[b], K[b+8])}
+//   H1   heavy unary        S only (the packer gives an accumulator operand a slot: handlers that never read
+//                           ACC let the compiler keep ACC in place across the dispatch loop)
+//                           x {plain, affine prefix arg = fma(a, K[b], K[b+8])}
 //   BC   commutative binary (add, mul, negmul), operands ordered S < K < A:   SS SK SA KA AA
 //   BN   ordered binary (sub, div):                                 SS SK KS SA AS KA AK AA
 //   T    fused multiply-add family, product operands ordered S < K < A, at most one A:
 //                                                      SSS SSK SSA SKS SKK SKA SAS SAK KAS KAK
-// Everything else (pow, powi, builtins, operand staging, the rare kind combinations above) runs through
-// generic micro-ops that decode `kinds` at run time.
+// Everything else (pow, powi, 1/expm1, builtins, operand staging, the rare kind combinations above) is COLD:
+// generic micro-ops that decode `kinds` at run time inside one out-of-line function which works memory to
+// memory (ACC is exchanged through a reserved register-file slot), so that their register needs and call
+// sequences do not weigh on the hot dispatch loop.
 #pragma once
 #include <stdint.h>
 
@@ -35,10 +39,10 @@ constexpr int UINSTR_WORDS = 4; // 64-bit words
 
 constexpr uint32_t U_END = 0, U_LOADK = 1;
 constexpr uint32_t U_U1 = 2;                                  // + 2 * u + (a is A)
-constexpr uint32_t U_H1 = U_U1 + 2 * D_N_LIGHT_UNARY;         // + 4 * h + 2 * prefixed + (a is A)
-constexpr uint32_t H1_SIN = 0, H1_COS = 1, H1_EXP = 2, H1_LN = 3, H1_RECIPEXPM1 = 4, H1_EXPSQR = 5,
-                   H1_EXPSQRNEG = 6, H1_EXPNEG = 7, H1_SINCOS = 8, H1_COUNT = 9;
-constexpr uint32_t U_BC = U_H1 + 4 * H1_COUNT;                // + 5 * i + variant
+constexpr uint32_t U_H1 = U_U1 + 2 * D_N_LIGHT_UNARY;         // + 2 * h + prefixed
+constexpr uint32_t H1_SIN = 0, H1_COS = 1, H1_EXP = 2, H1_LN = 3, H1_EXPSQR = 4, H1_EXPSQRNEG = 5, H1_EXPNEG = 6,
+                   H1_SINCOS = 7, H1_COUNT = 8;
+constexpr uint32_t U_BC = U_H1 + 2 * H1_COUNT;                // + 5 * i + variant
 constexpr uint32_t BC_ADD = 0, BC_MUL = 1, BC_NEGMUL = 2, BC_COUNT = 3;
 constexpr uint32_t BC_SS = 0, BC_SK = 1, BC_SA = 2, BC_KA = 3, BC_AA = 4;
 constexpr uint32_t U_BN = U_BC + 5 * BC_COUNT;                // + 8 * i + variant
@@ -50,7 +54,8 @@ constexpr uint32_t T_SSS = 0, T_SSK = 1, T_SSA = 2, T_SKS = 3, T_SKK = 4, T_SKA 
                    T_KAS = 8, T_KAK = 9;
 constexpr uint32_t U_G = U_T + 10 * T_COUNT;                  // generic micro-ops
 constexpr uint32_t G_POW = 0, G_POWI = 1, G_BUILTIN1 = 2, G_BUILTIN2 = 3, G_BUILTIN3 = 4, G_BUILTIN4 = 5,
-                   G_ARG2 = 6, G_FMA = 7, G_FMS = 8, G_FNMA = 9, G_FNMS = 10, G_DIV = 11, G_COUNT = 12;
+                   G_ARG2 = 6, G_FMA = 7, G_FMS = 8, G_FNMA = 9, G_FNMS = 10, G_DIV = 11, G_RECIPEXPM1 = 12, G_COUNT = 13;
+constexpr uint32_t NO_PREFIX = 0xffffffffu; // field b of G_RECIPEXPM1 when there is no affine prefix
 constexpr uint32_t U_COUNT = U_G + G_COUNT;
 
 constexpr int32_t NO_DEST = -1;

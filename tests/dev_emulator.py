@@ -184,27 +184,30 @@ def run_device_program(code: Sequence[int], consts: np.ndarray, param_slot: Sequ
 
 
 # ---- packed micro-instruction image (symbanafis_b200/csrc/uop.h, produced by pack.cpp) -------------------
-N_H1 = 9
+N_H1 = 8
 U_END, U_LOADK, U_U1 = 0, 1, 2
 U_H1 = U_U1 + 2 * N_LIGHT_UNARY
-U_BC = U_H1 + 4 * N_H1
+U_BC = U_H1 + 2 * N_H1
 U_BN = U_BC + 5 * 3
 U_T = U_BN + 8 * 2
 U_G = U_T + 10 * 4
-H1_NAMES = ["sin", "cos", "exp", "ln", "recipexpm1", "expsqr", "expsqrneg", "expneg", "sincos"]
+H1_NAMES = ["sin", "cos", "exp", "ln", "expsqr", "expsqrneg", "expneg", "sincos"]
 BC_NAMES = ["add", "mul", "negmul"]
 BC_KINDS = ["SS", "SK", "SA", "KA", "AA"]
 BN_NAMES = ["sub", "div"]
 BN_KINDS = ["SS", "SK", "KS", "SA", "AS", "KA", "AK", "AA"]
 T_NAMES = ["fma", "fms", "fnma", "fnms"]
 T_KINDS = ["SSS", "SSK", "SSA", "SKS", "SKK", "SKA", "SAS", "SAK", "KAS", "KAK"]
-G_NAMES = ["pow", "powi", "builtin1", "builtin2", "builtin3", "builtin4", "arg2", "fma", "fms", "fnma", "fnms", "div"]
+G_NAMES = ["pow", "powi", "builtin1", "builtin2", "builtin3", "builtin4", "arg2", "fma", "fms", "fnma", "fnms", "div",
+           "recipexpm1"]
+NO_PREFIX = 0xFFFFFFFF
 
 
 def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iters: int = 1) -> List[np.ndarray]:
     """Executes the packed image exactly as kernel.cu does (register file addressed by byte offset, constants
     read from the image, accumulator, sign-tested destination store), leaf math delegated to the oracle."""
     image = np.asarray(pk["image"], dtype=np.uint64)
+    assert int(pk["code_off"]) >= 32, "byte offset 0 must not be a program counter (hot_run returns 0 for finished)"
     kview = image.view(np.float64)
     P = int(pk["points_per_thread"])
     slot_bytes = 128 * 8 * P
@@ -272,9 +275,9 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
                 x = acc if is_a else S(fa)
                 r = x.copy() if name == "copy" else ref1(_UNARY_REF[name], x)
             elif uop < U_BC:
-                h, v = divmod(uop - U_H1, 4)
-                x = acc if (v & 1) else S(fa)
-                if v & 2:
+                h, prefixed = divmod(uop - U_H1, 2)
+                x = S(fa)  # the hot heavy handlers never read ACC
+                if prefixed:
                     x = ref3("MulAdd", x, K(fb), K(fb + 8))
                 name = H1_NAMES[h]
                 if name == "expneg":
@@ -302,6 +305,11 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
                 ka, kb, kc = kinds & 3, (kinds >> 2) & 3, (kinds >> 4) & 3
                 if name in ("pow", "div"):
                     r = ref2(_BINARY_REF[name], by_kind(ka, fa), by_kind(kb, fb))
+                elif name == "recipexpm1":
+                    x = by_kind(ka, fa)
+                    if fb != NO_PREFIX:
+                        x = ref3("MulAdd", x, K(fb), K(fb + 8))
+                    r = ref1("RecipExpm1", x)
                 elif name == "powi":
                     r = _leaf(("Powi", 1, 0, i32(imm)), 1).eval_batch([by_kind(ka, fa)], n_points)[0]
                 elif name == "builtin1":
