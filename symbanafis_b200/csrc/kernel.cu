@@ -36,21 +36,11 @@
 // needs it (see devmath.cuh).
 #include "kernel.cuh"
 
+#include <cstddef>
 #include <cstdio>
 
 #include "devmath.cuh"
 #include "leanmath.cuh"
-
-// resident blocks per SM the register allocation aims for, per points-per-thread variant (tuning knobs)
-#ifndef SAF_MINB_P4
-#define SAF_MINB_P4 6
-#endif
-#ifndef SAF_MINB_P2
-#define SAF_MINB_P2 6
-#endif
-#ifndef SAF_MINB_P1
-#define SAF_MINB_P1 6
-#endif
 
 namespace saf {
 
@@ -78,52 +68,69 @@ __device__ __forceinline__ void st_stream2(double *p, double a, double b) {
 
 extern __shared__ __align__(16) unsigned char saf_smem[];
 
-// Shared-memory register file.  For P >= 2 a thread's points are stored as P/2 pairs; pair g of the slot
-// at byte offset `off` lives at  off + g * PAIR_BYTES + tid * 16  (`my` already includes tid * 16).
+// Shared-memory register file, addressed by 32-bit shared-space addresses.  For P >= 2 a thread's points are
+// stored as P/2 pairs; pair g of the slot at byte offset `off` lives at  off + g * PAIR_BYTES + tid * 16
+// (`my` = block's shared base + tid * 16).  The base arrives as an opaque function argument / is computed once:
+// when the code mentions the shared-memory symbol itself ptxas re-derives the base (S2UR + UMOV + ULEA) on
+// every access.
+__device__ __forceinline__ void lds64(uint32_t addr, double &x) {
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr));
+}
+__device__ __forceinline__ void lds128(uint32_t addr, double &x, double &y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double x) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_base32() { return (uint32_t)__cvta_generic_to_shared(saf_smem); }
+
 template <int P>
 struct Rf {
     static constexpr uint32_t PAIR_BYTES = BLOCK_THREADS * 16;
-    __device__ __forceinline__ static char *mine() {
-        return reinterpret_cast<char *>(saf_smem) + threadIdx.x * (P == 1 ? 8 : 16);
-    }
-    __device__ __forceinline__ static void load(const char *my, uint32_t off, Pt<P> &o) {
-        const char *p = my + off;
+    __device__ __forceinline__ static uint32_t mine(uint32_t smem32) { return smem32 + threadIdx.x * (P == 1 ? 8u : 16u); }
+    __device__ __forceinline__ static void load(uint32_t my, uint32_t off, Pt<P> &o) {
+        const uint32_t p = my + off;
         if constexpr (P == 1) {
-            o.v[0] = *reinterpret_cast<const double *>(p);
+            lds64(p, o.v[0]);
         } else {
 #pragma unroll
-            for (int g = 0; g < P / 2; ++g) {
-                double2 t = *reinterpret_cast<const double2 *>(p + g * PAIR_BYTES);
-                o.v[2 * g] = t.x;
-                o.v[2 * g + 1] = t.y;
-            }
+            for (int g = 0; g < P / 2; ++g) lds128(p + g * PAIR_BYTES, o.v[2 * g], o.v[2 * g + 1]);
         }
     }
-    __device__ __forceinline__ static void store(char *my, uint32_t off, const Pt<P> &o) {
-        char *p = my + off;
+    __device__ __forceinline__ static void store(uint32_t my, uint32_t off, const Pt<P> &o) {
+        const uint32_t p = my + off;
         if constexpr (P == 1) {
-            *reinterpret_cast<double *>(p) = o.v[0];
+            sts64(p, o.v[0]);
         } else {
 #pragma unroll
-            for (int g = 0; g < P / 2; ++g)
-                *reinterpret_cast<double2 *>(p + g * PAIR_BYTES) = make_double2(o.v[2 * g], o.v[2 * g + 1]);
+            for (int g = 0; g < P / 2; ++g) sts128(p + g * PAIR_BYTES, o.v[2 * g], o.v[2 * g + 1]);
         }
     }
 };
 
 #define SAF_FOR_P _Pragma("unroll") for (int p = 0; p < P; ++p)
 
-__device__ __forceinline__ uint2 split64(unsigned long long w) { return make_uint2((uint32_t)w, (uint32_t)(w >> 32)); }
+// Markers for tools/patch_brx.py: nvcc lowers a C++ switch to a compare tree (ptxas then folds only 3-case
+// leaves into jump tables); the build rewrites the PTX of hot_run to ONE brx.idx over all micro-ops.  The
+// markers are PTX comments that carry the opcode register / the case value to the patcher.
+#define SAF_DISPATCH(u) asm volatile("// SAF_DISPATCH %0 %1;" ::"r"(u), "n"((int)U_COUNT));
+#define SAF_CASE(v) asm volatile("// SAF_CASE %0;" ::"n"((int)(v)));
+#define SAF_CASE_DEFAULT asm volatile("// SAF_CASE default;");
 
-// Per-block context behind the register file in shared memory: what hot_run needs besides the image.
-struct BlockCtx {
-    uint32_t n_params;
-    uint32_t result_k_mask;
-    int32_t acc_off;
-    uint32_t code_off;
-    int32_t param_off[MAX_COLS];
-    int32_t result_off[MAX_OUTS];
-};
+__device__ __forceinline__ uint2 split64(unsigned long long w) { return make_uint2((uint32_t)w, (uint32_t)(w >> 32)); }
 
 } // namespace
 
@@ -143,7 +150,7 @@ template <int P>
 __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int32_t acc_off, int32_t x0_off,
                                      int32_t x1_off) {
     using RF = Rf<P>;
-    char *const my = RF::mine();
+    const uint32_t my = RF::mine(smem_base32());
     const unsigned long long *w = reinterpret_cast<const unsigned long long *>(img + cur);
     const uint2 q0 = split64(w[0]), q1 = split64(w[1]), q2 = split64(w[2]), q3 = split64(w[3]);
     const uint32_t uop = q0.x, fa = q1.x, fb = q1.y, fc = q2.x, imm = q2.y, kinds = q3.x;
@@ -230,28 +237,34 @@ __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int
 // counter travels in the high word.  IMG_SMEM: the image sits in shared memory at byte offset `img_s`,
 // otherwise in global memory at `img_g`.
 template <int P, bool IMG_SMEM>
-__device__ __noinline__ unsigned long long hot_run(uint32_t img_s, const unsigned char *img_g, uint32_t ctx_off,
-                                                   uint32_t pc, uint32_t it, uint32_t iters) {
+__device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img_s, const unsigned char *img_g,
+                                                   uint32_t ctx_off, uint32_t pc, uint32_t it, uint32_t iters) {
     using RF = Rf<P>;
-    char *const my = RF::mine();
-    const BlockCtx *const ctx = reinterpret_cast<const BlockCtx *>(saf_smem + ctx_off);
-    const unsigned char *const img_sm = saf_smem + img_s;
+    const uint32_t my = RF::mine(smem32);
+    const uint32_t ctx = smem32 + ctx_off;   // BlockCtx
+    const uint32_t img_sm = smem32 + img_s;  // image, when staged in shared memory
+    const uint32_t acc_off = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, acc_off));
 
     auto img128 = [&](uint32_t off) -> uint4 { // 16 bytes of the image (warp-uniform address)
-        if constexpr (IMG_SMEM) return *reinterpret_cast<const uint4 *>(img_sm + off);
+        if constexpr (IMG_SMEM) return lds_u128(img_sm + off);
         else return __ldg(reinterpret_cast<const uint4 *>(img_g + off));
     };
     auto img32 = [&](uint32_t off) -> uint32_t {
-        if constexpr (IMG_SMEM) return *reinterpret_cast<const uint32_t *>(img_sm + off);
+        if constexpr (IMG_SMEM) return lds_u32(img_sm + off);
         else return __ldg(reinterpret_cast<const uint32_t *>(img_g + off));
     };
     auto konst = [&](uint32_t off) -> double {
-        if constexpr (IMG_SMEM) return *reinterpret_cast<const double *>(img_sm + off);
-        else return __ldg(reinterpret_cast<const double *>(img_g + off));
+        if constexpr (IMG_SMEM) {
+            double k;
+            lds64(img_sm + off, k);
+            return k;
+        } else {
+            return __ldg(reinterpret_cast<const double *>(img_g + off));
+        }
     };
 
     Pt<P> acc;
-    RF::load(my, (uint32_t)ctx->acc_off, acc);
+    RF::load(my, acc_off, acc);
 
     for (;;) {
         for (;;) {
@@ -271,46 +284,47 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t img_s, const unsigne
 
 // light unary: a from a slot / from ACC
 #define U1CASE(OP, EXPR)                                                                                   \
-    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY): LS(a, fa) SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } break;
+    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY): SAF_CASE(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY)) LS(a, fa) SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_CASE(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1) SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } break;
 // heavy unary: operand from a slot, {plain, affine prefix}; BODY maps a.v -> acc.v and never reads ACC
 #define H1PREFIX { const double k1_ = konst(fb), k2_ = konst(fb + 8); SAF_FOR_P a.v[p] = __fma_rn(a.v[p], k1_, k2_); }
 #define H1CASE(H, BODY)                                                                                    \
-    case U_H1 + 2 * (H) + 0: LS(a, fa) { BODY } break;                                                     \
-    case U_H1 + 2 * (H) + 1: LS(a, fa) H1PREFIX { BODY } break;
+    case U_H1 + 2 * (H) + 0: SAF_CASE(U_H1 + 2 * (H) + 0) LS(a, fa) { BODY } break;                                                     \
+    case U_H1 + 2 * (H) + 1: SAF_CASE(U_H1 + 2 * (H) + 1) LS(a, fa) H1PREFIX { BODY } break;
 // commutative binary: SS SK SA KA AA
 #define BCCASE(I, EXPR)                                                                                    \
-    case U_BC + 5 * (I) + BC_SS: LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BC + 5 * (I) + BC_SK: LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BC + 5 * (I) + BC_SA: LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BC + 5 * (I) + BC_KA: { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BC + 5 * (I) + BC_AA: SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break;
+    case U_BC + 5 * (I) + BC_SS: SAF_CASE(U_BC + 5 * (I) + BC_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BC + 5 * (I) + BC_SK: SAF_CASE(U_BC + 5 * (I) + BC_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BC + 5 * (I) + BC_SA: SAF_CASE(U_BC + 5 * (I) + BC_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BC + 5 * (I) + BC_KA: SAF_CASE(U_BC + 5 * (I) + BC_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BC + 5 * (I) + BC_AA: SAF_CASE(U_BC + 5 * (I) + BC_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break;
 // ordered binary: SS SK KS SA AS KA AK AA
 #define BNCASE(I, EXPR)                                                                                    \
-    case U_BN + 8 * (I) + BN_SS: LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BN + 8 * (I) + BN_SK: LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BN + 8 * (I) + BN_KS: LS(b, fb) { const double x = konst(fa); SAF_FOR_P { const double y = b.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BN + 8 * (I) + BN_SA: LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BN + 8 * (I) + BN_AS: LS(b, fb) SAF_FOR_P { const double x = acc.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BN + 8 * (I) + BN_KA: { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BN + 8 * (I) + BN_AK: { const double y = konst(fb); SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BN + 8 * (I) + BN_AA: SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break;
+    case U_BN + 8 * (I) + BN_SS: SAF_CASE(U_BN + 8 * (I) + BN_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BN + 8 * (I) + BN_SK: SAF_CASE(U_BN + 8 * (I) + BN_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BN + 8 * (I) + BN_KS: SAF_CASE(U_BN + 8 * (I) + BN_KS) LS(b, fb) { const double x = konst(fa); SAF_FOR_P { const double y = b.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BN + 8 * (I) + BN_SA: SAF_CASE(U_BN + 8 * (I) + BN_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BN + 8 * (I) + BN_AS: SAF_CASE(U_BN + 8 * (I) + BN_AS) LS(b, fb) SAF_FOR_P { const double x = acc.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
+    case U_BN + 8 * (I) + BN_KA: SAF_CASE(U_BN + 8 * (I) + BN_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BN + 8 * (I) + BN_AK: SAF_CASE(U_BN + 8 * (I) + BN_AK) { const double y = konst(fb); SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_BN + 8 * (I) + BN_AA: SAF_CASE(U_BN + 8 * (I) + BN_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break;
 // fused multiply-add family: x * y (+/-) z
 #define TCASE(T, EXPR)                                                                                     \
-    case U_T + 10 * (T) + T_SSS: { const uint32_t fc = FC; LS(a, fa) LS(b, fb) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SSK: { const uint32_t fc = FC; LS(a, fa) LS(b, fb) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SSA: { LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SKS: { const uint32_t fc = FC; LS(a, fa) LS(c, fc) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SKK: { const uint32_t fc = FC; LS(a, fa) const double y = konst(fb), z = konst(fc); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SKA: { LS(a, fa) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SAS: { const uint32_t fc = FC; LS(a, fa) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SAK: { const uint32_t fc = FC; LS(a, fa) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_KAS: { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_KAK: { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break;
+    case U_T + 10 * (T) + T_SSS: SAF_CASE(U_T + 10 * (T) + T_SSS) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SSK: SAF_CASE(U_T + 10 * (T) + T_SSK) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SSA: SAF_CASE(U_T + 10 * (T) + T_SSA) { LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SKS: SAF_CASE(U_T + 10 * (T) + T_SKS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SKK: SAF_CASE(U_T + 10 * (T) + T_SKK) { const uint32_t fc = FC; LS(a, fa) const double y = konst(fb), z = konst(fc); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SKA: SAF_CASE(U_T + 10 * (T) + T_SKA) { LS(a, fa) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SAS: SAF_CASE(U_T + 10 * (T) + T_SAS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_SAK: SAF_CASE(U_T + 10 * (T) + T_SAK) { const uint32_t fc = FC; LS(a, fa) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_KAS: SAF_CASE(U_T + 10 * (T) + T_KAS) { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
+    case U_T + 10 * (T) + T_KAK: SAF_CASE(U_T + 10 * (T) + T_KAK) { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break;
 
+            SAF_DISPATCH(uop)
             switch (uop) {
-            case U_END: goto program_end;
-            case U_LOADK: { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } break;
+            case U_END: SAF_CASE(U_END) goto program_end;
+            case U_LOADK: SAF_CASE(U_LOADK) { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } break;
 
             U1CASE(D_COPY, x)
             U1CASE(D_NEG, -x)
@@ -350,8 +364,8 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t img_s, const unsigne
             TCASE(T_FNMS, __fma_rn(-x, y, -z))
 
             // cold micro-ops leave the loop: ACC goes to its slot, the caller runs cold_op and re-enters
-            default:
-                RF::store(my, (uint32_t)ctx->acc_off, acc);
+            default: SAF_CASE_DEFAULT
+                RF::store(my, acc_off, acc);
                 return ((unsigned long long)it << 32) | cur;
             }
             if (fd >= 0) RF::store(my, (uint32_t)fd, acc);
@@ -360,28 +374,33 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t img_s, const unsigne
         if (++it >= iters) return 0ull;
         // ---- in-kernel feedback: parameter j <- result j (result slots never alias parameter slots,
         // lower.cpp); the state stays on chip between iterations ----
-        for (uint32_t j = 0; j < ctx->n_params; ++j) {
-            const int32_t s = ctx->param_off[j];
-            if (s < 0) continue;
-            Pt<P> v;
-            if ((ctx->result_k_mask >> j) & 1u) {
-                const double k = konst((uint32_t)ctx->result_off[j]);
-                SAF_FOR_P v.v[p] = k;
-            } else {
-                RF::load(my, (uint32_t)ctx->result_off[j], v);
+        {
+            const uint32_t n_params = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, n_params));
+            const uint32_t k_mask = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, result_k_mask));
+            for (uint32_t j = 0; j < n_params; ++j) {
+                const int32_t s = (int32_t)lds_u32(ctx + (uint32_t)offsetof(BlockCtx, param_off) + 4u * j);
+                if (s < 0) continue;
+                const uint32_t r = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, result_off) + 4u * j);
+                Pt<P> v;
+                if ((k_mask >> j) & 1u) {
+                    const double k = konst(r);
+                    SAF_FOR_P v.v[p] = k;
+                } else {
+                    RF::load(my, r, v);
+                }
+                RF::store(my, (uint32_t)s, v);
             }
-            RF::store(my, (uint32_t)s, v);
+            pc = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, code_off));
         }
-        pc = ctx->code_off;
     }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------
 template <int P, bool IMG_SMEM>
-__global__ void __launch_bounds__(BLOCK_THREADS, (P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1))
-saf_interp_kernel(const __grid_constant__ LaunchDesc d) {
+__device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     using RF = Rf<P>;
-    char *const my = RF::mine();
+    const uint32_t smem32 = smem_base32();
+    const uint32_t my = RF::mine(smem32);
 
     // ---- stage the block context (and the image) behind the register file ----
     const uint32_t ctx_off = d.n_slots * (uint32_t)(BLOCK_THREADS * P * 8);
@@ -444,7 +463,7 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d) {
         {
             uint32_t pc = d.code_off, it = 0;
             for (;;) {
-                const unsigned long long st = hot_run<P, IMG_SMEM>(img_s, d.image_global, ctx_off, pc, it, iters);
+                const unsigned long long st = hot_run<P, IMG_SMEM>(smem32, img_s, d.image_global, ctx_off, pc, it, iters);
                 pc = (uint32_t)st;
                 if (pc == 0u) break;
                 it = (uint32_t)(st >> 32);
@@ -481,11 +500,25 @@ saf_interp_kernel(const __grid_constant__ LaunchDesc d) {
     }
 }
 
+// ---- entry points (extern "C": looked up by name in the cubin, launch.cu) ---------------------------------
+#define SAF_ENTRY(NAME, P, SM, MINB)                                                                       \
+    extern "C" __global__ void __launch_bounds__(BLOCK_THREADS, MINB) NAME(const __grid_constant__ LaunchDesc d) { \
+        interp_body<P, SM>(d);                                                                             \
+    }
+SAF_ENTRY(saf_interp_p4_smem, 4, true, SAF_MINB_P4)
+#ifndef SAF_FAST_BUILD
+SAF_ENTRY(saf_interp_p4_gmem, 4, false, SAF_MINB_P4)
+SAF_ENTRY(saf_interp_p2_smem, 2, true, SAF_MINB_P2)
+SAF_ENTRY(saf_interp_p2_gmem, 2, false, SAF_MINB_P2)
+SAF_ENTRY(saf_interp_p1_smem, 1, true, SAF_MINB_P1)
+SAF_ENTRY(saf_interp_p1_gmem, 1, false, SAF_MINB_P1)
+#endif
+
 // ---- FP64 pipe peak probe ---------------------------------------------------------------------------
 // The roofline of this path is the FP64 pipe (BASELINE.json north_star), whose peak is not in
 // MEASURED_PEAKS.json.  This kernel measures it on the box: 8 independent DFMA chains per thread,
 // enough warps to saturate the pipe; bench.py divides lane-instructions by the CUDA-event time.
-__global__ void __launch_bounds__(256) saf_fp64_peak_kernel(double *sink, int iters, double seed) {
+extern "C" __global__ void __launch_bounds__(256) saf_fp64_peak_kernel(double *sink, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
            a7 = a0 + 7;
     const double m = 1.0000001, c = 1e-9;
@@ -499,124 +532,6 @@ __global__ void __launch_bounds__(256) saf_fp64_peak_kernel(double *sink, int it
     }
     double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (s == 123.456) sink[0] = s; // never true: keeps the chains alive
-}
-
-cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream) {
-    saf_fp64_peak_kernel<<<blocks, 256, 0, stream>>>(sink, iters, 0.5);
-    return cudaGetLastError();
-}
-
-// ---- host side -------------------------------------------------------------------------------------
-
-template <int P, bool IMG_SMEM>
-static cudaError_t launch_one(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream) {
-    auto kern = saf_interp_kernel<P, IMG_SMEM>;
-    // opt in once per (instantiation, device) to the full dynamic shared-memory carve-out
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-        int optin = 0;
-        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
-    kern<<<shape.grid, shape.block, shape.smem_bytes, stream>>>(desc);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream) {
-#ifdef SAF_FAST_BUILD // developer builds: one instantiation only (tools/sass_probe.sh)
-    if (shape.points_per_thread != 4 || !shape.image_in_smem) return cudaErrorNotSupported;
-    return launch_one<4, true>(desc, shape, stream);
-#else
-    const bool s = shape.image_in_smem;
-    switch (shape.points_per_thread) {
-    case 4: return s ? launch_one<4, true>(desc, shape, stream) : launch_one<4, false>(desc, shape, stream);
-    case 2: return s ? launch_one<2, true>(desc, shape, stream) : launch_one<2, false>(desc, shape, stream);
-    default: return s ? launch_one<1, true>(desc, shape, stream) : launch_one<1, false>(desc, shape, stream);
-    }
-#endif
-}
-
-// register file + block context (+ the image when it is staged in shared memory)
-size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t image_bytes_in_smem) {
-    return (size_t)n_slots * (size_t)BLOCK_THREADS * (size_t)points_per_thread * 8 + sizeof(BlockCtx) +
-           ((image_bytes_in_smem + 15) & ~(size_t)15);
-}
-
-static int resident_blocks_for(int P) { return P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1; }
-
-cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
-                                     int force_points_per_thread, int *points_per_thread) {
-    int sms = 0, smem_optin = 0;
-    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (e != cudaSuccess) return e;
-    const size_t smem_sm = (size_t)smem_optin; // per-block opt-in limit ~= per-SM capacity minus 1 KB
-    // More points per thread amortise the dispatch; they need (a) 16-byte aligned columns, (b) enough
-    // points to still give every SM several blocks, (c) a register file that leaves >= 2 blocks per SM.
-    // n_slots + 3: room for the reserved slots the packer adds.
-    auto fits = [&](int p, int min_blocks) {
-        return (interpreter_smem_bytes(n_slots + 3, p, 0) + 1024) * (size_t)min_blocks <= smem_sm + 1024;
-    };
-    auto enough = [&](int p) {
-        return n_points >= (unsigned long long)sms * 3ull * (unsigned long long)BLOCK_THREADS * (unsigned long long)p;
-    };
-    int P = 1;
-    if (aligned16 && enough(4) && fits(4, 2)) P = 4;
-    else if (aligned16 && enough(2) && fits(2, 2)) P = 2;
-    if (force_points_per_thread == 1 || (aligned16 && (force_points_per_thread == 2 || force_points_per_thread == 4)))
-        P = force_points_per_thread;
-    while (P > 1 && !fits(P, 1)) P >>= 1;
-    if (!fits(P, 1)) return cudaErrorInvalidConfiguration;
-    *points_per_thread = P;
-    return cudaSuccess;
-}
-
-cudaError_t choose_shape(int device, uint32_t n_slots, size_t image_bytes, unsigned long long n_points, int P,
-                         LaunchShape *shape) {
-    int sms = 0, smem_optin = 0;
-    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (e != cudaSuccess) return e;
-    const size_t rf = interpreter_smem_bytes(n_slots, P, 0);
-    if (rf > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
-    // the image rides in shared memory when it is small next to the register file (it must not cost a
-    // resident block) and always when it is tiny
-    bool in_smem = image_bytes <= IMAGE_SMEM_ALWAYS;
-    if (!in_smem && image_bytes <= IMAGE_SMEM_MAX) {
-        const size_t with = interpreter_smem_bytes(n_slots, P, image_bytes);
-        const size_t blocks_without = ((size_t)smem_optin + 1024) / (rf + 1024);
-        const size_t blocks_with = with <= (size_t)smem_optin ? ((size_t)smem_optin + 1024) / (with + 1024) : 0;
-        const size_t want = (size_t)resident_blocks_for(P);
-        in_smem = blocks_with >= (blocks_without < want ? blocks_without : want);
-    }
-    size_t smem = interpreter_smem_bytes(n_slots, P, in_smem ? image_bytes : 0);
-    if (smem > (size_t)smem_optin) {
-        in_smem = false;
-        smem = rf;
-    }
-    size_t resident = (size_t)resident_blocks_for(P); // __launch_bounds__ register budget
-    const size_t by_smem = ((size_t)smem_optin + 1024) / (smem + 1024);
-    if (by_smem < resident) resident = by_smem;
-    if (resident < 1) resident = 1;
-    const unsigned long long tile = (unsigned long long)BLOCK_THREADS * P;
-    const unsigned long long n_tiles = (n_points + tile - 1) / tile;
-    unsigned long long grid = (unsigned long long)sms * resident;
-    if (grid > n_tiles) grid = n_tiles;
-    if (grid < 1) grid = 1;
-    shape->points_per_thread = P;
-    shape->block = BLOCK_THREADS;
-    shape->grid = (int)grid;
-    shape->smem_bytes = smem;
-    shape->image_in_smem = in_smem;
-    return cudaSuccess;
 }
 
 } // namespace saf

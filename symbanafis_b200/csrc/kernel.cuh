@@ -6,6 +6,18 @@
 #include "saf_isa.h"
 #include "uop.h"
 
+// resident blocks per SM the register allocation aims for, per points-per-thread variant (tuning knobs)
+#ifndef SAF_MINB_P4
+#define SAF_MINB_P4 6
+#endif
+#ifndef SAF_MINB_P2
+#define SAF_MINB_P2 6
+#endif
+#ifndef SAF_MINB_P1
+#define SAF_MINB_P1 6
+#endif
+
+
 namespace saf {
 
 // Everything the kernel needs besides the program image, passed by value in the kernel parameter
@@ -54,6 +66,16 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
 cudaError_t choose_shape(int device, uint32_t n_slots, size_t image_bytes, unsigned long long n_points,
                          int points_per_thread, LaunchShape *shape);
 size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t image_bytes_in_smem);
+
+// Per-block context behind the register file in shared memory: what hot_run needs besides the image.
+struct BlockCtx {
+    uint32_t n_params;
+    uint32_t result_k_mask;
+    int32_t acc_off;
+    uint32_t code_off;
+    int32_t param_off[MAX_COLS];
+    int32_t result_off[MAX_OUTS];
+};
 
 // FP64-pipe peak probe: blocks x 256 threads, each `iters` x 64 dependent-chain DFMAs.
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);

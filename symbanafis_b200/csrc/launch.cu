@@ -1,0 +1,210 @@
+// launch.cu -- host side of the interpreter kernel: loads the cubin that the build produced from kernel.cu
+// (nvcc -ptx -> tools/patch_brx.py -> ptxas, see Makefile) and launches its entry points.
+//
+// The cubin is embedded in this library (.incbin below) and loaded once per device through the driver API,
+// whose entry points come from cudaGetDriverEntryPoint, so the library links against the CUDA runtime only
+// and still loads on machines without a driver (program creation / lowering / export work there).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "kernel.cuh"
+
+// the patched, ptxas-compiled kernel image
+asm(".section .rodata\n"
+    ".global saf_kernel_cubin\n"
+    ".global saf_kernel_cubin_end\n"
+    ".balign 16\n"
+    "saf_kernel_cubin:\n"
+    ".incbin \"" SAF_CUBIN_PATH "\"\n"
+    "saf_kernel_cubin_end:\n"
+    ".byte 0\n"
+    ".previous\n");
+extern "C" const unsigned char saf_kernel_cubin[];
+
+namespace saf {
+
+namespace {
+
+struct Driver {
+    CUresult (*module_load_data)(CUmodule *, const void *) = nullptr;
+    CUresult (*module_get_function)(CUfunction *, CUmodule, const char *) = nullptr;
+    CUresult (*func_set_attribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*launch)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                       void **, void **) = nullptr;
+    bool ready = false;
+} g_drv;
+
+struct DeviceModule {
+    CUmodule mod = nullptr;
+    CUfunction interp[6] = {};
+    CUfunction peak = nullptr;
+    bool ready = false;
+};
+DeviceModule g_modules[64];
+std::mutex g_module_mu;
+
+cudaError_t as_cuda(CUresult r) {
+    if (r == CUDA_SUCCESS) return cudaSuccess;
+    if (r == CUDA_ERROR_OUT_OF_MEMORY) return cudaErrorMemoryAllocation;
+    if (r == CUDA_ERROR_INVALID_VALUE) return cudaErrorInvalidValue;
+    if (r == CUDA_ERROR_LAUNCH_OUT_OF_RESOURCES) return cudaErrorLaunchOutOfResources;
+    if (r == CUDA_ERROR_NO_BINARY_FOR_GPU) return cudaErrorNoKernelImageForDevice;
+    if (r == CUDA_ERROR_INVALID_IMAGE) return cudaErrorInvalidKernelImage;
+    return cudaErrorUnknown;
+}
+
+template <typename F>
+cudaError_t entry(const char *name, F *out) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (q != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorSymbolNotFound;
+    *out = reinterpret_cast<F>(fn);
+    return cudaSuccess;
+}
+
+cudaError_t module_for_current_device(DeviceModule **out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(g_module_mu);
+    DeviceModule &m = g_modules[dev];
+    if (!m.ready) {
+        e = cudaFree(nullptr); // make sure the runtime's primary context exists and is current
+        if (e != cudaSuccess) return e;
+        if (!g_drv.ready) {
+            if ((e = entry("cuModuleLoadData", &g_drv.module_load_data)) != cudaSuccess) return e;
+            if ((e = entry("cuModuleGetFunction", &g_drv.module_get_function)) != cudaSuccess) return e;
+            if ((e = entry("cuFuncSetAttribute", &g_drv.func_set_attribute)) != cudaSuccess) return e;
+            if ((e = entry("cuLaunchKernel", &g_drv.launch)) != cudaSuccess) return e;
+            g_drv.ready = true;
+        }
+        CUresult r = g_drv.module_load_data(&m.mod, saf_kernel_cubin);
+        if (r != CUDA_SUCCESS) return as_cuda(r);
+        static const char *names[6] = {"saf_interp_p4_smem", "saf_interp_p4_gmem", "saf_interp_p2_smem",
+                                       "saf_interp_p2_gmem", "saf_interp_p1_smem", "saf_interp_p1_gmem"};
+        int optin = 0;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return e;
+        for (int k = 0; k < 6; ++k) {
+            r = g_drv.module_get_function(&m.interp[k], m.mod, names[k]);
+            if (r != CUDA_SUCCESS) return as_cuda(r);
+            // opt in to the full dynamic shared-memory carve-out
+            r = g_drv.func_set_attribute(m.interp[k], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, optin);
+            if (r != CUDA_SUCCESS) return as_cuda(r);
+        }
+        r = g_drv.module_get_function(&m.peak, m.mod, "saf_fp64_peak_kernel");
+        if (r != CUDA_SUCCESS) return as_cuda(r);
+        m.ready = true;
+    }
+    *out = &m;
+    return cudaSuccess;
+}
+
+} // namespace
+
+
+cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream) {
+    const int li = shape.points_per_thread == 4 ? 0 : shape.points_per_thread == 2 ? 1 : 2;
+    const int k = 2 * li + (shape.image_in_smem ? 0 : 1);
+    DeviceModule *m = nullptr;
+    cudaError_t e = module_for_current_device(&m);
+    if (e != cudaSuccess) return e;
+    void *args[] = {const_cast<LaunchDesc *>(&desc)};
+    return as_cuda(g_drv.launch(m->interp[k], (unsigned)shape.grid, 1, 1, (unsigned)shape.block, 1, 1,
+                                (unsigned)shape.smem_bytes, (CUstream)stream, args, nullptr));
+}
+
+cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream) {
+    DeviceModule *m = nullptr;
+    cudaError_t e = module_for_current_device(&m);
+    if (e != cudaSuccess) return e;
+    double seed = 0.5;
+    void *args[] = {&sink, &iters, &seed};
+    return as_cuda(g_drv.launch(m->peak, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
+}
+
+// register file + block context (+ the image when it is staged in shared memory)
+size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t image_bytes_in_smem) {
+    return (size_t)n_slots * (size_t)BLOCK_THREADS * (size_t)points_per_thread * 8 + sizeof(BlockCtx) +
+           ((image_bytes_in_smem + 15) & ~(size_t)15);
+}
+
+static int resident_blocks_for(int P) { return P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1; }
+
+cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
+                                     int force_points_per_thread, int *points_per_thread) {
+    int sms = 0, smem_optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return e;
+    const size_t smem_sm = (size_t)smem_optin; // per-block opt-in limit ~= per-SM capacity minus 1 KB
+    // More points per thread amortise the dispatch; they need (a) 16-byte aligned columns, (b) enough
+    // points to still give every SM several blocks, (c) a register file that leaves >= 2 blocks per SM.
+    // n_slots + 3: room for the reserved slots the packer adds.
+    auto fits = [&](int p, int min_blocks) {
+        return (interpreter_smem_bytes(n_slots + 3, p, 0) + 1024) * (size_t)min_blocks <= smem_sm + 1024;
+    };
+    auto enough = [&](int p) {
+        return n_points >= (unsigned long long)sms * 3ull * (unsigned long long)BLOCK_THREADS * (unsigned long long)p;
+    };
+    int P = 1;
+    if (aligned16 && enough(4) && fits(4, 2)) P = 4;
+    else if (aligned16 && enough(2) && fits(2, 2)) P = 2;
+    if (force_points_per_thread == 1 || (aligned16 && (force_points_per_thread == 2 || force_points_per_thread == 4)))
+        P = force_points_per_thread;
+    while (P > 1 && !fits(P, 1)) P >>= 1;
+    if (!fits(P, 1)) return cudaErrorInvalidConfiguration;
+    *points_per_thread = P;
+    return cudaSuccess;
+}
+
+cudaError_t choose_shape(int device, uint32_t n_slots, size_t image_bytes, unsigned long long n_points, int P,
+                         LaunchShape *shape) {
+    int sms = 0, smem_optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return e;
+    const size_t rf = interpreter_smem_bytes(n_slots, P, 0);
+    if (rf > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
+    // the image rides in shared memory when it is small next to the register file (it must not cost a
+    // resident block) and always when it is tiny
+    bool in_smem = image_bytes <= IMAGE_SMEM_ALWAYS;
+    if (!in_smem && image_bytes <= IMAGE_SMEM_MAX) {
+        const size_t with = interpreter_smem_bytes(n_slots, P, image_bytes);
+        const size_t blocks_without = ((size_t)smem_optin + 1024) / (rf + 1024);
+        const size_t blocks_with = with <= (size_t)smem_optin ? ((size_t)smem_optin + 1024) / (with + 1024) : 0;
+        const size_t want = (size_t)resident_blocks_for(P);
+        in_smem = blocks_with >= (blocks_without < want ? blocks_without : want);
+    }
+    size_t smem = interpreter_smem_bytes(n_slots, P, in_smem ? image_bytes : 0);
+    if (smem > (size_t)smem_optin) {
+        in_smem = false;
+        smem = rf;
+    }
+    size_t resident = (size_t)resident_blocks_for(P); // __launch_bounds__ register budget
+    const size_t by_smem = ((size_t)smem_optin + 1024) / (smem + 1024);
+    if (by_smem < resident) resident = by_smem;
+    if (resident < 1) resident = 1;
+    const unsigned long long tile = (unsigned long long)BLOCK_THREADS * P;
+    const unsigned long long n_tiles = (n_points + tile - 1) / tile;
+    unsigned long long grid = (unsigned long long)sms * resident;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    shape->points_per_thread = P;
+    shape->block = BLOCK_THREADS;
+    shape->grid = (int)grid;
+    shape->smem_bytes = smem;
+    shape->image_in_smem = in_smem;
+    return cudaSuccess;
+}
+
+} // namespace saf
