@@ -117,12 +117,16 @@ SAF_API int saf_program_export(const saf_program *prog, uint64_t *code, size_t c
 /* Copies out the PACKED micro-instruction image the kernel executes for `points_per_thread` in {1, 2, 4}
  * (layout: symbanafis_b200/csrc/uop.h): constants first, micro-instructions from byte `code_off`.
  * param_off / result_off are byte offsets (-1 = parameter never read), result_is_k[k] = 1 when result k is
- * a constant whose offset points into the image.  For the CPU emulator of the test-suite and for tooling.
+ * a constant whose offset points into the image.  Iterated maps are double buffered when possible
+ * (*double_buffered = 1): the image then holds the program twice, the second copy with parameter and result slots
+ * swapped, each U_END continuing with the other copy, and after an EVEN number of iterations the results sit at
+ * result_off_even.  For the CPU emulator of the test-suite and for tooling.
  * Any pointer may be NULL; n_words always receives the full size. */
 SAF_API int saf_program_export_packed(const saf_program *prog, int points_per_thread,
                               uint64_t *image, size_t cap_words, size_t *n_words,
                               uint32_t *code_off, uint32_t *n_slots, int32_t *x_off /* [3]: x0, x1, acc */,
-                              int32_t *param_off, int32_t *result_off, uint8_t *result_is_k);
+                              int32_t *param_off, int32_t *result_off, uint8_t *result_is_k,
+                              int32_t *result_off_even, int *double_buffered);
 
 /* ---- evaluation --------------------------------------------------------------------------- */
 

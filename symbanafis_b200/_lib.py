@@ -91,7 +91,7 @@ def lib() -> C.CDLL:
     L.saf_program_export.argtypes = [vp, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), vp, vp]
     L.saf_program_export.restype = C.c_int
     L.saf_program_export_packed.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(u32), C.POINTER(u32),
-                                            vp, vp, vp, vp]
+                                            vp, vp, vp, vp, vp, C.POINTER(C.c_int)]
     L.saf_program_export_packed.restype = C.c_int
     L.saf_eval_device.argtypes = [vp, PP, C.POINTER(sz), sz, PP, sz, C.c_uint, vp]
     L.saf_eval_device.restype = C.c_int
@@ -213,22 +213,25 @@ class DeviceProgramHandle:
     def export_packed(self, points_per_thread: int):
         """The packed micro-instruction image for one register-file layout (csrc/uop.h):
         dict(image uint64[], code_off, n_slots, x_off int32[3] = staging x0, x1 and the ACC slot, param_off int32[], result_off int32[],
-        result_is_k uint8[])."""
+        result_is_k uint8[], result_off_even int32[], double_buffered)."""
         nw, co, ns = C.c_size_t(), C.c_uint32(), C.c_uint32()
         check(lib().saf_program_export_packed(self._h, points_per_thread, None, 0, C.byref(nw), C.byref(co),
-                                              C.byref(ns), None, None, None, None))
+                                              C.byref(ns), None, None, None, None, None, None))
         info = self.info()
         image = np.zeros(nw.value, dtype=np.uint64)
         x_off = np.zeros(3, dtype=np.int32)  # x0, x1, acc
         poff = np.zeros(max(1, info.param_count), dtype=np.int32)
         roff = np.zeros(max(1, info.n_results), dtype=np.int32)
         rk = np.zeros(max(1, info.n_results), dtype=np.uint8)
+        roff_even = np.zeros(max(1, info.n_results), dtype=np.int32)
+        dbuf = C.c_int(0)
         check(lib().saf_program_export_packed(self._h, points_per_thread, image.ctypes.data, image.size, C.byref(nw),
                                               C.byref(co), C.byref(ns), x_off.ctypes.data, poff.ctypes.data,
-                                              roff.ctypes.data, rk.ctypes.data))
+                                              roff.ctypes.data, rk.ctypes.data, roff_even.ctypes.data, C.byref(dbuf)))
         return {"image": image, "code_off": co.value, "n_slots": ns.value, "x_off": x_off,
                 "param_off": poff[:info.param_count], "result_off": roff[:info.n_results],
-                "result_is_k": rk[:info.n_results], "points_per_thread": points_per_thread}
+                "result_is_k": rk[:info.n_results], "points_per_thread": points_per_thread,
+                "result_off_even": roff_even[:info.n_results], "double_buffered": bool(dbuf.value)}
 
     # -- evaluation ----------------------------------------------------------------------------
     def eval_host(self, cols: Sequence[np.ndarray], outs: Sequence[np.ndarray], n_points: int,

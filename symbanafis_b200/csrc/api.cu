@@ -242,10 +242,12 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     d.x0_off = pk->x0_off;
     d.x1_off = pk->x1_off;
     for (uint32_t j = 0; j < dp.param_count; ++j) d.param_off[j] = pk->param_off[j];
+    const bool even = pk->double_buffered && (d.iters % 2ull == 0ull);
     for (uint32_t k = 0; k < d.n_results; ++k) {
-        d.result_off[k] = pk->result_off[k];
+        d.result_off[k] = even ? pk->result_off_even[k] : pk->result_off[k];
         if (pk->result_is_k[k]) d.result_k_mask |= 1u << k;
     }
+    d.n_feedback = pk->double_buffered ? 0u : dp.param_count; // parameters hot_run copies back between iterations
     rc = ensure_device_image(const_cast<saf_program *>(prog), device, *pk, &d.image_global);
     if (rc != SAF_OK) return rc;
     d.image_bytes = (uint32_t)(pk->image.size() * 8);
@@ -262,7 +264,8 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
 
 extern "C" int saf_program_export_packed(const saf_program *p, int points_per_thread, uint64_t *image, size_t cap_words,
                                          size_t *n_words, uint32_t *code_off, uint32_t *n_slots, int32_t *x_off,
-                                         int32_t *param_off, int32_t *result_off, uint8_t *result_is_k) {
+                                         int32_t *param_off, int32_t *result_off, uint8_t *result_is_k,
+                                         int32_t *result_off_even, int *double_buffered) {
     if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
     if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4)
         return fail(SAF_ERR_INVALID_ARGUMENT, "points_per_thread must be 1, 2 or 4");
@@ -280,6 +283,8 @@ extern "C" int saf_program_export_packed(const saf_program *p, int points_per_th
     }
     if (param_off) std::copy(pk->param_off.begin(), pk->param_off.end(), param_off);
     if (result_off) std::copy(pk->result_off.begin(), pk->result_off.end(), result_off);
+    if (result_off_even) std::copy(pk->result_off_even.begin(), pk->result_off_even.end(), result_off_even);
+    if (double_buffered) *double_buffered = pk->double_buffered ? 1 : 0;
     if (result_is_k) std::copy(pk->result_is_k.begin(), pk->result_is_k.end(), result_is_k);
     return SAF_OK;
 }

@@ -323,7 +323,7 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img
 
             SAF_DISPATCH(uop)
             switch (uop) {
-            case U_END: SAF_CASE(U_END) goto program_end;
+            case U_END: SAF_CASE(U_END) pc = fa; goto program_end; // a = where the next iteration starts
             case U_LOADK: SAF_CASE(U_LOADK) { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } break;
 
             U1CASE(D_COPY, x)
@@ -390,7 +390,6 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img
                 }
                 RF::store(my, (uint32_t)s, v);
             }
-            pc = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, code_off));
         }
     }
 }
@@ -408,7 +407,7 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     {
         BlockCtx *ctx = reinterpret_cast<BlockCtx *>(saf_smem + ctx_off);
         if (threadIdx.x == 0) {
-            ctx->n_params = d.n_params;
+            ctx->n_params = d.n_feedback;
             ctx->result_k_mask = d.result_k_mask;
             ctx->acc_off = d.acc_off;
             ctx->code_off = d.code_off;

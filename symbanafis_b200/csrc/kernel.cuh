@@ -31,6 +31,7 @@ struct LaunchDesc {
     uint32_t code_off;                   // first micro-instruction in the image
     uint32_t n_slots;                    // register-file slots (incl. staging slots)
     uint32_t n_params;                   // columns the program can read (param_count)
+    uint32_t n_feedback;                 // parameters copied back from results between iterations (0 = double buffered)
     uint32_t n_results;
     uint32_t flags;                      // SAF_EVAL_BROADCAST
     uint32_t result_k_mask;              // bit k: result k is a constant (result_off = image offset)

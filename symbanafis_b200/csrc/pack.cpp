@@ -71,7 +71,13 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
     }
     std::vector<double> K(dp.consts.begin(), dp.consts.end());
     std::map<uint64_t, uint32_t> mul_pair; // bits(k1) -> byte offset of the pair {k1, -0.0}
-    auto soff = [&](uint32_t f) { return field_index(f) * SB; };
+    // slot renaming of the current pass (identity for copy A, parameter <-> result swap for copy B)
+    std::vector<uint32_t> slot_map(dp.n_slots);
+    for (uint32_t i = 0; i < dp.n_slots; ++i) slot_map[i] = i;
+    auto soff = [&](uint32_t f) {
+        const uint32_t i = field_index(f);
+        return (i < slot_map.size() ? slot_map[i] : i) * SB;
+    };
     auto koff = [&](uint32_t f) { return field_index(f) * 8u; };
     auto off_of = [&](uint32_t f) -> uint32_t {
         switch (field_kind(f)) {
@@ -82,11 +88,12 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
     };
     auto dest_of = [&](uint32_t f) -> int32_t { return field_kind(f) == KIND_S ? (int32_t)soff(f) : NO_DEST; };
 
-    std::vector<UI> U;
     auto kinds3 = [](uint32_t fa, uint32_t fb, uint32_t fc) {
         return field_kind(fa) | (field_kind(fb) << 2) | (field_kind(fc) << 4);
     };
 
+    // converts the decoded program under the current slot_map; returns 0 or an error code
+    auto build = [&](std::vector<UI> &U) -> int {
     for (const Dec &d : code) {
         UI u;
         u.d = dest_of(d.fd);
@@ -242,7 +249,44 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
         }
         U.push_back(u);
     }
-    // one padding instruction: the kernel prefetches the instruction after U_END
+    return SAF_OK;
+    }; // build
+
+    std::vector<UI> U;
+    int rc = build(U);
+    if (rc != SAF_OK) return rc;
+
+    // ---- double buffering for iterated maps --------------------------------------------------------------
+    // Between two iterations of saf_iterate_* parameter j must receive result j.  Instead of copying slots,
+    // the image carries a second copy of the program in which parameter slot and result slot of every j have
+    // swapped names: copy A leaves its results where copy B expects its parameters and vice versa, and the
+    // U_END of each copy continues with the other one.  Possible when the pairing is a bijection on slots.
+    const size_t n_res = dp.result_field.size();
+    bool dbuf = n_res == dp.param_count && n_res > 0;
+    if (dbuf) {
+        std::vector<int> seen(dp.n_slots, 0);
+        for (uint32_t j = 0; j < dp.param_count && dbuf; ++j) {
+            const uint32_t f = dp.result_field[j];
+            if (field_kind(f) != KIND_S) dbuf = false;                  // constant result: needs the copy loop
+            else if (dp.param_slot[j] == NO_SLOT) continue;             // nothing to feed back
+            else if (seen[field_index(f)]++ || seen[dp.param_slot[j]]++) dbuf = false;
+        }
+        // a result slot that is fed back must not also be the result of a parameter that is not
+        for (uint32_t j = 0; j < dp.param_count && dbuf; ++j)
+            if (dp.param_slot[j] == NO_SLOT && seen[field_index(dp.result_field[j])]) dbuf = false;
+    }
+    const size_t n_a = U.size(); // micro-instructions of copy A incl. its U_END
+    if (dbuf) {
+        for (uint32_t j = 0; j < dp.param_count; ++j) {
+            if (dp.param_slot[j] == NO_SLOT) continue;
+            const uint32_t r = field_index(dp.result_field[j]), q = dp.param_slot[j];
+            slot_map[q] = r;
+            slot_map[r] = q;
+        }
+        rc = build(U);
+        if (rc != SAF_OK) return rc;
+    }
+    // one padding instruction: the kernel may prefetch the instruction after the last U_END
     U.push_back(UI());
 
     // ---- image: [constants, padded to 32 bytes][micro-instructions] ----
@@ -260,7 +304,22 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
     }
     out.n_instr = (uint32_t)U.size();
     out.code_off = (uint32_t)(k_words * 8);
+    out.double_buffered = dbuf;
+    // U_END.a = where the next iteration starts
+    {
+        const uint32_t start_a = out.code_off, start_b = out.code_off + (uint32_t)(n_a * UINSTR_BYTES);
+        uint64_t *end_a = &out.image[k_words + (n_a - 1) * UINSTR_WORDS];
+        end_a[1] = (uint64_t)(dbuf ? start_b : start_a);
+        if (dbuf) {
+            uint64_t *end_b = &out.image[k_words + (U.size() - 2) * UINSTR_WORDS];
+            end_b[1] = (uint64_t)start_a;
+        }
+    }
 
+    // offsets seen from outside: copy A's names (identity map); after an even number of iterations of a
+    // double-buffered image the results sit under copy B's names
+    std::vector<uint32_t> map_b = slot_map;
+    for (uint32_t i = 0; i < dp.n_slots; ++i) slot_map[i] = i;
     out.param_off.assign(dp.param_count, -1);
     for (uint32_t j = 0; j < dp.param_count; ++j)
         if (dp.param_slot[j] != NO_SLOT) out.param_off[j] = (int32_t)((uint32_t)dp.param_slot[j] * SB);
@@ -268,6 +327,7 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
         const bool is_k = field_kind(f) == KIND_K;
         out.result_is_k.push_back(is_k ? 1 : 0);
         out.result_off.push_back((int32_t)(is_k ? koff(f) : soff(f)));
+        out.result_off_even.push_back((int32_t)(is_k ? koff(f) : (dbuf ? map_b[field_index(f)] : field_index(f)) * SB));
     }
     return SAF_OK;
 }

@@ -22,6 +22,10 @@ struct PackedProgram {
     int32_t x0_off = -1, x1_off = -1;  // staging slots of Builtin3/4 operands (byte offsets), -1 when unused
     std::vector<int32_t> param_off;    // per parameter: register-file byte offset, -1 = never read
     std::vector<int32_t> result_off;   // per result: byte offset (register file or image)
+    // Iterated maps: the image holds the program twice with parameter and result slots swapped in the second
+    // copy (no copies between iterations); after an EVEN number of iterations results sit at result_off_even.
+    bool double_buffered = false;
+    std::vector<int32_t> result_off_even;
     std::vector<uint8_t> result_is_k;  // per result: 1 = constant (offset into the image)
 };
 

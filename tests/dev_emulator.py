@@ -252,19 +252,24 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
     def ref3(name, x, y, z):
         return _leaf((name, 3, 0, 1, 2), 3).eval_batch([x, y, z], n_points)[0]
 
-    def result_value(k: int) -> np.ndarray:
-        off = int(pk["result_off"][k])
+    dbuf = bool(pk.get("double_buffered", False))
+    final_off = pk["result_off_even"] if (dbuf and iters % 2 == 0) else pk["result_off"]
+
+    def result_value(k: int, offs=None) -> np.ndarray:
+        off = int((pk["result_off"] if offs is None else offs)[k])
         return K(off) if pk["result_is_k"][k] else S(off).copy()
 
     i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
+    pc = int(pk["code_off"]) // 8
     for it in range(iters):
-        pc = int(pk["code_off"]) // 8
         while True:
             w0, w1, w2, w3 = (int(x) for x in image[pc:pc + 4])
             pc += 4
             uop, fd = w0 & 0xFFFFFFFF, i32(w0 >> 32)
             fa, fb, fc, imm, kinds = w1 & 0xFFFFFFFF, w1 >> 32, w2 & 0xFFFFFFFF, w2 >> 32, w3 & 0xFFFFFFFF
             if uop == U_END:
+                assert fa % 32 == 0 and fa >= int(pk["code_off"]), "U_END must point at the next iteration's start"
+                pc = fa // 8
                 break
             keep_acc = False
             if uop == U_LOADK:
@@ -334,8 +339,8 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
                 acc = r
             if fd >= 0:
                 store(fd, acc)
-        if it + 1 < iters:
+        if it + 1 < iters and not dbuf:
             for j, off in enumerate(pk["param_off"]):  # sequential, exactly like the kernel's feedback loop
                 if int(off) >= 0:
                     store(int(off), result_value(j))
-    return [result_value(k) for k in range(len(pk["result_off"]))]
+    return [result_value(k, final_off) for k in range(len(pk["result_off"]))]
