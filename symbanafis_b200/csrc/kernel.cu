@@ -153,7 +153,7 @@ __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int
     const uint32_t my = RF::mine(smem_base32());
     const unsigned long long *w = reinterpret_cast<const unsigned long long *>(img + cur);
     const uint2 q0 = split64(w[0]), q1 = split64(w[1]), q2 = split64(w[2]), q3 = split64(w[3]);
-    const uint32_t uop = q0.x, fa = q1.x, fb = q1.y, fc = q2.x, imm = q2.y, kinds = q3.x;
+    const uint32_t uop = q3.y, fa = q1.x, fb = q1.y, fc = q2.x, imm = q2.y, kinds = q3.x; // word 0 holds the NEXT opcode
     const int32_t fd = (int32_t)q0.y;
     auto konst = [&](uint32_t off) -> double { return *reinterpret_cast<const double *>(img + off); };
     auto any = [&](uint32_t kind, uint32_t f, Pt<P> &o) {
@@ -266,14 +266,18 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img
     Pt<P> acc;
     RF::load(my, acc_off, acc);
 
+    // the opcode travels one instruction ahead of its operands (uop.h): read it from the instruction itself
+    // only when the loop is entered
+    uint32_t uop = img32(pc + 28);
     for (;;) {
         for (;;) {
-            const uint4 q = img128(pc);
-            const uint32_t uop = q.x;
+            const uint4 q = img128(pc); // {next uop, d, a, b}
             const int32_t fd = (int32_t)q.y;
             const uint32_t fa = q.z, fb = q.w;
             const uint32_t cur = pc;
             pc += UINSTR_BYTES;
+            const uint32_t uop_now = uop;
+            uop = q.x;
 
             Pt<P> a, b, c;
 
@@ -321,8 +325,8 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img
     case U_T + 10 * (T) + T_KAS: SAF_CASE(U_T + 10 * (T) + T_KAS) { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
     case U_T + 10 * (T) + T_KAK: SAF_CASE(U_T + 10 * (T) + T_KAK) { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break;
 
-            SAF_DISPATCH(uop)
-            switch (uop) {
+            SAF_DISPATCH(uop_now)
+            switch (uop_now) {
             case U_END: SAF_CASE(U_END) pc = fa; goto program_end; // a = where the next iteration starts
             case U_LOADK: SAF_CASE(U_LOADK) { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } break;
 

@@ -294,13 +294,25 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
     const size_t k_words = std::max<size_t>(4, (K.size() + 3) & ~(size_t)3);
     out.image.assign(k_words + U.size() * UINSTR_WORDS, 0);
     for (size_t i = 0; i < K.size(); ++i) std::memcpy(&out.image[i], &K[i], 8);
-    for (size_t i = 0; i < U.size(); ++i) {
+    // word 0 carries the opcode of the NEXT micro-instruction to execute (uop.h): the dispatch of instruction
+    // i + 1 then does not wait for the fetch of instruction i + 1.  After a U_END that is the first opcode of
+    // the copy the next iteration runs.
+    const size_t n_total = U.size();
+    const size_t start_b_index = n_a; // first micro-instruction of copy B (when double buffered)
+    for (size_t i = 0; i < n_total; ++i) {
         const UI &u = U[i];
+        uint32_t next = 0;
+        if (u.uop == U_END && i + 1 < n_total) {
+            if (i == n_a - 1) next = U[dbuf ? start_b_index : 0].uop; // end of copy A
+            else next = U[0].uop;                                    // end of copy B
+        } else if (i + 1 < n_total) {
+            next = U[i + 1].uop;
+        }
         uint64_t *w = &out.image[k_words + i * UINSTR_WORDS];
-        w[0] = (uint64_t)u.uop | ((uint64_t)(uint32_t)u.d << 32);
+        w[0] = (uint64_t)next | ((uint64_t)(uint32_t)u.d << 32);
         w[1] = (uint64_t)u.a | ((uint64_t)u.b << 32);
         w[2] = (uint64_t)u.c | ((uint64_t)u.imm << 32);
-        w[3] = (uint64_t)u.kinds;
+        w[3] = (uint64_t)u.kinds | ((uint64_t)u.uop << 32);
     }
     out.n_instr = (uint32_t)U.size();
     out.code_off = (uint32_t)(k_words * 8);

@@ -8,10 +8,14 @@
 // instructions, and a sign-tested store.  No operand-kind decoding, shifting or masking happens in the
 // hot handlers.
 //
-//   word 0: [31:0] uop            [63:32] d   destination byte offset in the register file, < 0 = ACC only
+//   word 0: [31:0] uop of the NEXT micro-instruction to execute   [63:32] d   destination byte offset in the
+//                  register file, < 0 = ACC only
 //   word 1: [31:0] a              [63:32] b   S operands: byte offset of the slot in the register file
-//   word 2: [31:0] c              [63:32] imm K operands: byte offset of the constant in the blob
-//   word 3: [31:0] kinds (generic ops: kind(a) | kind(b) << 2 | kind(c) << 4)
+//   word 2: [31:0] c              [63:32] imm K operands: byte offset of the constant in the image
+//   word 3: [31:0] kinds (generic ops: kind(a) | kind(b) << 2 | kind(c) << 4)   [63:32] uop of THIS instruction
+// The dispatch loop carries the opcode from one instruction to the next (word 0), so the jump-table lookup of
+// instruction i + 1 starts while the operands of instruction i + 1 are still being fetched; word 3 is read only
+// when the loop is (re-)entered.  U_END: a = byte offset where the next iteration starts.
 //
 // Operand kinds S (register-file slot), K (constant table), A (accumulator = previous result), see
 // saf_isa.h.  Specialised micro-op families (operand kinds fixed by the opcode):

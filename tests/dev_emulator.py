@@ -261,12 +261,16 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
 
     i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
     pc = int(pk["code_off"]) // 8
+    carried = None
     for it in range(iters):
         while True:
             w0, w1, w2, w3 = (int(x) for x in image[pc:pc + 4])
             pc += 4
-            uop, fd = w0 & 0xFFFFFFFF, i32(w0 >> 32)
-            fa, fb, fc, imm, kinds = w1 & 0xFFFFFFFF, w1 >> 32, w2 & 0xFFFFFFFF, w2 >> 32, w3 & 0xFFFFFFFF
+            uop_next, fd = w0 & 0xFFFFFFFF, i32(w0 >> 32)
+            fa, fb, fc, imm, kinds, uop = w1 & 0xFFFFFFFF, w1 >> 32, w2 & 0xFFFFFFFF, w2 >> 32, w3 & 0xFFFFFFFF, w3 >> 32
+            # the kernel dispatches on the opcode carried by the PREVIOUS instruction: both must agree
+            assert carried is None or carried == uop, "word 0 of the previous instruction does not carry this opcode"
+            carried = uop_next
             if uop == U_END:
                 assert fa % 32 == 0 and fa >= int(pk["code_off"]), "U_END must point at the next iteration's start"
                 pc = fa // 8
