@@ -251,6 +251,12 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     fp64_peak = _lib.measure_fp64_peak()  # DFMA lane-instr/s, measured live on this GPU
+    ideal = None
+    if rank == 0 and w.name == "clifford":
+        # the same map hard-coded around the same sin/cos kernels, no interpreter: what interpretation costs
+        t_ideal = _lib.measure_clifford_probe(n, iters)
+        ideal = {"kernel": "saf_clifford_probe_kernel (hard-coded map, state in registers, same launch shape)",
+                 "ms_per_step": 1e3 * t_ideal, "value": n * iters / t_ideal, "unit": UNIT}
 
     for _ in range(max(3, args.warmup)):
         device_step()
@@ -367,6 +373,7 @@ def run_ours(args):
                 "sharding": "one rank per GPU, each rank its own shard, no collective",
             },
             "roofline": roofline,
+            "ideal_kernel": ideal,
             "cpu_baseline": cb,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 8 * n * n_state * world, "d2h_bytes_per_step": 8 * n * n_out * world,

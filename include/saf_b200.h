@@ -169,6 +169,10 @@ SAF_API int saf_device_count(int *count);
  * lane-instructions per second (x2 = FLOP/s).  This is the compute roofline denominator of this path;
  * it is not part of the evaluation path. */
 SAF_API int saf_measure_fp64_peak(double *dfma_lanes_per_second);
+/* Times the Clifford map hard-coded around the same lean sin/cos kernels (no interpreter, state in registers,
+ * same launch shape): the "ideal kernel" reference point bench.py prints next to the interpreter's number.
+ * Not part of the evaluation path. */
+SAF_API int saf_measure_clifford_probe(size_t n_points, int iters, double *seconds);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 SAF_API uint64_t saf_kernel_launch_count(void);
 SAF_API const char *saf_version(void);

@@ -64,6 +64,7 @@ EXPORTED_SYMBOLS = [
     "saf_program_disassemble", "saf_program_export", "saf_program_export_packed", "saf_eval_device", "saf_eval_host",
     "saf_eval_host_multi", "saf_iterate_device", "saf_iterate_host", "saf_last_error",
     "saf_device_count", "saf_kernel_launch_count", "saf_version", "saf_measure_fp64_peak",
+    "saf_measure_clifford_probe",
 ]
 
 
@@ -109,6 +110,8 @@ def lib() -> C.CDLL:
     L.saf_kernel_launch_count.restype = u64
     L.saf_measure_fp64_peak.argtypes = [C.POINTER(C.c_double)]
     L.saf_measure_fp64_peak.restype = C.c_int
+    L.saf_measure_clifford_probe.argtypes = [sz, C.c_int, C.POINTER(C.c_double)]
+    L.saf_measure_clifford_probe.restype = C.c_int
     L.saf_version.restype = C.c_char_p
     _lib = L
     return L
@@ -140,6 +143,13 @@ def measure_fp64_peak() -> float:
     """FP64 pipe peak of the current device in DFMA lane-instructions per second."""
     v = C.c_double(0.0)
     check(lib().saf_measure_fp64_peak(C.byref(v)))
+    return v.value
+
+
+def measure_clifford_probe(n_points: int, iters: int) -> float:
+    """Seconds of the hard-coded Clifford kernel (no interpreter) for n_points x iters: the ideal-kernel reference."""
+    v = C.c_double(0.0)
+    check(lib().saf_measure_clifford_probe(n_points, iters, C.byref(v)))
     return v.value
 
 

@@ -250,9 +250,9 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     d.n_feedback = pk->double_buffered ? 0u : dp.param_count; // parameters hot_run copies back between iterations
     rc = ensure_device_image(const_cast<saf_program *>(prog), device, *pk, &d.image_global);
     if (rc != SAF_OK) return rc;
-    d.image_bytes = (uint32_t)(pk->image.size() * 8);
+    d.code_bytes = pk->code_bytes;
     LaunchShape shape;
-    e = choose_shape(device, pk->n_slots, pk->image.size() * 8, n_points, P, &shape);
+    e = choose_shape(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points, P, &shape);
     if (e == cudaErrorInvalidConfiguration)
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_shape");
@@ -568,6 +568,39 @@ extern "C" int saf_measure_fp64_peak(double *dfma_lanes_per_second) {
     cudaEventDestroy(e1);
     cudaFree(sink);
     *dfma_lanes_per_second = best;
+    return SAF_OK;
+}
+
+extern "C" int saf_measure_clifford_probe(size_t n_points, int iters, double *seconds) {
+    if (!seconds || n_points == 0 || iters <= 0) return fail(SAF_ERR_INVALID_ARGUMENT, "bad argument");
+    int dev = 0, sms = 0;
+    SAF_CUDA(cudaGetDevice(&dev));
+    SAF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *xs = nullptr, *ys = nullptr;
+    SAF_CUDA(cudaMalloc(&xs, n_points * 8));
+    SAF_CUDA(cudaMalloc(&ys, n_points * 8));
+    std::vector<double> h(n_points);
+    for (size_t i = 0; i < n_points; ++i) h[i] = -2.0 + 4.0 * (double)((i * 2654435761ull) % 1000003ull) / 1000003.0;
+    cudaEvent_t e0, e1;
+    SAF_CUDA(cudaEventCreate(&e0));
+    SAF_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        SAF_CUDA(cudaMemcpy(xs, h.data(), n_points * 8, cudaMemcpyHostToDevice));
+        SAF_CUDA(cudaMemcpy(ys, h.data(), n_points * 8, cudaMemcpyHostToDevice));
+        SAF_CUDA(cudaEventRecord(e0, 0));
+        SAF_CUDA(launch_clifford_probe(xs, ys, n_points, iters, sms * SAF_MINB_P4, 0));
+        SAF_CUDA(cudaEventRecord(e1, 0));
+        SAF_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SAF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && (best == 0.0 || ms * 1e-3 < best)) best = ms * 1e-3;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(xs);
+    cudaFree(ys);
+    *seconds = best;
     return SAF_OK;
 }
 

@@ -5,10 +5,12 @@
 // opcode branch are warp-uniform: there is no divergence in the dispatch, only inside the data-dependent
 // slow paths of a few special functions.
 //
-//   program image               : packed micro-instructions + constants (uop.h / pack.cpp), staged once per
-//                                 block into SHARED memory (one 16-byte broadcast load fetches opcode,
-//                                 destination and two operands); programs whose image does not fit beside
-//                                 the register file are read from global memory through the read-only path
+//   program image               : packed micro-instructions + constants (uop.h / pack.cpp).  Constants are
+//                                 staged once per block into SHARED memory; the code runs out of a 16 KB
+//                                 shared-memory WINDOW (one 16-byte broadcast load fetches next opcode,
+//                                 destination and two operands) that is restaged from global memory at
+//                                 U_NEXTWIN micro-ops -- programs of any length, no per-instruction bounds
+//                                 checks, programs under 512 micro-instructions never restage
 //   live values ("registers")   : shared memory laid out [slot][pair][thread] as f64x2 (f64 for P=1):
 //                                 consecutive lanes touch consecutive 16-byte words -> conflict free;
 //                                 operands arrive as byte offsets: one integer add per access
@@ -231,32 +233,46 @@ __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int
 }
 
 // ---- the dispatch loop ------------------------------------------------------------------------------
-// Runs micro-instructions from `pc` -- over as many iterations of the program as remain, feeding results
-// back into the parameters between iterations -- until the program ends for the last time (returns pc = 0)
-// or a cold micro-op is met (returns its pc; ACC has been written to its reserved slot).  The iteration
-// counter travels in the high word.  IMG_SMEM: the image sits in shared memory at byte offset `img_s`,
-// otherwise in global memory at `img_g`.
-template <int P, bool IMG_SMEM>
-__device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img_s, const unsigned char *img_g,
-                                                   uint32_t ctx_off, uint32_t pc, uint32_t it, uint32_t iters) {
+// Runs micro-instructions from code offset `pc` -- over as many iterations of the program as remain -- until the
+// program ends for the last time (returns HOT_DONE) or a cold micro-op is met (returns its code offset in the low
+// word, the iteration counter in the high word; ACC has been written to its reserved slot).  The code is executed
+// out of the shared-memory window at `win_s` (CODE_WINDOW_BYTES, uop.h); the window that contains `pc` must be
+// staged when hot_run is entered.  K_SMEM: the constant table sits in shared memory at `k_s`, otherwise it is
+// read from the image in global memory.  All threads of the block run hot_run together (same program, same
+// iteration count), so the window restaging may use block barriers.
+constexpr unsigned long long HOT_DONE = ~0ull;
+
+__device__ __forceinline__ void stage_window(uint32_t win_sm, const unsigned char *code_g, uint32_t win_g, uint32_t code_bytes) {
+    const uint32_t bytes = min(CODE_WINDOW_BYTES, code_bytes - win_g);
+    const uint4 *src = reinterpret_cast<const uint4 *>(code_g + win_g);
+    __syncthreads(); // everybody is done with the previous window
+    for (uint32_t i = threadIdx.x; i < bytes / 16u; i += BLOCK_THREADS) {
+        const uint4 v = __ldg(src + i);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(win_sm + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    __syncthreads();
+}
+
+template <int P, bool K_SMEM>
+__device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx_off, const unsigned char *img_g,
+                                                   uint32_t pc_code, uint32_t it, uint32_t iters) {
     using RF = Rf<P>;
     const uint32_t my = RF::mine(smem32);
-    const uint32_t ctx = smem32 + ctx_off;   // BlockCtx
-    const uint32_t img_sm = smem32 + img_s;  // image, when staged in shared memory
+    const uint32_t ctx = smem32 + ctx_off;                           // BlockCtx
+    const uint32_t k_sm = ctx + (uint32_t)sizeof(BlockCtx);           // constant table (K_SMEM)
     const uint32_t acc_off = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, acc_off));
+    const uint32_t code_off = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, code_off));
+    const uint32_t code_bytes = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, code_bytes));
+    const uint32_t win_sm = k_sm + (K_SMEM ? code_off : 0u);          // code window
+    const unsigned char *const code_g = img_g + code_off;
+    uint32_t win_g = pc_code & ~(CODE_WINDOW_BYTES - 1u);             // code offset of the staged window
+    uint32_t pc = win_sm + (pc_code & (CODE_WINDOW_BYTES - 1u));      // shared address of the next instruction
 
-    auto img128 = [&](uint32_t off) -> uint4 { // 16 bytes of the image (warp-uniform address)
-        if constexpr (IMG_SMEM) return lds_u128(img_sm + off);
-        else return __ldg(reinterpret_cast<const uint4 *>(img_g + off));
-    };
-    auto img32 = [&](uint32_t off) -> uint32_t {
-        if constexpr (IMG_SMEM) return lds_u32(img_sm + off);
-        else return __ldg(reinterpret_cast<const uint32_t *>(img_g + off));
-    };
+    auto img32 = [&](uint32_t addr) -> uint32_t { return lds_u32(addr); }; // word of the current instruction
     auto konst = [&](uint32_t off) -> double {
-        if constexpr (IMG_SMEM) {
+        if constexpr (K_SMEM) {
             double k;
-            lds64(img_sm + off, k);
+            lds64(k_sm + off, k);
             return k;
         } else {
             return __ldg(reinterpret_cast<const double *>(img_g + off));
@@ -268,10 +284,10 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img
 
     // the opcode travels one instruction ahead of its operands (uop.h): read it from the instruction itself
     // only when the loop is entered
-    uint32_t uop = img32(pc + 28);
+    uint32_t uop = lds_u32(pc + 28);
     for (;;) {
         for (;;) {
-            const uint4 q = img128(pc); // {next uop, d, a, b}
+            const uint4 q = lds_u128(pc); // {next uop, d, a, b}
             const int32_t fd = (int32_t)q.y;
             const uint32_t fa = q.z, fb = q.w;
             const uint32_t cur = pc;
@@ -327,7 +343,21 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img
 
             SAF_DISPATCH(uop_now)
             switch (uop_now) {
-            case U_END: SAF_CASE(U_END) pc = fa; goto program_end; // a = where the next iteration starts
+            case U_END: SAF_CASE(U_END) { // a = code offset where the next iteration starts
+                if (++it >= iters) return HOT_DONE;
+                const uint32_t w = fa & ~(CODE_WINDOW_BYTES - 1u);
+                if (w != win_g) {
+                    win_g = w;
+                    stage_window(win_sm, code_g, win_g, code_bytes);
+                }
+                pc = win_sm + (fa & (CODE_WINDOW_BYTES - 1u));
+                goto program_end;
+            }
+            case U_NEXTWIN: SAF_CASE(U_NEXTWIN) // end of the staged window: stage the next one, continue at its start
+                win_g += CODE_WINDOW_BYTES;
+                stage_window(win_sm, code_g, win_g, code_bytes);
+                pc = win_sm;
+                continue;
             case U_LOADK: SAF_CASE(U_LOADK) { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } break;
 
             U1CASE(D_COPY, x)
@@ -370,12 +400,11 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img
             // cold micro-ops leave the loop: ACC goes to its slot, the caller runs cold_op and re-enters
             default: SAF_CASE_DEFAULT
                 RF::store(my, acc_off, acc);
-                return ((unsigned long long)it << 32) | cur;
+                return ((unsigned long long)it << 32) | (win_g + (cur - win_sm));
             }
             if (fd >= 0) RF::store(my, (uint32_t)fd, acc);
         }
     program_end:
-        if (++it >= iters) return 0ull;
         // ---- in-kernel feedback: parameter j <- result j (result slots never alias parameter slots,
         // lower.cpp); the state stays on chip between iterations ----
         {
@@ -399,15 +428,16 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t img
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------
-template <int P, bool IMG_SMEM>
+template <int P, bool K_SMEM>
 __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     using RF = Rf<P>;
     const uint32_t smem32 = smem_base32();
     const uint32_t my = RF::mine(smem32);
 
-    // ---- stage the block context (and the image) behind the register file ----
+    // ---- behind the register file: block context, constant table (K_SMEM), code window ----
     const uint32_t ctx_off = d.n_slots * (uint32_t)(BLOCK_THREADS * P * 8);
-    const uint32_t img_s = ctx_off + (uint32_t)sizeof(BlockCtx);
+    const uint32_t k_s = ctx_off + (uint32_t)sizeof(BlockCtx);
+    const uint32_t win_s = k_s + (K_SMEM ? d.code_off : 0u);
     {
         BlockCtx *ctx = reinterpret_cast<BlockCtx *>(saf_smem + ctx_off);
         if (threadIdx.x == 0) {
@@ -415,17 +445,18 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
             ctx->result_k_mask = d.result_k_mask;
             ctx->acc_off = d.acc_off;
             ctx->code_off = d.code_off;
+            ctx->code_bytes = d.code_bytes;
         }
         if (threadIdx.x < MAX_COLS) ctx->param_off[threadIdx.x] = d.param_off[threadIdx.x];
         if (threadIdx.x < MAX_OUTS) ctx->result_off[threadIdx.x] = d.result_off[threadIdx.x];
-        if constexpr (IMG_SMEM) {
+        if constexpr (K_SMEM) {
             const uint4 *src = reinterpret_cast<const uint4 *>(d.image_global);
-            uint4 *dst = reinterpret_cast<uint4 *>(saf_smem + img_s);
-            for (uint32_t i = threadIdx.x; i < d.image_bytes / 16u; i += BLOCK_THREADS) dst[i] = __ldg(src + i);
+            uint4 *dst = reinterpret_cast<uint4 *>(saf_smem + k_s);
+            for (uint32_t i = threadIdx.x; i < d.code_off / 16u; i += BLOCK_THREADS) dst[i] = __ldg(src + i);
         }
-        __syncthreads();
+        stage_window(smem32 + win_s, d.image_global + d.code_off, 0u, d.code_bytes); // barriers inside
     }
-    const unsigned char *const img_generic = IMG_SMEM ? (saf_smem + img_s) : d.image_global;
+    const bool multi_window = d.code_bytes > CODE_WINDOW_BYTES;
     const uint32_t iters = (uint32_t)d.iters;
 
     constexpr unsigned long long TILE = (unsigned long long)BLOCK_THREADS * P;
@@ -464,13 +495,15 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
 
         // ---- the program: hot_run until it ends, cold micro-ops in between ----
         {
-            uint32_t pc = d.code_off, it = 0;
+            if (multi_window && tile != blockIdx.x) // the previous tile left the last window staged
+                stage_window(smem32 + win_s, d.image_global + d.code_off, 0u, d.code_bytes);
+            uint32_t pc = 0, it = 0;
             for (;;) {
-                const unsigned long long st = hot_run<P, IMG_SMEM>(smem32, img_s, d.image_global, ctx_off, pc, it, iters);
+                const unsigned long long st = hot_run<P, K_SMEM>(smem32, ctx_off, d.image_global, pc, it, iters);
+                if (st == HOT_DONE) break;
                 pc = (uint32_t)st;
-                if (pc == 0u) break;
                 it = (uint32_t)(st >> 32);
-                cold_op<P>(img_generic, pc, d.acc_off, d.x0_off, d.x1_off);
+                cold_op<P>(d.image_global, d.code_off + pc, d.acc_off, d.x0_off, d.x1_off);
                 pc += UINSTR_BYTES;
             }
         }
@@ -479,7 +512,7 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
         for (uint32_t k = 0; k < d.n_results; ++k) {
             Pt<P> v;
             if ((d.result_k_mask >> k) & 1u) {
-                const double kv = *reinterpret_cast<const double *>(img_generic + (uint32_t)d.result_off[k]);
+                const double kv = __ldg(reinterpret_cast<const double *>(d.image_global + (uint32_t)d.result_off[k]));
                 SAF_FOR_P v.v[p] = kv;
             } else {
                 RF::load(my, (uint32_t)d.result_off[k], v);
@@ -508,13 +541,14 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     extern "C" __global__ void __launch_bounds__(BLOCK_THREADS, MINB) NAME(const __grid_constant__ LaunchDesc d) { \
         interp_body<P, SM>(d);                                                                             \
     }
-SAF_ENTRY(saf_interp_p4_smem, 4, true, SAF_MINB_P4)
+// *_ksm: constant table staged in shared memory; *_kgm: read from global memory (very large tables)
+SAF_ENTRY(saf_interp_p4_ksm, 4, true, SAF_MINB_P4)
 #ifndef SAF_FAST_BUILD
-SAF_ENTRY(saf_interp_p4_gmem, 4, false, SAF_MINB_P4)
-SAF_ENTRY(saf_interp_p2_smem, 2, true, SAF_MINB_P2)
-SAF_ENTRY(saf_interp_p2_gmem, 2, false, SAF_MINB_P2)
-SAF_ENTRY(saf_interp_p1_smem, 1, true, SAF_MINB_P1)
-SAF_ENTRY(saf_interp_p1_gmem, 1, false, SAF_MINB_P1)
+SAF_ENTRY(saf_interp_p4_kgm, 4, false, SAF_MINB_P4)
+SAF_ENTRY(saf_interp_p2_ksm, 2, true, SAF_MINB_P2)
+SAF_ENTRY(saf_interp_p2_kgm, 2, false, SAF_MINB_P2)
+SAF_ENTRY(saf_interp_p1_ksm, 1, true, SAF_MINB_P1)
+SAF_ENTRY(saf_interp_p1_kgm, 1, false, SAF_MINB_P1)
 #endif
 
 // ---- FP64 pipe peak probe ---------------------------------------------------------------------------
@@ -535,6 +569,55 @@ extern "C" __global__ void __launch_bounds__(256) saf_fp64_peak_kernel(double *s
     }
     double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (s == 123.456) sink[0] = s; // never true: keeps the chains alive
+}
+
+
+// ---- "ideal kernel" probe ---------------------------------------------------------------------------------
+// What the lean sin/cos kernels reach WITHOUT an interpreter around them: the Clifford map hard-coded, 4 points
+// per thread, state in registers, same launch shape as the interpreter.  bench.py reports it next to the
+// interpreter's number: the gap between the two is what interpretation costs, the gap between this and the
+// DFMA-chain peak is what the FP64 pipe loses on a realistic instruction mix.
+extern "C" __global__ void __launch_bounds__(BLOCK_THREADS, SAF_MINB_P4)
+saf_clifford_probe_kernel(double *xs, double *ys, unsigned long long n, int iters, double a, double b, double c, double d) {
+    const unsigned long long tile = (unsigned long long)BLOCK_THREADS * 4;
+    for (unsigned long long base = (unsigned long long)blockIdx.x * tile; base < n; base += (unsigned long long)gridDim.x * tile) {
+        double x[4], y[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const unsigned long long i = base + (unsigned long long)p * BLOCK_THREADS + threadIdx.x;
+            x[p] = i < n ? xs[i] : 0.0;
+            y[p] = i < n ? ys[i] : 0.0;
+        }
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+            double t[4], s1[4], c1[4], s2[4], c2[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) t[p] = __dmul_rn(y[p], a);
+            lm::sin_n<4>(t, s1);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) t[p] = __dmul_rn(x[p], a);
+            lm::cos_n<4>(t, c1);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) t[p] = __dmul_rn(x[p], b);
+            lm::sin_n<4>(t, s2);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) t[p] = __dmul_rn(y[p], b);
+            lm::cos_n<4>(t, c2);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                x[p] = __fma_rn(c, c1[p], s1[p]);
+                y[p] = __fma_rn(d, c2[p], s2[p]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const unsigned long long i = base + (unsigned long long)p * BLOCK_THREADS + threadIdx.x;
+            if (i < n) {
+                xs[i] = x[p];
+                ys[i] = y[p];
+            }
+        }
+    }
 }
 
 } // namespace saf

@@ -27,8 +27,8 @@ struct LaunchDesc {
     unsigned long long n_points;
     unsigned long long iters;            // >= 1; > 1 only for saf_iterate_*
     const unsigned char *image_global;   // packed image (pack.h) in global memory
-    uint32_t image_bytes;                // multiple of 16
-    uint32_t code_off;                   // first micro-instruction in the image
+    uint32_t code_off;                   // byte offset of the code in the image = size of the constant table
+    uint32_t code_bytes;
     uint32_t n_slots;                    // register-file slots (incl. staging slots)
     uint32_t n_params;                   // columns the program can read (param_count)
     uint32_t n_feedback;                 // parameters copied back from results between iterations (0 = double buffered)
@@ -44,16 +44,15 @@ struct LaunchDesc {
     int32_t result_off[MAX_OUTS];
 };
 
-// The image is staged in shared memory when it fits there without costing a resident block.
-constexpr size_t IMAGE_SMEM_ALWAYS = 4096;   // always staged up to this size
-constexpr size_t IMAGE_SMEM_MAX = 48 * 1024; // never staged above this size
+// Constant tables up to this size are staged in shared memory (larger ones are read from global memory).
+constexpr size_t K_SMEM_MAX = 24 * 1024;
 
 struct LaunchShape {
     int points_per_thread; // 1, 2 or 4
     int block;             // threads per block (always BLOCK_THREADS)
     int grid;
     size_t smem_bytes;
-    bool image_in_smem;    // the kernel copies the image into shared memory (else reads it from global memory)
+    bool k_in_smem;        // the constant table is staged in shared memory (else read from global memory)
 };
 
 // Launches the interpreter; desc.image_global must point at a device copy of the packed image.
@@ -63,22 +62,30 @@ cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape,
 // force_points_per_thread: 0 = automatic, 1 / 2 / 4 = tuning override (SAF_POINTS_PER_THREAD).
 cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
                                      int force_points_per_thread, int *points_per_thread);
-// Grid / shared memory / image placement for the packed program.
-cudaError_t choose_shape(int device, uint32_t n_slots, size_t image_bytes, unsigned long long n_points,
+// Grid / shared memory / constant-table placement for the packed program.
+cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
                          int points_per_thread, LaunchShape *shape);
-size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t image_bytes_in_smem);
+// register file + block context + constant table (when staged) + code window
+size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes);
 
 // Per-block context behind the register file in shared memory: what hot_run needs besides the image.
-struct BlockCtx {
+struct alignas(16) BlockCtx { // a multiple of 16 bytes: the constant table and the code window follow it
     uint32_t n_params;
     uint32_t result_k_mask;
     int32_t acc_off;
     uint32_t code_off;
+    uint32_t code_bytes;
+    uint32_t pad_;
     int32_t param_off[MAX_COLS];
     int32_t result_off[MAX_OUTS];
 };
 
+static_assert(sizeof(BlockCtx) % 16 == 0, "the code window behind BlockCtx is fetched with 16-byte loads");
+
 // FP64-pipe peak probe: blocks x 256 threads, each `iters` x 64 dependent-chain DFMAs.
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);
+// Hard-coded Clifford map with the same lean sin/cos kernels (no interpreter): the "ideal kernel" reference point.
+cudaError_t launch_clifford_probe(double *xs, double *ys, unsigned long long n, int iters, int blocks,
+                                  cudaStream_t stream);
 
 } // namespace saf

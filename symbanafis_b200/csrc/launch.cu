@@ -42,6 +42,7 @@ struct DeviceModule {
     CUmodule mod = nullptr;
     CUfunction interp[6] = {};
     CUfunction peak = nullptr;
+    CUfunction clifford_probe = nullptr;
     bool ready = false;
 };
 DeviceModule g_modules[64];
@@ -87,8 +88,8 @@ cudaError_t module_for_current_device(DeviceModule **out) {
         }
         CUresult r = g_drv.module_load_data(&m.mod, saf_kernel_cubin);
         if (r != CUDA_SUCCESS) return as_cuda(r);
-        static const char *names[6] = {"saf_interp_p4_smem", "saf_interp_p4_gmem", "saf_interp_p2_smem",
-                                       "saf_interp_p2_gmem", "saf_interp_p1_smem", "saf_interp_p1_gmem"};
+        static const char *names[6] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm",
+                                       "saf_interp_p2_kgm", "saf_interp_p1_ksm", "saf_interp_p1_kgm"};
         int optin = 0;
         e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e != cudaSuccess) return e;
@@ -101,6 +102,8 @@ cudaError_t module_for_current_device(DeviceModule **out) {
         }
         r = g_drv.module_get_function(&m.peak, m.mod, "saf_fp64_peak_kernel");
         if (r != CUDA_SUCCESS) return as_cuda(r);
+        r = g_drv.module_get_function(&m.clifford_probe, m.mod, "saf_clifford_probe_kernel");
+        if (r != CUDA_SUCCESS) return as_cuda(r);
         m.ready = true;
     }
     *out = &m;
@@ -112,7 +115,7 @@ cudaError_t module_for_current_device(DeviceModule **out) {
 
 cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream) {
     const int li = shape.points_per_thread == 4 ? 0 : shape.points_per_thread == 2 ? 1 : 2;
-    const int k = 2 * li + (shape.image_in_smem ? 0 : 1);
+    const int k = 2 * li + (shape.k_in_smem ? 0 : 1);
     DeviceModule *m = nullptr;
     cudaError_t e = module_for_current_device(&m);
     if (e != cudaSuccess) return e;
@@ -130,10 +133,22 @@ cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t s
     return as_cuda(g_drv.launch(m->peak, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr));
 }
 
-// register file + block context (+ the image when it is staged in shared memory)
-size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t image_bytes_in_smem) {
+cudaError_t launch_clifford_probe(double *xs, double *ys, unsigned long long n, int iters, int blocks,
+                                  cudaStream_t stream) {
+    DeviceModule *m = nullptr;
+    cudaError_t e = module_for_current_device(&m);
+    if (e != cudaSuccess) return e;
+    double a = -1.4, b = 1.6, c = 1.0, d = 0.7;
+    void *args[] = {&xs, &ys, &n, &iters, &a, &b, &c, &d};
+    return as_cuda(g_drv.launch(m->clifford_probe, (unsigned)blocks, 1, 1, BLOCK_THREADS, 1, 1, 0, (CUstream)stream, args,
+                                nullptr));
+}
+
+// register file + block context + constant table (when staged) + code window
+size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes) {
+    const size_t window = code_bytes < CODE_WINDOW_BYTES ? code_bytes : CODE_WINDOW_BYTES;
     return (size_t)n_slots * (size_t)BLOCK_THREADS * (size_t)points_per_thread * 8 + sizeof(BlockCtx) +
-           ((image_bytes_in_smem + 15) & ~(size_t)15);
+           ((k_bytes_in_smem + 15) & ~(size_t)15) + ((window + 15) & ~(size_t)15);
 }
 
 static int resident_blocks_for(int P) { return P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1; }
@@ -150,7 +165,7 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
     // points to still give every SM several blocks, (c) a register file that leaves >= 2 blocks per SM.
     // n_slots + 3: room for the reserved slots the packer adds.
     auto fits = [&](int p, int min_blocks) {
-        return (interpreter_smem_bytes(n_slots + 3, p, 0) + 1024) * (size_t)min_blocks <= smem_sm + 1024;
+        return (interpreter_smem_bytes(n_slots + 3, p, 0, CODE_WINDOW_BYTES) + 1024) * (size_t)min_blocks <= smem_sm + 1024;
     };
     auto enough = [&](int p) {
         return n_points >= (unsigned long long)sms * 3ull * (unsigned long long)BLOCK_THREADS * (unsigned long long)p;
@@ -166,30 +181,20 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
     return cudaSuccess;
 }
 
-cudaError_t choose_shape(int device, uint32_t n_slots, size_t image_bytes, unsigned long long n_points, int P,
-                         LaunchShape *shape) {
+cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
+                         int P, LaunchShape *shape) {
     int sms = 0, smem_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
-    const size_t rf = interpreter_smem_bytes(n_slots, P, 0);
-    if (rf > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
-    // the image rides in shared memory when it is small next to the register file (it must not cost a
-    // resident block) and always when it is tiny
-    bool in_smem = image_bytes <= IMAGE_SMEM_ALWAYS;
-    if (!in_smem && image_bytes <= IMAGE_SMEM_MAX) {
-        const size_t with = interpreter_smem_bytes(n_slots, P, image_bytes);
-        const size_t blocks_without = ((size_t)smem_optin + 1024) / (rf + 1024);
-        const size_t blocks_with = with <= (size_t)smem_optin ? ((size_t)smem_optin + 1024) / (with + 1024) : 0;
-        const size_t want = (size_t)resident_blocks_for(P);
-        in_smem = blocks_with >= (blocks_without < want ? blocks_without : want);
+    bool k_in_smem = k_bytes <= K_SMEM_MAX;
+    size_t smem = interpreter_smem_bytes(n_slots, P, k_in_smem ? k_bytes : 0, code_bytes);
+    if (smem > (size_t)smem_optin && k_in_smem) {
+        k_in_smem = false;
+        smem = interpreter_smem_bytes(n_slots, P, 0, code_bytes);
     }
-    size_t smem = interpreter_smem_bytes(n_slots, P, in_smem ? image_bytes : 0);
-    if (smem > (size_t)smem_optin) {
-        in_smem = false;
-        smem = rf;
-    }
+    if (smem > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
     size_t resident = (size_t)resident_blocks_for(P); // __launch_bounds__ register budget
     const size_t by_smem = ((size_t)smem_optin + 1024) / (smem + 1024);
     if (by_smem < resident) resident = by_smem;
@@ -203,7 +208,7 @@ cudaError_t choose_shape(int device, uint32_t n_slots, size_t image_bytes, unsig
     shape->block = BLOCK_THREADS;
     shape->grid = (int)grid;
     shape->smem_bytes = smem;
-    shape->image_in_smem = in_smem;
+    shape->k_in_smem = k_in_smem;
     return cudaSuccess;
 }
 

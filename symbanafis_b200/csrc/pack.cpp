@@ -286,47 +286,48 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
         rc = build(U);
         if (rc != SAF_OK) return rc;
     }
-    // one padding instruction: the kernel may prefetch the instruction after the last U_END
-    U.push_back(UI());
 
-    // ---- image: [constants, padded to 32 bytes][micro-instructions] ----
-    // never empty: byte offset 0 is not a valid program counter (hot_run returns pc = 0 for "program finished")
-    const size_t k_words = std::max<size_t>(4, (K.size() + 3) & ~(size_t)3);
-    out.image.assign(k_words + U.size() * UINSTR_WORDS, 0);
+    // ---- windows: the last slot of every code window is U_NEXTWIN (uop.h) ----
+    // index_of[i] = slot of logical instruction i in the windowed stream
+    std::vector<UI> Wd;
+    std::vector<size_t> index_of(U.size());
+    for (size_t i = 0; i < U.size(); ++i) {
+        if (Wd.size() % CODE_WINDOW_INSTR == CODE_WINDOW_INSTR - 1) {
+            UI nw;
+            nw.uop = U_NEXTWIN;
+            Wd.push_back(nw);
+        }
+        index_of[i] = Wd.size();
+        Wd.push_back(U[i]);
+    }
+    const size_t start_a = index_of[0], start_b = dbuf ? index_of[n_a] : index_of[0];
+    const size_t end_a = index_of[n_a - 1], end_b = index_of[U.size() - 1];
+    // U_END.a = code offset where the next iteration starts
+    Wd[end_a].a = (uint32_t)(start_b * UINSTR_BYTES);
+    if (dbuf) Wd[end_b].a = (uint32_t)(start_a * UINSTR_BYTES);
+
+    // ---- image: [constants, padded to 32 bytes][code] ----
+    const size_t k_words = (K.size() + 3) & ~(size_t)3;
+    out.image.assign(k_words + Wd.size() * UINSTR_WORDS, 0);
     for (size_t i = 0; i < K.size(); ++i) std::memcpy(&out.image[i], &K[i], 8);
     // word 0 carries the opcode of the NEXT micro-instruction to execute (uop.h): the dispatch of instruction
     // i + 1 then does not wait for the fetch of instruction i + 1.  After a U_END that is the first opcode of
     // the copy the next iteration runs.
-    const size_t n_total = U.size();
-    const size_t start_b_index = n_a; // first micro-instruction of copy B (when double buffered)
-    for (size_t i = 0; i < n_total; ++i) {
-        const UI &u = U[i];
+    for (size_t i = 0; i < Wd.size(); ++i) {
+        const UI &u = Wd[i];
         uint32_t next = 0;
-        if (u.uop == U_END && i + 1 < n_total) {
-            if (i == n_a - 1) next = U[dbuf ? start_b_index : 0].uop; // end of copy A
-            else next = U[0].uop;                                    // end of copy B
-        } else if (i + 1 < n_total) {
-            next = U[i + 1].uop;
-        }
+        if (u.uop == U_END) next = Wd[u.a / UINSTR_BYTES].uop;
+        else if (i + 1 < Wd.size()) next = Wd[i + 1].uop;
         uint64_t *w = &out.image[k_words + i * UINSTR_WORDS];
         w[0] = (uint64_t)next | ((uint64_t)(uint32_t)u.d << 32);
         w[1] = (uint64_t)u.a | ((uint64_t)u.b << 32);
         w[2] = (uint64_t)u.c | ((uint64_t)u.imm << 32);
         w[3] = (uint64_t)u.kinds | ((uint64_t)u.uop << 32);
     }
-    out.n_instr = (uint32_t)U.size();
+    out.n_instr = (uint32_t)Wd.size();
     out.code_off = (uint32_t)(k_words * 8);
+    out.code_bytes = (uint32_t)(Wd.size() * UINSTR_BYTES);
     out.double_buffered = dbuf;
-    // U_END.a = where the next iteration starts
-    {
-        const uint32_t start_a = out.code_off, start_b = out.code_off + (uint32_t)(n_a * UINSTR_BYTES);
-        uint64_t *end_a = &out.image[k_words + (n_a - 1) * UINSTR_WORDS];
-        end_a[1] = (uint64_t)(dbuf ? start_b : start_a);
-        if (dbuf) {
-            uint64_t *end_b = &out.image[k_words + (U.size() - 2) * UINSTR_WORDS];
-            end_b[1] = (uint64_t)start_a;
-        }
-    }
 
     // offsets seen from outside: copy A's names (identity map); after an even number of iterations of a
     // double-buffered image the results sit under copy B's names

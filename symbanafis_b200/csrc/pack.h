@@ -12,10 +12,12 @@ namespace saf {
 
 struct PackedProgram {
     int points_per_thread = 0;
-    // image = constant table (padded to 32 bytes), then n_instr micro-instructions (incl. U_END and one
-    // padding instruction for the prefetch); every K operand is a byte offset into this image
+    // image = constant table (padded to 32 bytes), then the code: n_instr micro-instruction slots cut into
+    // windows of CODE_WINDOW_BYTES (uop.h).  K operands are byte offsets into the image, program counters are
+    // byte offsets into the code.
     std::vector<uint64_t> image;
-    uint32_t code_off = 0;             // byte offset of the first micro-instruction in the image
+    uint32_t code_off = 0;             // byte offset of the code in the image = size of the constant table
+    uint32_t code_bytes = 0;
     uint32_t n_instr = 0;
     uint32_t n_slots = 0;              // register-file slots incl. the reserved ones below
     int32_t acc_off = 0;               // reserved slot through which ACC is handed to cold micro-ops / heavy ops

@@ -17,6 +17,11 @@
 // instruction i + 1 starts while the operands of instruction i + 1 are still being fetched; word 3 is read only
 // when the loop is (re-)entered.  U_END: a = byte offset where the next iteration starts.
 //
+// Program counters are byte offsets into the CODE part of the image.  The kernel executes the code out of a
+// shared-memory window of CODE_WINDOW_BYTES: the code is cut into windows of that size whose last slot holds
+// U_NEXTWIN ("stage the next window, continue at its start"), so programs of any length run with on-chip
+// instruction fetch and no per-instruction bounds check; programs that fit one window never restage.
+//
 // Operand kinds S (register-file slot), K (constant table), A (accumulator = previous result), see
 // saf_isa.h.  Specialised micro-op families (operand kinds fixed by the opcode):
 //   U1   light unary        x {S, A}
@@ -40,9 +45,11 @@ namespace saf {
 
 constexpr int UINSTR_BYTES = 32;
 constexpr int UINSTR_WORDS = 4; // 64-bit words
+constexpr uint32_t CODE_WINDOW_BYTES = 16 * 1024; // 512 micro-instructions, power of two
+constexpr uint32_t CODE_WINDOW_INSTR = CODE_WINDOW_BYTES / UINSTR_BYTES;
 
-constexpr uint32_t U_END = 0, U_LOADK = 1;
-constexpr uint32_t U_U1 = 2;                                  // + 2 * u + (a is A)
+constexpr uint32_t U_END = 0, U_LOADK = 1, U_NEXTWIN = 2;
+constexpr uint32_t U_U1 = 3;                                  // + 2 * u + (a is A)
 constexpr uint32_t U_H1 = U_U1 + 2 * D_N_LIGHT_UNARY;         // + 2 * h + prefixed
 constexpr uint32_t H1_SIN = 0, H1_COS = 1, H1_EXP = 2, H1_LN = 3, H1_EXPSQR = 4, H1_EXPSQRNEG = 5, H1_EXPNEG = 6,
                    H1_SINCOS = 7, H1_COUNT = 8;

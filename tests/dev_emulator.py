@@ -185,7 +185,8 @@ def run_device_program(code: Sequence[int], consts: np.ndarray, param_slot: Sequ
 
 # ---- packed micro-instruction image (symbanafis_b200/csrc/uop.h, produced by pack.cpp) -------------------
 N_H1 = 8
-U_END, U_LOADK, U_U1 = 0, 1, 2
+U_END, U_LOADK, U_NEXTWIN, U_U1 = 0, 1, 2, 3
+CODE_WINDOW_BYTES = 16 * 1024
 U_H1 = U_U1 + 2 * N_LIGHT_UNARY
 U_BC = U_H1 + 2 * N_H1
 U_BN = U_BC + 5 * 3
@@ -207,7 +208,6 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
     """Executes the packed image exactly as kernel.cu does (register file addressed by byte offset, constants
     read from the image, accumulator, sign-tested destination store), leaf math delegated to the oracle."""
     image = np.asarray(pk["image"], dtype=np.uint64)
-    assert int(pk["code_off"]) >= 32, "byte offset 0 must not be a program counter (hot_run returns 0 for finished)"
     kview = image.view(np.float64)
     P = int(pk["points_per_thread"])
     slot_bytes = 128 * 8 * P
@@ -260,11 +260,12 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
         return K(off) if pk["result_is_k"][k] else S(off).copy()
 
     i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
-    pc = int(pk["code_off"]) // 8
+    code0 = int(pk["code_off"]) // 8  # program counters are byte offsets into the code part of the image
+    pc = 0
     carried = None
     for it in range(iters):
         while True:
-            w0, w1, w2, w3 = (int(x) for x in image[pc:pc + 4])
+            w0, w1, w2, w3 = (int(x) for x in image[code0 + pc:code0 + pc + 4])
             pc += 4
             uop_next, fd = w0 & 0xFFFFFFFF, i32(w0 >> 32)
             fa, fb, fc, imm, kinds, uop = w1 & 0xFFFFFFFF, w1 >> 32, w2 & 0xFFFFFFFF, w2 >> 32, w3 & 0xFFFFFFFF, w3 >> 32
@@ -272,9 +273,13 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
             assert carried is None or carried == uop, "word 0 of the previous instruction does not carry this opcode"
             carried = uop_next
             if uop == U_END:
-                assert fa % 32 == 0 and fa >= int(pk["code_off"]), "U_END must point at the next iteration's start"
+                assert fa % 32 == 0 and code0 + fa // 8 < len(image), "U_END must point at the next iteration's start"
                 pc = fa // 8
                 break
+            if uop == U_NEXTWIN:  # last slot of a code window: execution continues in the next window
+                assert (pc * 8) % CODE_WINDOW_BYTES == 0, "U_NEXTWIN must be the last slot of its window"
+                continue
+            assert ((pc - 4) * 8) % CODE_WINDOW_BYTES != CODE_WINDOW_BYTES - 32, "window's last slot must be U_NEXTWIN"
             keep_acc = False
             if uop == U_LOADK:
                 r = K(fa)
