@@ -388,11 +388,74 @@ def test_device_resident_columns_and_streams():
         assert_close(t[1:].cpu().numpy(), r, RTOL, ATOL, what="unaligned device outputs")
 
 
-def test_large_program_takes_the_global_memory_path():
-    w = workloads.terrain_gradient(n_terms=160)  # code + constants exceed the constant-bank blob
+def test_large_program_runs_through_several_code_windows():
+    w = workloads.terrain_gradient(n_terms=160)  # > 512 micro-instructions: several 16 KB code windows
     n = 2000
     cols = w.make_inputs(n, 2)
     ref = OracleProgram.from_program(w.program).run_chunked(cols, n)
     got = gpu_eval(w.program, cols, n)
     for g, r in zip(got, ref):
         assert_close(g, r, RTOL, ATOL, what="large program")
+
+
+def test_large_program_several_tiles_per_block_and_points_per_thread(monkeypatch):
+    # many tiles per block: every tile restarts in window 0, so the first window must be restaged
+    w = workloads.terrain_gradient(n_terms=60)
+    info = _handle(w.program).info()
+    assert info.n_dev_instructions > 512
+    n = 700_001  # odd: the last tile is ragged; > resident blocks x tile size: grid-stride loop
+    cols = w.make_inputs(n, 9)
+    ref = OracleProgram.from_program(w.program).run_chunked(cols, n)
+    got = gpu_eval(w.program, cols, n)
+    for g, r in zip(got, ref):
+        assert_close(g, r, RTOL, ATOL, what="multi-window program over many tiles")
+
+
+@pytest.mark.parametrize("iters", [1, 2, 3, 4, 9, 10])
+def test_double_buffered_iteration_parity_of_the_iteration_count(iters):
+    # the iterated image holds the program twice with parameter and result slots swapped: results come from a
+    # different set of slots after an even / odd number of iterations
+    w = workloads.get("aizawa")
+    n = 4099
+    cols = w.make_inputs(n, 31)
+    h = _handle(w.program)
+    assert h.export_packed(4)["double_buffered"]
+    a = [c.copy() for c in cols]
+    h.iterate_host(a, iters)
+    b = [c.copy() for c in cols]
+    for _ in range(iters):  # one iteration per launch = plain single passes
+        outs = [np.empty(n) for _ in b]
+        h.eval_host(b, outs, n)
+        b = outs
+    for x, y in zip(a, b):
+        assert bits_equal(x, y)
+
+
+def test_iteration_with_constant_and_parameter_results_uses_the_copy_path():
+    # (x, y) -> (y, 2.5): result 1 is a constant, so the image cannot be double buffered
+    prog = Program(flat=assemble([]), consts=[2.5], arg_pool=[], param_count=2, workspace_size=3, result_regs=[1, 2])
+    h = _handle(prog)
+    assert not h.export_packed(4)["double_buffered"]
+    rng = np.random.default_rng(5)
+    x, y = rng.normal(size=1000), rng.normal(size=1000)
+    for iters, ex, ey in ((1, y, np.full(1000, 2.5)), (2, np.full(1000, 2.5), np.full(1000, 2.5))):
+        st = [x.copy(), y.copy()]
+        h.iterate_host(st, iters)
+        assert bits_equal(st[0], ex) and bits_equal(st[1], ey)
+
+
+def test_host_call_sharded_over_devices():
+    # saf_eval_host_multi: contiguous shards, one host thread + stream set per device, no collective.
+    # With one GPU the same device is listed twice (two concurrent shards on one device).
+    w = workloads.get("aizawa")
+    n = 300_007
+    cols = w.make_inputs(n, 13)
+    h = _handle(w.program)
+    ref = [np.empty(n) for _ in w.program.result_regs]
+    h.eval_host(cols, ref, n)
+    ndev = device_count()
+    for devices in ([0, 0], list(range(ndev)), [0] * 3):
+        got = [np.full(n, -1.0) for _ in ref]
+        h.eval_host(cols, got, n, devices=devices)
+        for g, r in zip(got, ref):
+            assert bits_equal(g, r), devices
