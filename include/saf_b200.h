@@ -114,7 +114,7 @@ SAF_API int saf_program_export(const saf_program *prog, uint64_t *code, size_t c
                        double *consts, size_t cap_consts, size_t *n_consts,
                        uint16_t *param_slot, uint32_t *result_field);
 
-/* Copies out the PACKED micro-instruction image the kernel executes for `points_per_thread` in {1, 2, 4}
+/* Copies out the PACKED micro-instruction image the kernel executes for `points_per_thread` in {1, 2, 4, 8}
  * (layout: symbanafis_b200/csrc/uop.h): constants first, micro-instructions from byte `code_off`.
  * param_off / result_off are byte offsets (-1 = parameter never read), result_is_k[k] = 1 when result k is
  * a constant whose offset points into the image.  Iterated maps are double buffered when possible

@@ -51,12 +51,12 @@ struct saf_program {
     DeviceProgram dev;
     std::mutex mu;
     // packed micro-instruction images, one per register-file layout (P = 1, 2, 4), built on first use
-    PackedProgram packed[3];
-    bool packed_ready[3] = {false, false, false};
+    PackedProgram packed[4];
+    bool packed_ready[4] = {false, false, false, false};
     std::map<std::pair<int, int>, unsigned char *> copies; // (device, P) -> global-memory image for big programs
 };
 
-static int layout_index(int P) { return P == 4 ? 2 : P == 2 ? 1 : 0; }
+static int layout_index(int P) { return P == 8 ? 3 : P == 4 ? 2 : P == 2 ? 1 : 0; }
 
 static int build_program(std::vector<RefProgram> refs, saf_program **out) {
     std::unique_ptr<saf_program> p(new (std::nothrow) saf_program());
@@ -267,8 +267,8 @@ extern "C" int saf_program_export_packed(const saf_program *p, int points_per_th
                                          int32_t *param_off, int32_t *result_off, uint8_t *result_is_k,
                                          int32_t *result_off_even, int *double_buffered) {
     if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
-    if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4)
-        return fail(SAF_ERR_INVALID_ARGUMENT, "points_per_thread must be 1, 2 or 4");
+    if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4 && points_per_thread != 8)
+        return fail(SAF_ERR_INVALID_ARGUMENT, "points_per_thread must be 1, 2, 4 or 8");
     const PackedProgram *pk = nullptr;
     int rc = packed_for(const_cast<saf_program *>(p), points_per_thread, &pk);
     if (rc != SAF_OK) return rc;

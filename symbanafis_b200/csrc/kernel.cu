@@ -1,6 +1,6 @@
 // kernel.cu -- the sm_100a interpreter kernel for SymbAnaFis device programs.
 //
-// One thread evaluates P points (P = 1, 2 or 4), 128 threads per block.  Every lane of every warp runs
+// One thread evaluates P points (P = 1, 2, 4 or 8), 128 threads per block.  Every lane of every warp runs
 // the SAME program on different points, so the program counter, the fetched micro-instruction and the
 // opcode branch are warp-uniform: there is no divergence in the dispatch, only inside the data-dependent
 // slow paths of a few special functions.
@@ -549,6 +549,8 @@ SAF_ENTRY(saf_interp_p2_ksm, 2, true, SAF_MINB_P2)
 SAF_ENTRY(saf_interp_p2_kgm, 2, false, SAF_MINB_P2)
 SAF_ENTRY(saf_interp_p1_ksm, 1, true, SAF_MINB_P1)
 SAF_ENTRY(saf_interp_p1_kgm, 1, false, SAF_MINB_P1)
+SAF_ENTRY(saf_interp_p8_ksm, 8, true, SAF_MINB_P8)
+SAF_ENTRY(saf_interp_p8_kgm, 8, false, SAF_MINB_P8)
 #endif
 
 // ---- FP64 pipe peak probe ---------------------------------------------------------------------------

@@ -10,6 +10,9 @@
 #ifndef SAF_MINB_P4
 #define SAF_MINB_P4 6
 #endif
+#ifndef SAF_MINB_P8
+#define SAF_MINB_P8 4
+#endif
 #ifndef SAF_MINB_P2
 #define SAF_MINB_P2 6
 #endif
@@ -48,7 +51,7 @@ struct LaunchDesc {
 constexpr size_t K_SMEM_MAX = 24 * 1024;
 
 struct LaunchShape {
-    int points_per_thread; // 1, 2 or 4
+    int points_per_thread; // 1, 2, 4 or 8
     int block;             // threads per block (always BLOCK_THREADS)
     int grid;
     size_t smem_bytes;
@@ -59,7 +62,7 @@ struct LaunchShape {
 cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream);
 
 // Points per thread for a program with n_slots live values (before reserved slots) on `device`.
-// force_points_per_thread: 0 = automatic, 1 / 2 / 4 = tuning override (SAF_POINTS_PER_THREAD).
+// force_points_per_thread: 0 = automatic, 1 / 2 / 4 / 8 = tuning override (SAF_POINTS_PER_THREAD).
 cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
                                      int force_points_per_thread, int *points_per_thread);
 // Grid / shared memory / constant-table placement for the packed program.

@@ -40,7 +40,7 @@ struct Driver {
 
 struct DeviceModule {
     CUmodule mod = nullptr;
-    CUfunction interp[6] = {};
+    CUfunction interp[8] = {};
     CUfunction peak = nullptr;
     CUfunction clifford_probe = nullptr;
     bool ready = false;
@@ -88,12 +88,12 @@ cudaError_t module_for_current_device(DeviceModule **out) {
         }
         CUresult r = g_drv.module_load_data(&m.mod, saf_kernel_cubin);
         if (r != CUDA_SUCCESS) return as_cuda(r);
-        static const char *names[6] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm",
-                                       "saf_interp_p2_kgm", "saf_interp_p1_ksm", "saf_interp_p1_kgm"};
+        static const char *names[8] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
+                                       "saf_interp_p1_ksm", "saf_interp_p1_kgm", "saf_interp_p8_ksm", "saf_interp_p8_kgm"};
         int optin = 0;
         e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e != cudaSuccess) return e;
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 8; ++k) {
             r = g_drv.module_get_function(&m.interp[k], m.mod, names[k]);
             if (r != CUDA_SUCCESS) return as_cuda(r);
             // opt in to the full dynamic shared-memory carve-out
@@ -114,7 +114,7 @@ cudaError_t module_for_current_device(DeviceModule **out) {
 
 
 cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream) {
-    const int li = shape.points_per_thread == 4 ? 0 : shape.points_per_thread == 2 ? 1 : 2;
+    const int li = shape.points_per_thread == 4 ? 0 : shape.points_per_thread == 2 ? 1 : shape.points_per_thread == 1 ? 2 : 3;
     const int k = 2 * li + (shape.k_in_smem ? 0 : 1);
     DeviceModule *m = nullptr;
     cudaError_t e = module_for_current_device(&m);
@@ -151,7 +151,7 @@ size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_
            ((k_bytes_in_smem + 15) & ~(size_t)15) + ((window + 15) & ~(size_t)15);
 }
 
-static int resident_blocks_for(int P) { return P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1; }
+static int resident_blocks_for(int P) { return P == 8 ? SAF_MINB_P8 : P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1; }
 
 cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
                                      int force_points_per_thread, int *points_per_thread) {
@@ -173,7 +173,8 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
     int P = 1;
     if (aligned16 && enough(4) && fits(4, 2)) P = 4;
     else if (aligned16 && enough(2) && fits(2, 2)) P = 2;
-    if (force_points_per_thread == 1 || (aligned16 && (force_points_per_thread == 2 || force_points_per_thread == 4)))
+    if (force_points_per_thread == 1 ||
+        (aligned16 && (force_points_per_thread == 2 || force_points_per_thread == 4 || force_points_per_thread == 8)))
         P = force_points_per_thread;
     while (P > 1 && !fits(P, 1)) P >>= 1;
     if (!fits(P, 1)) return cudaErrorInvalidConfiguration;
