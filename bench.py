@@ -115,6 +115,18 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
+def measured_traffic(workload_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the interpreter launch from the committed ncu capture
+    (profiles/r01_dram_traffic.json), or None when that workload has not been captured."""
+    path = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f).get(workload_name)
+        return None if t is None else t["dram_bytes_read"] + t["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def workload_setup(args):
     from symbanafis_b200 import workloads
     w = workloads.get(args.workload)
@@ -322,10 +334,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks ----
-    t = torch.tensor([step_ms, e2e_ms, t_wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, e2e_ms, t_wall = (float(x) for x in t.cpu())
+    from symbanafis_b200.sharding import max_over_ranks
+    step_ms, e2e_ms, t_wall = max_over_ranks([step_ms, e2e_ms, t_wall], device=dev)
 
     units_per_step_gpu = n * iters
     units_per_step = units_per_step_gpu * world
@@ -343,7 +353,9 @@ def run_ours(args):
             achieved = 2.0 * slots_launch / dur / 1e12
             peak = 2.0 * fp64_peak / 1e12
             roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak if peak else None, "traffic": None,
+                        "frac": achieved / peak if peak else None,
+                        "traffic": measured_traffic(w.name) if (n == w.n_points) else None,
+                        "traffic_unit": "DRAM bytes per launch (ncu --set full capture, profiles/r01_dram_traffic.json)",
                         "peak_source": "DFMA-chain probe measured in this run (saf_measure_fp64_peak); "
                                        "FP64 is not in MEASURED_PEAKS.json",
                         "algorithmic": f"{info.fp64_slots:g} FP64 issue slots/point-eval (FMA = 2 FLOP) x "
@@ -353,7 +365,8 @@ def run_ours(args):
         else:
             achieved = bytes_launch / dur / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                        "frac": achieved / hbm_gbs, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                        "frac": achieved / hbm_gbs, "traffic": measured_traffic(w.name) if (n == w.n_points) else None,
+                        "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                         "algorithmic": f"{info.bytes_per_point:g} B/point x {n} points/launch",
                         "fp64_leg": {"achieved_tflops": 2.0 * slots_launch / dur / 1e12,
                                      "peak_tflops": 2.0 * fp64_peak / 1e12}}
