@@ -164,6 +164,8 @@ extern "C" int saf_program_export(const saf_program *p, uint64_t *code, size_t c
     return SAF_OK;
 }
 
+constexpr uint64_t kMaxItersPerLaunch = 1ull << 30;
+
 // ---- launch -------------------------------------------------------------------------------------------
 static int packed_for(saf_program *p, int P, const PackedProgram **out) {
     const int li = layout_index(P);
@@ -326,7 +328,14 @@ extern "C" int saf_iterate_device(const saf_program *prog, double *const *state,
     if (iters == 0 || n_points == 0) return SAF_OK;
     std::vector<size_t> lens(n_state, n_points);
     std::vector<const double *> cols(state, state + n_state);
-    return launch_on_device(prog, cols.data(), lens.data(), n_state, state, n_points, iters, 0, (cudaStream_t)stream);
+    // the kernel counts iterations in 32 bits: longer runs are a sequence of launches (the state is in the columns)
+    while (iters > 0) {
+        const uint64_t now = std::min<uint64_t>(iters, kMaxItersPerLaunch);
+        int rc = launch_on_device(prog, cols.data(), lens.data(), n_state, state, n_points, now, 0, (cudaStream_t)stream);
+        if (rc != SAF_OK) return rc;
+        iters -= now;
+    }
+    return SAF_OK;
 }
 
 // ---- host-buffer path -----------------------------------------------------------------------------------
@@ -487,7 +496,13 @@ extern "C" int saf_iterate_host(const saf_program *prog, double *const *state, s
     if (iters == 0 || n_points == 0) return SAF_OK;
     std::vector<size_t> lens(n_state, n_points);
     std::vector<const double *> cols(state, state + n_state);
-    return eval_host_range(prog, cols.data(), lens.data(), n_state, state, 0, n_points, iters, 0);
+    while (iters > 0) { // see saf_iterate_device
+        const uint64_t now = std::min<uint64_t>(iters, kMaxItersPerLaunch);
+        int rc = eval_host_range(prog, cols.data(), lens.data(), n_state, state, 0, n_points, now, 0);
+        if (rc != SAF_OK) return rc;
+        iters -= now;
+    }
+    return SAF_OK;
 }
 
 extern "C" int saf_eval_host_multi(const saf_program *prog, const double *const *cols, const size_t *lens,

@@ -459,3 +459,80 @@ def test_host_call_sharded_over_devices():
         h.eval_host(cols, got, n, devices=devices)
         for g, r in zip(got, ref):
             assert bits_equal(g, r), devices
+
+
+def test_constant_table_too_large_for_shared_memory_is_read_from_global_memory():
+    # 3500 distinct constants (28 KB > the 24 KB staging limit) added one by one: 3500 instructions = 7 code windows
+    rng = np.random.default_rng(17)
+    n_k = 3500
+    consts = rng.uniform(-1.0, 1.0, n_k)
+    instrs, acc = [], 0
+    tmp = 1 + n_k
+    for i in range(n_k):
+        instrs.append(("Add", tmp, acc, 1 + i))
+        acc = tmp
+    prog = Program(flat=assemble(instrs), consts=consts, arg_pool=[], param_count=1, workspace_size=2 + n_k,
+                   result_regs=[tmp])
+    h = _handle(prog)
+    pk = h.export_packed(4)
+    assert pk["code_off"] > 24 * 1024 and len(pk["image"]) * 8 - pk["code_off"] > 5 * 16 * 1024
+    n = 5000
+    x = rng.normal(size=n)
+    ref = OracleProgram.from_program(prog).eval_batch([x], n)[0]
+    got = gpu_eval(prog, [x], n)[0]
+    assert bits_equal(got, ref)
+
+
+# ---- BASELINE.json's full sizes, through size-independent properties ---------------------------------------------
+
+def test_full_size_clifford_1m_particles_1000_iterations_properties():
+    torch = pytest.importorskip("torch")
+    w = workloads.get("clifford")
+    n, iters = w.n_points, w.iterations
+    assert (n, iters) == (1_000_000, 1000)
+    cols = w.make_inputs(n, 2)
+    h = _handle(w.program)
+    dev = torch.device("cuda", 0)
+    a = [torch.from_numpy(c).to(dev) for c in cols]
+    b = [t.clone() for t in a]
+    h.iterate_device([t.data_ptr() for t in a], n, iters)          # 1000 iterations in one launch
+    for k in (500, 499, 1):                                          # == the same 1000 in three launches, bit for bit
+        h.iterate_device([t.data_ptr() for t in b], n, k)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x.view(torch.int64), y.view(torch.int64))
+    # the map sends everything into |x| <= 1 + |c|, |y| <= 1 + |d| (c = 1.0, d = 0.7) and never produces NaN
+    x, y = (t.cpu().numpy() for t in a)
+    assert np.isfinite(x).all() and np.isfinite(y).all()
+    assert np.abs(x).max() <= 2.0 + 1e-12 and np.abs(y).max() <= 1.7 + 1e-12
+    # one more step from that state agrees with the oracle on every particle
+    ref = OracleProgram.from_program(w.program).iterate([x, y], 1)
+    h.iterate_device([t.data_ptr() for t in a], n, 1)
+    torch.cuda.synchronize()
+    for t, r in zip(a, ref):
+        assert_close(t.cpu().numpy(), r, RTOL, ATOL, what="clifford step from the 1000th state")
+
+
+def test_full_size_terrain_gradient_sharding_independence_and_sampled_parity():
+    torch = pytest.importorskip("torch")
+    w = workloads.get("terrain_gradient")
+    n = 12_500_000  # one GPU's shard of the 100 M points of BASELINE.json config 5
+    cols = w.make_inputs(n, 42)
+    h = _handle(w.program)
+    dev = torch.device("cuda", 0)
+    tc = [torch.from_numpy(c).to(dev) for c in cols]
+    whole = [torch.empty(n, dtype=torch.float64, device=dev) for _ in w.program.result_regs]
+    h.eval_device([t.data_ptr() for t in tc], [n] * len(tc), [t.data_ptr() for t in whole], n)
+    # any contiguous sharding gives the same bits (points are independent): 3 ragged shards
+    parts = [torch.empty(n, dtype=torch.float64, device=dev) for _ in whole]
+    cuts = [0, 4_000_002, 9_999_998, n]  # even offsets keep the columns 16-byte aligned
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        h.eval_device([t[b:e].data_ptr() for t in tc], [e - b] * len(tc), [t[b:e].data_ptr() for t in parts], e - b)
+    torch.cuda.synchronize()
+    for x, y in zip(whole, parts):
+        assert torch.equal(x.view(torch.int64), y.view(torch.int64))
+    # sampled parity against the oracle
+    idx = np.random.default_rng(0).choice(n, 3000, replace=False)
+    ref = OracleProgram.from_program(w.program).eval_batch([c[idx] for c in cols], idx.size)
+    for t, r in zip(whole, ref):
+        assert_close(t.cpu().numpy()[idx], r, 1e-11, 1e-12, what="terrain gradient sample")
