@@ -1,0 +1,81 @@
+"""The C-ABI library on a machine without a GPU: it loads, exports every symbol include/saf_b200.h declares, and the
+host-only entry points (program creation, info, export, error reporting) behave; evaluation entry points fail
+loudly (SAF_ERR_CUDA) instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from symbanafis_b200 import _lib, workloads
+from symbanafis_b200._lib import DeviceProgramHandle, SafError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "saf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"SAF_API\s+[\w\s\*]+?\b(saf_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 17 and "saf_eval_host" in names and "saf_program_export_packed" in names
+    L = _lib.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names, "symbanafis_b200/_lib.py binds a different set than the header declares"
+
+
+def test_version_and_last_error_are_strings():
+    L = _lib.lib()
+    assert b"sm_100a" in L.saf_version()
+    assert isinstance(L.saf_last_error(), bytes)
+
+
+def test_host_only_entry_points_work_without_a_device():
+    w = workloads.get("clifford")
+    p = w.program
+    h = DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size, p.result_regs)
+    info = h.info()
+    assert (info.param_count, info.n_results) == (2, 2)
+    assert info.fp64_slots == 70.0 and info.bytes_per_point == 32.0
+    assert "sin" in h.disassemble()
+    for ppt in (1, 2, 4, 8):
+        pk = h.export_packed(ppt)
+        assert pk["double_buffered"] and pk["code_off"] % 32 == 0 and len(pk["image"]) * 8 > pk["code_off"]
+    with pytest.raises(SafError) as ei:
+        h.export_packed(3)
+    assert ei.value.code == _lib.SAF_ERR_INVALID_ARGUMENT
+
+
+def test_argument_errors_have_distinct_status_codes():
+    L = _lib.lib()
+    out = C.c_void_p()
+    assert L.saf_program_create(None, 0, None, 0, None, 0, 0, 0, None, 0, C.byref(out)) == _lib.SAF_ERR_INVALID_ARGUMENT
+    assert L.saf_program_create(None, 0, None, 0, None, 0, 0, 0, None, 0, None) == _lib.SAF_ERR_INVALID_ARGUMENT
+    assert L.saf_program_get_info(None, None) == _lib.SAF_ERR_INVALID_ARGUMENT
+    assert b"" != L.saf_last_error()
+    L.saf_program_destroy(None)  # a no-op, like dropping nothing
+
+
+@pytest.mark.skipif(_lib.device_count() > 0, reason="checks the behaviour WITHOUT a CUDA device")
+def test_evaluation_fails_loudly_without_a_device():
+    w = workloads.get("single_expr")
+    p = w.program
+    h = DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size, p.result_regs)
+    x = np.linspace(-1, 1, 16)
+    out = np.zeros(16)
+    with pytest.raises(SafError) as ei:
+        h.eval_host([x], [out], 16)
+    assert ei.value.code == _lib.SAF_ERR_CUDA  # no CPU fallback
+    # column-length mismatch is diagnosed before any device work (batch.rs:48-50)
+    with pytest.raises(SafError) as ei:
+        h.eval_host([x[:5]], [out], 16)
+    assert ei.value.code == _lib.SAF_ERR_COLUMN_LENGTH_MISMATCH
+    # the Python mirror raises too
+    from symbanafis_b200.evaluator import CompiledEvaluator
+    with pytest.raises(Exception):
+        CompiledEvaluator("x^2", ["x"]).eval_batch([x])

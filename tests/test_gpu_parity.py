@@ -536,3 +536,34 @@ def test_full_size_terrain_gradient_sharding_independence_and_sampled_parity():
     ref = OracleProgram.from_program(w.program).eval_batch([c[idx] for c in cols], idx.size)
     for t, r in zip(whole, ref):
         assert_close(t.cpu().numpy()[idx], r, 1e-11, 1e-12, what="terrain gradient sample")
+
+
+def test_one_handle_used_from_many_host_threads():
+    # the reference evaluator is Send + Sync (api.rs:113-124); Rayon workers call it concurrently
+    import threading
+    w = workloads.get("aizawa")
+    h = _handle(w.program)
+    n = 200_003
+    cols = w.make_inputs(n, 77)
+    ref = [np.empty(n) for _ in w.program.result_regs]
+    h.eval_host(cols, ref, n)
+    results, errors = [None] * 8, []
+
+    def work(i):
+        try:
+            out = [np.full(n, -5.0) for _ in ref]
+            for _ in range(3):
+                h.eval_host(cols, out, n)
+            results[i] = out
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for out in results:
+        for g, r in zip(out, ref):
+            assert bits_equal(g, r)
