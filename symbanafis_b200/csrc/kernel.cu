@@ -123,6 +123,30 @@ struct Rf {
     }
 };
 
+// destination store of a micro-instruction: predicated, not branched (d < 0 = result stays in ACC only)
+template <int P>
+__device__ __forceinline__ void store_if(uint32_t my, int32_t fd, const Pt<P> &o) {
+    const uint32_t p = my + (uint32_t)fd;
+    if constexpr (P == 1) {
+        asm volatile("{ .reg .pred q; setp.ge.s32 q, %0, 0; @q st.shared.f64 [%1], %2; }" ::"r"(fd), "r"(p), "d"(o.v[0]) : "memory");
+    } else if constexpr (P == 2) {
+        asm volatile("{ .reg .pred q; setp.ge.s32 q, %0, 0; @q st.shared.v2.f64 [%1], {%2, %3}; }" ::"r"(fd), "r"(p), "d"(o.v[0]),
+                     "d"(o.v[1])
+                     : "memory");
+    } else if constexpr (P == 4) {
+        asm volatile("{ .reg .pred q; setp.ge.s32 q, %0, 0; @q st.shared.v2.f64 [%1], {%2, %3}; @q st.shared.v2.f64 [%1+2048], {%4, %5}; }" ::"r"(fd),
+                     "r"(p), "d"(o.v[0]), "d"(o.v[1]), "d"(o.v[2]), "d"(o.v[3])
+                     : "memory");
+    } else {
+        static_assert(P == 8, "points per thread");
+        asm volatile("{ .reg .pred q; setp.ge.s32 q, %0, 0; @q st.shared.v2.f64 [%1], {%2, %3}; @q st.shared.v2.f64 [%1+2048], {%4, %5}; "
+                     "@q st.shared.v2.f64 [%1+4096], {%6, %7}; @q st.shared.v2.f64 [%1+6144], {%8, %9}; }" ::"r"(fd),
+                     "r"(p), "d"(o.v[0]), "d"(o.v[1]), "d"(o.v[2]), "d"(o.v[3]), "d"(o.v[4]), "d"(o.v[5]), "d"(o.v[6]), "d"(o.v[7])
+                     : "memory");
+    }
+}
+static_assert(BLOCK_THREADS * 16 == 2048, "store_if hard-codes the pair stride");
+
 #define SAF_FOR_P _Pragma("unroll") for (int p = 0; p < P; ++p)
 
 // Markers for tools/patch_brx.py: nvcc lowers a C++ switch to a compare tree (ptxas then folds only 3-case
@@ -131,6 +155,9 @@ struct Rf {
 #define SAF_DISPATCH(u) asm volatile("// SAF_DISPATCH %0 %1;" ::"r"(u), "n"((int)U_COUNT));
 #define SAF_CASE(v) asm volatile("// SAF_CASE %0;" ::"n"((int)(v)));
 #define SAF_CASE_DEFAULT asm volatile("// SAF_CASE default;");
+// end of a handler: the next dispatch happens right here (threaded code) -- the patcher replaces the jump back to
+// the loop head that follows this marker by its own brx.idx; `id` keeps the compiler from merging handler tails
+#define SAF_REDISPATCH(u, id) asm volatile("// SAF_REDISPATCH %0 %1;" ::"r"(u), "n"((int)(id)));
 
 __device__ __forceinline__ uint2 split64(unsigned long long w) { return make_uint2((uint32_t)w, (uint32_t)(w >> 32)); }
 
@@ -282,19 +309,42 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
     Pt<P> acc;
     RF::load(my, acc_off, acc);
 
-    // the opcode travels one instruction ahead of its operands (uop.h): read it from the instruction itself
-    // only when the loop is entered
+    // Every handler ends with "store the destination, fetch the next micro-instruction" (SAF_NEXT).  With
+    // THREADED dispatch it then jumps through the table itself: one indirect branch per micro-op and no trip
+    // through a common loop head -- shorter latency per micro-op, which pays when few warps are resident (small
+    // batches, big register files: the P = 1 and P = 2 layouts; double pendulum -7 %, terrain gradient -13 %).
+    // Otherwise all handlers return to one dispatch at the loop head, which ptxas keeps entirely in the uniform
+    // datapath: fewer issue slots, which pays when the machine is full (P >= 4; Clifford +5 %, Aizawa +15 %
+    // against threaded).  The opcode travels one instruction ahead of its operands (uop.h): it is read from the
+    // instruction itself only when the loop is entered.
+    constexpr bool THREADED = P <= 2;
     uint32_t uop = lds_u32(pc + 28);
+    int32_t fd;
+    uint32_t fa, fb, cur, uop_now;
+#define SAF_FETCH                                                                                          \
+    {                                                                                                      \
+        const uint4 q_ = lds_u128(pc); /* {next uop, d, a, b} */                                           \
+        fd = (int32_t)q_.y; fa = q_.z; fb = q_.w;                                                          \
+        cur = pc; pc += UINSTR_BYTES;                                                                      \
+        uop_now = uop; uop = q_.x;                                                                         \
+    }
+#define SAF_NEXT(id)                                                                                       \
+    {                                                                                                      \
+        if constexpr (THREADED) {                                                                          \
+            if (fd >= 0) RF::store(my, (uint32_t)fd, acc);                                                 \
+            SAF_FETCH SAF_REDISPATCH(uop_now, id) continue;                                                \
+        } else {                                                                                           \
+            break; /* common tail below the switch: store, then the fetch at the loop head */              \
+        }                                                                                                  \
+    }
+#define SAF_RESTART(id) /* after U_END / U_NEXTWIN: no destination */                                      \
+    {                                                                                                      \
+        if constexpr (THREADED) { SAF_FETCH SAF_REDISPATCH(uop_now, id) }                                  \
+        continue;                                                                                          \
+    }
+    if constexpr (THREADED) SAF_FETCH
     for (;;) {
-        for (;;) {
-            const uint4 q = lds_u128(pc); // {next uop, d, a, b}
-            const int32_t fd = (int32_t)q.y;
-            const uint32_t fa = q.z, fb = q.w;
-            const uint32_t cur = pc;
-            pc += UINSTR_BYTES;
-            const uint32_t uop_now = uop;
-            uop = q.x;
-
+            if constexpr (!THREADED) SAF_FETCH
             Pt<P> a, b, c;
 
 #define LS(x, f) RF::load(my, (f), x);
@@ -304,42 +354,42 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
 
 // light unary: a from a slot / from ACC
 #define U1CASE(OP, EXPR)                                                                                   \
-    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY): SAF_CASE(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY)) LS(a, fa) SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_CASE(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1) SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } break;
+    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY): SAF_CASE(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY)) LS(a, fa) SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY)) \
+    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_CASE(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1) SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1)
 // heavy unary: operand from a slot, {plain, affine prefix}; BODY maps a.v -> acc.v and never reads ACC
 #define H1PREFIX { const double k1_ = konst(fb), k2_ = konst(fb + 8); SAF_FOR_P a.v[p] = __fma_rn(a.v[p], k1_, k2_); }
 #define H1CASE(H, BODY)                                                                                    \
-    case U_H1 + 2 * (H) + 0: SAF_CASE(U_H1 + 2 * (H) + 0) LS(a, fa) { BODY } break;                                                     \
-    case U_H1 + 2 * (H) + 1: SAF_CASE(U_H1 + 2 * (H) + 1) LS(a, fa) H1PREFIX { BODY } break;
+    case U_H1 + 2 * (H) + 0: SAF_CASE(U_H1 + 2 * (H) + 0) LS(a, fa) { BODY } SAF_NEXT(U_H1 + 2 * (H) + 0)                                                     \
+    case U_H1 + 2 * (H) + 1: SAF_CASE(U_H1 + 2 * (H) + 1) LS(a, fa) H1PREFIX { BODY } SAF_NEXT(U_H1 + 2 * (H) + 1)
 // commutative binary: SS SK SA KA AA
 #define BCCASE(I, EXPR)                                                                                    \
-    case U_BC + 5 * (I) + BC_SS: SAF_CASE(U_BC + 5 * (I) + BC_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BC + 5 * (I) + BC_SK: SAF_CASE(U_BC + 5 * (I) + BC_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BC + 5 * (I) + BC_SA: SAF_CASE(U_BC + 5 * (I) + BC_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BC + 5 * (I) + BC_KA: SAF_CASE(U_BC + 5 * (I) + BC_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BC + 5 * (I) + BC_AA: SAF_CASE(U_BC + 5 * (I) + BC_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break;
+    case U_BC + 5 * (I) + BC_SS: SAF_CASE(U_BC + 5 * (I) + BC_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_SS) \
+    case U_BC + 5 * (I) + BC_SK: SAF_CASE(U_BC + 5 * (I) + BC_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BC + 5 * (I) + BC_SK) \
+    case U_BC + 5 * (I) + BC_SA: SAF_CASE(U_BC + 5 * (I) + BC_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_SA) \
+    case U_BC + 5 * (I) + BC_KA: SAF_CASE(U_BC + 5 * (I) + BC_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BC + 5 * (I) + BC_KA) \
+    case U_BC + 5 * (I) + BC_AA: SAF_CASE(U_BC + 5 * (I) + BC_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_AA)
 // ordered binary: SS SK KS SA AS KA AK AA
 #define BNCASE(I, EXPR)                                                                                    \
-    case U_BN + 8 * (I) + BN_SS: SAF_CASE(U_BN + 8 * (I) + BN_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BN + 8 * (I) + BN_SK: SAF_CASE(U_BN + 8 * (I) + BN_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BN + 8 * (I) + BN_KS: SAF_CASE(U_BN + 8 * (I) + BN_KS) LS(b, fb) { const double x = konst(fa); SAF_FOR_P { const double y = b.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BN + 8 * (I) + BN_SA: SAF_CASE(U_BN + 8 * (I) + BN_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BN + 8 * (I) + BN_AS: SAF_CASE(U_BN + 8 * (I) + BN_AS) LS(b, fb) SAF_FOR_P { const double x = acc.v[p], y = b.v[p]; acc.v[p] = (EXPR); } break; \
-    case U_BN + 8 * (I) + BN_KA: SAF_CASE(U_BN + 8 * (I) + BN_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BN + 8 * (I) + BN_AK: SAF_CASE(U_BN + 8 * (I) + BN_AK) { const double y = konst(fb); SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_BN + 8 * (I) + BN_AA: SAF_CASE(U_BN + 8 * (I) + BN_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } break;
+    case U_BN + 8 * (I) + BN_SS: SAF_CASE(U_BN + 8 * (I) + BN_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_SS) \
+    case U_BN + 8 * (I) + BN_SK: SAF_CASE(U_BN + 8 * (I) + BN_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_SK) \
+    case U_BN + 8 * (I) + BN_KS: SAF_CASE(U_BN + 8 * (I) + BN_KS) LS(b, fb) { const double x = konst(fa); SAF_FOR_P { const double y = b.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_KS) \
+    case U_BN + 8 * (I) + BN_SA: SAF_CASE(U_BN + 8 * (I) + BN_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_SA) \
+    case U_BN + 8 * (I) + BN_AS: SAF_CASE(U_BN + 8 * (I) + BN_AS) LS(b, fb) SAF_FOR_P { const double x = acc.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_AS) \
+    case U_BN + 8 * (I) + BN_KA: SAF_CASE(U_BN + 8 * (I) + BN_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_KA) \
+    case U_BN + 8 * (I) + BN_AK: SAF_CASE(U_BN + 8 * (I) + BN_AK) { const double y = konst(fb); SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_AK) \
+    case U_BN + 8 * (I) + BN_AA: SAF_CASE(U_BN + 8 * (I) + BN_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_AA)
 // fused multiply-add family: x * y (+/-) z
 #define TCASE(T, EXPR)                                                                                     \
-    case U_T + 10 * (T) + T_SSS: SAF_CASE(U_T + 10 * (T) + T_SSS) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SSK: SAF_CASE(U_T + 10 * (T) + T_SSK) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SSA: SAF_CASE(U_T + 10 * (T) + T_SSA) { LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SKS: SAF_CASE(U_T + 10 * (T) + T_SKS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SKK: SAF_CASE(U_T + 10 * (T) + T_SKK) { const uint32_t fc = FC; LS(a, fa) const double y = konst(fb), z = konst(fc); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SKA: SAF_CASE(U_T + 10 * (T) + T_SKA) { LS(a, fa) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SAS: SAF_CASE(U_T + 10 * (T) + T_SAS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_SAK: SAF_CASE(U_T + 10 * (T) + T_SAK) { const uint32_t fc = FC; LS(a, fa) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_KAS: SAF_CASE(U_T + 10 * (T) + T_KAS) { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } break; \
-    case U_T + 10 * (T) + T_KAK: SAF_CASE(U_T + 10 * (T) + T_KAK) { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } break;
+    case U_T + 10 * (T) + T_SSS: SAF_CASE(U_T + 10 * (T) + T_SSS) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSS) \
+    case U_T + 10 * (T) + T_SSK: SAF_CASE(U_T + 10 * (T) + T_SSK) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSK) \
+    case U_T + 10 * (T) + T_SSA: SAF_CASE(U_T + 10 * (T) + T_SSA) { LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSA) \
+    case U_T + 10 * (T) + T_SKS: SAF_CASE(U_T + 10 * (T) + T_SKS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKS) \
+    case U_T + 10 * (T) + T_SKK: SAF_CASE(U_T + 10 * (T) + T_SKK) { const uint32_t fc = FC; LS(a, fa) const double y = konst(fb), z = konst(fc); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKK) \
+    case U_T + 10 * (T) + T_SKA: SAF_CASE(U_T + 10 * (T) + T_SKA) { LS(a, fa) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKA) \
+    case U_T + 10 * (T) + T_SAS: SAF_CASE(U_T + 10 * (T) + T_SAS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SAS) \
+    case U_T + 10 * (T) + T_SAK: SAF_CASE(U_T + 10 * (T) + T_SAK) { const uint32_t fc = FC; LS(a, fa) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SAK) \
+    case U_T + 10 * (T) + T_KAS: SAF_CASE(U_T + 10 * (T) + T_KAS) { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_KAS) \
+    case U_T + 10 * (T) + T_KAK: SAF_CASE(U_T + 10 * (T) + T_KAK) { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_KAK)
 
             SAF_DISPATCH(uop_now)
             switch (uop_now) {
@@ -351,14 +401,33 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
                     stage_window(win_sm, code_g, win_g, code_bytes);
                 }
                 pc = win_sm + (fa & (CODE_WINDOW_BYTES - 1u));
-                goto program_end;
+                // in-kernel feedback for images that are not double buffered: parameter j <- result j (result
+                // slots never alias parameter slots, lower.cpp); the state stays on chip between iterations
+                const uint32_t n_fb = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, n_params));
+                if (n_fb != 0u) {
+                    const uint32_t k_mask = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, result_k_mask));
+                    for (uint32_t j = 0; j < n_fb; ++j) {
+                        const int32_t s_ = (int32_t)lds_u32(ctx + (uint32_t)offsetof(BlockCtx, param_off) + 4u * j);
+                        if (s_ < 0) continue;
+                        const uint32_t r_ = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, result_off) + 4u * j);
+                        Pt<P> v;
+                        if ((k_mask >> j) & 1u) {
+                            const double k = konst(r_);
+                            SAF_FOR_P v.v[p] = k;
+                        } else {
+                            RF::load(my, r_, v);
+                        }
+                        RF::store(my, (uint32_t)s_, v);
+                    }
+                }
+                SAF_RESTART(U_END)
             }
             case U_NEXTWIN: SAF_CASE(U_NEXTWIN) // end of the staged window: stage the next one, continue at its start
                 win_g += CODE_WINDOW_BYTES;
                 stage_window(win_sm, code_g, win_g, code_bytes);
                 pc = win_sm;
-                continue;
-            case U_LOADK: SAF_CASE(U_LOADK) { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } break;
+                SAF_RESTART(U_NEXTWIN)
+            case U_LOADK: SAF_CASE(U_LOADK) { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } SAF_NEXT(U_LOADK)
 
             U1CASE(D_COPY, x)
             U1CASE(D_NEG, -x)
@@ -402,28 +471,7 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
                 RF::store(my, acc_off, acc);
                 return ((unsigned long long)it << 32) | (win_g + (cur - win_sm));
             }
-            if (fd >= 0) RF::store(my, (uint32_t)fd, acc);
-        }
-    program_end:
-        // ---- in-kernel feedback: parameter j <- result j (result slots never alias parameter slots,
-        // lower.cpp); the state stays on chip between iterations ----
-        {
-            const uint32_t n_params = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, n_params));
-            const uint32_t k_mask = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, result_k_mask));
-            for (uint32_t j = 0; j < n_params; ++j) {
-                const int32_t s = (int32_t)lds_u32(ctx + (uint32_t)offsetof(BlockCtx, param_off) + 4u * j);
-                if (s < 0) continue;
-                const uint32_t r = lds_u32(ctx + (uint32_t)offsetof(BlockCtx, result_off) + 4u * j);
-                Pt<P> v;
-                if ((k_mask >> j) & 1u) {
-                    const double k = konst(r);
-                    SAF_FOR_P v.v[p] = k;
-                } else {
-                    RF::load(my, r, v);
-                }
-                RF::store(my, (uint32_t)s, v);
-            }
-        }
+            if (fd >= 0) RF::store(my, (uint32_t)fd, acc); // reached by the non-threaded handlers only
     }
 }
 
