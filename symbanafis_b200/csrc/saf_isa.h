@@ -14,7 +14,7 @@
 //         [63:48] b   second source field
 // A field is  index(14) << 2 | kind(2):
 //     kind 0 = S[index]  live-value slot of this point in the on-chip register file
-//     kind 1 = K[index]  constant table (constant bank / global memory, warp-uniform load)
+//     kind 1 = K[index]  constant table (staged in shared memory, warp-uniform broadcast load)
 //     kind 2 = ACC       the accumulator: result of the previous instruction, kept in real registers
 //     kind 3 = none
 // Every value-producing instruction leaves its result in ACC; if d is an S field it is also stored.

@@ -4,7 +4,7 @@
 // layout-independent: fields are slot / constant INDICES.  Before a launch the host packs it for one
 // register-file layout (points per thread P) into fixed-size 32-byte micro-instructions whose operands
 // are ready-to-use BYTE OFFSETS, and whose opcode says where every operand comes from, so that a handler
-// is: one integer add per shared-memory operand, one constant-bank load per constant operand, the FP64
+// is: one integer add per shared-memory operand, one broadcast load per constant operand, the FP64
 // instructions, and a sign-tested store.  No operand-kind decoding, shifting or masking happens in the
 // hot handlers.
 //
