@@ -395,6 +395,58 @@ std::vector<int32_t> schedule_by_progress(const Graph &g, const std::vector<uint
     return order;
 }
 
+// Chain following on top of a given order: right after an instruction whose value has exactly one consumer, emit
+// that consumer if everything else it needs has already been computed.  The value then travels through the
+// accumulator instead of a register-file slot (one shared-memory store and one load less), and the consumer's
+// other operands die earlier.  Any order produced this way is still topological.
+std::vector<int32_t> follow_chains(const Graph &g, const std::vector<uint8_t> &live, const std::vector<int32_t> &results,
+                                   const std::vector<int32_t> &base) {
+    const int32_t N = (int32_t)g.nodes.size();
+    auto producer = [&](int32_t v) -> int32_t {
+        uint8_t op = g.nodes[v].op;
+        if (op == V_COSPART) return g.nodes[v].a;
+        return op < V_PARAM ? v : -1;
+    };
+    std::vector<int32_t> n_uses(N, 0), only_consumer(N, -1);
+    for (int32_t n : base) {
+        const Node &nd = g.nodes[n];
+        for (int32_t s : {nd.a, nd.b, nd.c, nd.e}) {
+            if (s < 0) continue;
+            ++n_uses[s];
+            only_consumer[s] = n;
+        }
+    }
+    for (int32_t r : results) n_uses[r] += 2; // results stay in their slot: never chained away
+    std::vector<uint8_t> two_valued(N, 0);     // SINCOS nodes produce a second value (their COSPART)
+    for (auto &kv : g.cos_of) two_valued[kv.first] = 1;
+    std::vector<uint8_t> done(N, 0);
+    std::vector<int32_t> out;
+    out.reserve(base.size());
+    auto ready = [&](int32_t c, int32_t except) {
+        const Node &nd = g.nodes[c];
+        for (int32_t s : {nd.a, nd.b, nd.c, nd.e}) {
+            if (s < 0) continue;
+            const int32_t pr = producer(s);
+            if (pr >= 0 && pr != except && !done[pr]) return false;
+        }
+        return true;
+    };
+    for (int32_t n0 : base) {
+        int32_t n = n0;
+        while (n >= 0 && !done[n]) {
+            done[n] = 1;
+            out.push_back(n);
+            int32_t next = -1;
+            if (!two_valued[n] && n_uses[n] == 1) {
+                const int32_t c = only_consumer[n];
+                if (c >= 0 && live[c] && !done[c] && g.nodes[c].op < V_PARAM && ready(c, n)) next = c;
+            }
+            n = next;
+        }
+    }
+    return out;
+}
+
 std::vector<int32_t> schedule_nodes(const Graph &g, const std::vector<uint8_t> &live,
                                     const std::vector<int32_t> &results) {
     const int32_t N = (int32_t)g.nodes.size();
@@ -991,8 +1043,19 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
     int rc_a, rc_b;
     {
         std::string saved = err;
-        rc_a = emit_program(schedule_by_progress(g, live, results), cand_a);
+        const std::vector<int32_t> base_a = schedule_by_progress(g, live, results);
+        rc_a = emit_program(base_a, cand_a);
         err_a = err;
+        err = saved;
+        // chain following keeps (a)'s lockstep of the long sums and adds accumulator forwards inside a term
+        DeviceProgram cand_a2;
+        const int rc_a2 = emit_program(follow_chains(g, live, results, base_a), cand_a2);
+        if (rc_a2 == SAF_OK && (rc_a != SAF_OK || (cand_a2.n_slots <= cand_a.n_slots + cand_a.n_slots / 8 &&
+                                                   cand_a2.n_acc_forwards > cand_a.n_acc_forwards))) {
+            cand_a = std::move(cand_a2);
+            rc_a = rc_a2;
+            err_a = err;
+        }
         err = saved;
         rc_b = emit_program(schedule_nodes(g, live, results), cand_b);
         err_b = err;
@@ -1006,7 +1069,7 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
     else if (rc_b != SAF_OK) pick_a = true;
     else if (cand_a.n_slots * 4 < cand_b.n_slots * 3) pick_a = true;
     else if (cand_b.n_slots * 4 < cand_a.n_slots * 3) pick_a = false;
-    else pick_a = cand_a.n_acc_forwards >= cand_b.n_acc_forwards;
+    else pick_a = cand_a.n_acc_forwards > cand_b.n_acc_forwards; // ties: the demand-driven order measured faster
     if (pick_a) {
         out = std::move(cand_a);
         err = err_a;
