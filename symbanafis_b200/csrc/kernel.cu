@@ -328,21 +328,31 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
         cur = pc; pc += UINSTR_BYTES;                                                                      \
         uop_now = uop; uop = q_.x;                                                                         \
     }
+#define SAF_ROTATE /* the prefetched instruction becomes the current one */                               \
+    {                                                                                                      \
+        fd = (int32_t)qn.y; fa = qn.z; fb = qn.w;                                                          \
+        cur = pc; pc += UINSTR_BYTES;                                                                      \
+        uop_now = uop; uop = qn.x;                                                                         \
+    }
 #define SAF_NEXT(id)                                                                                       \
     {                                                                                                      \
         if constexpr (THREADED) {                                                                          \
             if (fd >= 0) RF::store(my, (uint32_t)fd, acc);                                                 \
-            SAF_FETCH SAF_REDISPATCH(uop_now, id) continue;                                                \
+            SAF_ROTATE SAF_REDISPATCH(uop_now, id) continue;                                               \
         } else {                                                                                           \
             break; /* common tail below the switch: store, then the fetch at the loop head */              \
         }                                                                                                  \
     }
-#define SAF_RESTART(id) /* after U_END / U_NEXTWIN: no destination */                                      \
+#define SAF_RESTART(id) /* after U_END / U_NEXTWIN (pc has changed): no destination */                     \
     {                                                                                                      \
-        if constexpr (THREADED) { SAF_FETCH SAF_REDISPATCH(uop_now, id) }                                  \
+        if constexpr (THREADED) { qn = lds_u128(pc); SAF_ROTATE SAF_REDISPATCH(uop_now, id) }              \
         continue;                                                                                          \
     }
-    if constexpr (THREADED) SAF_FETCH
+    // threaded handlers fetch the NEXT micro-instruction as their first action (pc already points at it), so that
+    // its latency overlaps their own operand loads
+#define SAF_ENTER(v) SAF_CASE(v) if constexpr (THREADED) { qn = lds_u128(pc); }
+    uint4 qn = make_uint4(0u, 0u, 0u, 0u);
+    if constexpr (THREADED) { qn = lds_u128(pc); SAF_ROTATE }
     for (;;) {
             if constexpr (!THREADED) SAF_FETCH
             Pt<P> a, b, c;
@@ -354,42 +364,42 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
 
 // light unary: a from a slot / from ACC
 #define U1CASE(OP, EXPR)                                                                                   \
-    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY): SAF_CASE(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY)) LS(a, fa) SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY)) \
-    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_CASE(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1) SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1)
+    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY): SAF_ENTER(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY)) LS(a, fa) SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY)) \
+    case U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1: SAF_ENTER(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1) SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_U1 + 2 * ((OP) - D_FIRST_LIGHT_UNARY) + 1)
 // heavy unary: operand from a slot, {plain, affine prefix}; BODY maps a.v -> acc.v and never reads ACC
 #define H1PREFIX { const double k1_ = konst(fb), k2_ = konst(fb + 8); SAF_FOR_P a.v[p] = __fma_rn(a.v[p], k1_, k2_); }
 #define H1CASE(H, BODY)                                                                                    \
-    case U_H1 + 2 * (H) + 0: SAF_CASE(U_H1 + 2 * (H) + 0) LS(a, fa) { BODY } SAF_NEXT(U_H1 + 2 * (H) + 0)                                                     \
-    case U_H1 + 2 * (H) + 1: SAF_CASE(U_H1 + 2 * (H) + 1) LS(a, fa) H1PREFIX { BODY } SAF_NEXT(U_H1 + 2 * (H) + 1)
+    case U_H1 + 2 * (H) + 0: SAF_ENTER(U_H1 + 2 * (H) + 0) LS(a, fa) { BODY } SAF_NEXT(U_H1 + 2 * (H) + 0)                                                     \
+    case U_H1 + 2 * (H) + 1: SAF_ENTER(U_H1 + 2 * (H) + 1) LS(a, fa) H1PREFIX { BODY } SAF_NEXT(U_H1 + 2 * (H) + 1)
 // commutative binary: SS SK SA KA AA
 #define BCCASE(I, EXPR)                                                                                    \
-    case U_BC + 5 * (I) + BC_SS: SAF_CASE(U_BC + 5 * (I) + BC_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_SS) \
-    case U_BC + 5 * (I) + BC_SK: SAF_CASE(U_BC + 5 * (I) + BC_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BC + 5 * (I) + BC_SK) \
-    case U_BC + 5 * (I) + BC_SA: SAF_CASE(U_BC + 5 * (I) + BC_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_SA) \
-    case U_BC + 5 * (I) + BC_KA: SAF_CASE(U_BC + 5 * (I) + BC_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BC + 5 * (I) + BC_KA) \
-    case U_BC + 5 * (I) + BC_AA: SAF_CASE(U_BC + 5 * (I) + BC_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_AA)
+    case U_BC + 5 * (I) + BC_SS: SAF_ENTER(U_BC + 5 * (I) + BC_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_SS) \
+    case U_BC + 5 * (I) + BC_SK: SAF_ENTER(U_BC + 5 * (I) + BC_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BC + 5 * (I) + BC_SK) \
+    case U_BC + 5 * (I) + BC_SA: SAF_ENTER(U_BC + 5 * (I) + BC_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_SA) \
+    case U_BC + 5 * (I) + BC_KA: SAF_ENTER(U_BC + 5 * (I) + BC_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BC + 5 * (I) + BC_KA) \
+    case U_BC + 5 * (I) + BC_AA: SAF_ENTER(U_BC + 5 * (I) + BC_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BC + 5 * (I) + BC_AA)
 // ordered binary: SS SK KS SA AS KA AK AA
 #define BNCASE(I, EXPR)                                                                                    \
-    case U_BN + 8 * (I) + BN_SS: SAF_CASE(U_BN + 8 * (I) + BN_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_SS) \
-    case U_BN + 8 * (I) + BN_SK: SAF_CASE(U_BN + 8 * (I) + BN_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_SK) \
-    case U_BN + 8 * (I) + BN_KS: SAF_CASE(U_BN + 8 * (I) + BN_KS) LS(b, fb) { const double x = konst(fa); SAF_FOR_P { const double y = b.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_KS) \
-    case U_BN + 8 * (I) + BN_SA: SAF_CASE(U_BN + 8 * (I) + BN_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_SA) \
-    case U_BN + 8 * (I) + BN_AS: SAF_CASE(U_BN + 8 * (I) + BN_AS) LS(b, fb) SAF_FOR_P { const double x = acc.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_AS) \
-    case U_BN + 8 * (I) + BN_KA: SAF_CASE(U_BN + 8 * (I) + BN_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_KA) \
-    case U_BN + 8 * (I) + BN_AK: SAF_CASE(U_BN + 8 * (I) + BN_AK) { const double y = konst(fb); SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_AK) \
-    case U_BN + 8 * (I) + BN_AA: SAF_CASE(U_BN + 8 * (I) + BN_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_AA)
+    case U_BN + 8 * (I) + BN_SS: SAF_ENTER(U_BN + 8 * (I) + BN_SS) LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_SS) \
+    case U_BN + 8 * (I) + BN_SK: SAF_ENTER(U_BN + 8 * (I) + BN_SK) LS(a, fa) { const double y = konst(fb); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_SK) \
+    case U_BN + 8 * (I) + BN_KS: SAF_ENTER(U_BN + 8 * (I) + BN_KS) LS(b, fb) { const double x = konst(fa); SAF_FOR_P { const double y = b.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_KS) \
+    case U_BN + 8 * (I) + BN_SA: SAF_ENTER(U_BN + 8 * (I) + BN_SA) LS(a, fa) SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_SA) \
+    case U_BN + 8 * (I) + BN_AS: SAF_ENTER(U_BN + 8 * (I) + BN_AS) LS(b, fb) SAF_FOR_P { const double x = acc.v[p], y = b.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_AS) \
+    case U_BN + 8 * (I) + BN_KA: SAF_ENTER(U_BN + 8 * (I) + BN_KA) { const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_KA) \
+    case U_BN + 8 * (I) + BN_AK: SAF_ENTER(U_BN + 8 * (I) + BN_AK) { const double y = konst(fb); SAF_FOR_P { const double x = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_BN + 8 * (I) + BN_AK) \
+    case U_BN + 8 * (I) + BN_AA: SAF_ENTER(U_BN + 8 * (I) + BN_AA) SAF_FOR_P { const double x = acc.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } SAF_NEXT(U_BN + 8 * (I) + BN_AA)
 // fused multiply-add family: x * y (+/-) z
 #define TCASE(T, EXPR)                                                                                     \
-    case U_T + 10 * (T) + T_SSS: SAF_CASE(U_T + 10 * (T) + T_SSS) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSS) \
-    case U_T + 10 * (T) + T_SSK: SAF_CASE(U_T + 10 * (T) + T_SSK) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSK) \
-    case U_T + 10 * (T) + T_SSA: SAF_CASE(U_T + 10 * (T) + T_SSA) { LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSA) \
-    case U_T + 10 * (T) + T_SKS: SAF_CASE(U_T + 10 * (T) + T_SKS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKS) \
-    case U_T + 10 * (T) + T_SKK: SAF_CASE(U_T + 10 * (T) + T_SKK) { const uint32_t fc = FC; LS(a, fa) const double y = konst(fb), z = konst(fc); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKK) \
-    case U_T + 10 * (T) + T_SKA: SAF_CASE(U_T + 10 * (T) + T_SKA) { LS(a, fa) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKA) \
-    case U_T + 10 * (T) + T_SAS: SAF_CASE(U_T + 10 * (T) + T_SAS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SAS) \
-    case U_T + 10 * (T) + T_SAK: SAF_CASE(U_T + 10 * (T) + T_SAK) { const uint32_t fc = FC; LS(a, fa) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SAK) \
-    case U_T + 10 * (T) + T_KAS: SAF_CASE(U_T + 10 * (T) + T_KAS) { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_KAS) \
-    case U_T + 10 * (T) + T_KAK: SAF_CASE(U_T + 10 * (T) + T_KAK) { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_KAK)
+    case U_T + 10 * (T) + T_SSS: SAF_ENTER(U_T + 10 * (T) + T_SSS) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSS) \
+    case U_T + 10 * (T) + T_SSK: SAF_ENTER(U_T + 10 * (T) + T_SSK) { const uint32_t fc = FC; LS(a, fa) LS(b, fb) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = b.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSK) \
+    case U_T + 10 * (T) + T_SSA: SAF_ENTER(U_T + 10 * (T) + T_SSA) { LS(a, fa) LS(b, fb) SAF_FOR_P { const double x = a.v[p], y = b.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SSA) \
+    case U_T + 10 * (T) + T_SKS: SAF_ENTER(U_T + 10 * (T) + T_SKS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKS) \
+    case U_T + 10 * (T) + T_SKK: SAF_ENTER(U_T + 10 * (T) + T_SKK) { const uint32_t fc = FC; LS(a, fa) const double y = konst(fb), z = konst(fc); SAF_FOR_P { const double x = a.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKK) \
+    case U_T + 10 * (T) + T_SKA: SAF_ENTER(U_T + 10 * (T) + T_SKA) { LS(a, fa) const double y = konst(fb); SAF_FOR_P { const double x = a.v[p], z = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SKA) \
+    case U_T + 10 * (T) + T_SAS: SAF_ENTER(U_T + 10 * (T) + T_SAS) { const uint32_t fc = FC; LS(a, fa) LS(c, fc) SAF_FOR_P { const double x = a.v[p], y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SAS) \
+    case U_T + 10 * (T) + T_SAK: SAF_ENTER(U_T + 10 * (T) + T_SAK) { const uint32_t fc = FC; LS(a, fa) const double z = konst(fc); SAF_FOR_P { const double x = a.v[p], y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_SAK) \
+    case U_T + 10 * (T) + T_KAS: SAF_ENTER(U_T + 10 * (T) + T_KAS) { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_KAS) \
+    case U_T + 10 * (T) + T_KAK: SAF_ENTER(U_T + 10 * (T) + T_KAK) { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_KAK)
 
             SAF_DISPATCH(uop_now)
             switch (uop_now) {
@@ -427,7 +437,7 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
                 stage_window(win_sm, code_g, win_g, code_bytes);
                 pc = win_sm;
                 SAF_RESTART(U_NEXTWIN)
-            case U_LOADK: SAF_CASE(U_LOADK) { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } SAF_NEXT(U_LOADK)
+            case U_LOADK: SAF_ENTER(U_LOADK) { const double k_ = konst(fa); SAF_FOR_P acc.v[p] = k_; } SAF_NEXT(U_LOADK)
 
             U1CASE(D_COPY, x)
             U1CASE(D_NEG, -x)
