@@ -24,6 +24,7 @@
 #include "kernel.cuh"
 #include "lower.h"
 #include "pack.h"
+#include "ruop.h"
 
 using namespace saf;
 
@@ -51,12 +52,14 @@ struct saf_program {
     DeviceProgram dev;
     std::mutex mu;
     // packed micro-instruction images, one per register-file layout (P = 1, 2, 4), built on first use
-    PackedProgram packed[4];
-    bool packed_ready[4] = {false, false, false, false};
+    PackedProgram packed[5];          // [4] = register machine (ruop.h)
+    bool packed_ready[5] = {false, false, false, false, false};
+    int r_pack_rc = 0;                // result of the register-machine packing (kept: failures are not retried)
     std::map<std::pair<int, int>, unsigned char *> copies; // (device, P) -> global-memory image for big programs
 };
 
-static int layout_index(int P) { return P == 8 ? 3 : P == 4 ? 2 : P == 2 ? 1 : 0; }
+constexpr int LAYOUT_R = 100 + R_POINTS; // layout id of the register machine
+static int layout_index(int P) { return P == LAYOUT_R ? 4 : P == 8 ? 3 : P == 4 ? 2 : P == 2 ? 1 : 0; }
 
 static int build_program(std::vector<RefProgram> refs, saf_program **out) {
     std::unique_ptr<saf_program> p(new (std::nothrow) saf_program());
@@ -172,9 +175,14 @@ static int packed_for(saf_program *p, int P, const PackedProgram **out) {
     std::lock_guard<std::mutex> lk(p->mu);
     if (!p->packed_ready[li]) {
         std::string err;
-        int rc = pack_program(p->dev, P, p->packed[li], err);
-        if (rc != SAF_OK) return fail(rc, err);
+        int rc = P == LAYOUT_R ? pack_program_r(p->dev, p->packed[li], err) : pack_program(p->dev, P, p->packed[li], err);
+        if (P == LAYOUT_R) p->r_pack_rc = rc;
+        if (rc != SAF_OK && P != LAYOUT_R) return fail(rc, err);
+        if (rc != SAF_OK) g_last_error = err;
         p->packed_ready[li] = true;
+    }
+    if (P == LAYOUT_R && p->r_pack_rc != SAF_OK) {
+        return p->r_pack_rc;
     }
     *out = &p->packed[li];
     return SAF_OK;
@@ -182,7 +190,7 @@ static int packed_for(saf_program *p, int P, const PackedProgram **out) {
 
 static int ensure_device_image(saf_program *p, int device, const PackedProgram &pk, const unsigned char **out) {
     std::lock_guard<std::mutex> lk(p->mu);
-    const auto key = std::make_pair(device, pk.points_per_thread);
+    const auto key = std::make_pair(device, pk.layout_id);
     auto it = p->copies.find(key);
     if (it != p->copies.end()) {
         *out = it->second;
@@ -236,7 +244,26 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_points_per_thread");
     const PackedProgram *pk = nullptr;
-    int rc = packed_for(const_cast<saf_program *>(prog), P, &pk);
+    int rc = SAF_OK;
+    // Register machine (ruop.h): live values in real registers, four points per thread.  It pays for programs made
+    // of plain arithmetic; transcendental-heavy programs keep the shared-memory machine, whose heavy handlers take
+    // their operand from any slot (SAF_MACHINE=r / s forces one of them: tuning knob).
+    static const int forced_machine = []() {
+        const char *v = getenv("SAF_MACHINE");
+        return !v ? 0 : v[0] == 'r' ? 1 : v[0] == 's' ? 2 : 0;
+    }();
+    bool use_r = false;
+    if (aligned && forced_machine != 2 && dp.consts.size() * 8 + 64 <= K_SMEM_MAX &&
+        (forced_machine == 1 || (dp.n_dev_instructions > 0 && dp.fp64_slots < 2.5 * dp.n_dev_instructions))) {
+        const PackedProgram *rp = nullptr;
+        if (packed_for(const_cast<saf_program *>(prog), LAYOUT_R, &rp) == SAF_OK && (d.iters == 1 || rp->can_iterate) &&
+            rp->code_off <= K_SMEM_MAX) {
+            pk = rp;
+            use_r = true;
+            P = R_POINTS;
+        }
+    }
+    if (!use_r) rc = packed_for(const_cast<saf_program *>(prog), P, &pk);
     if (rc != SAF_OK) return rc;
     d.code_off = pk->code_off;
     d.n_slots = pk->n_slots;
@@ -249,12 +276,12 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
         d.result_off[k] = even ? pk->result_off_even[k] : pk->result_off[k];
         if (pk->result_is_k[k]) d.result_k_mask |= 1u << k;
     }
-    d.n_feedback = pk->double_buffered ? 0u : dp.param_count; // parameters hot_run copies back between iterations
+    d.n_feedback = (pk->double_buffered || use_r) ? 0u : dp.param_count; // parameters hot_run copies back between iterations
     rc = ensure_device_image(const_cast<saf_program *>(prog), device, *pk, &d.image_global);
     if (rc != SAF_OK) return rc;
     d.code_bytes = pk->code_bytes;
     LaunchShape shape;
-    e = choose_shape(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points, P, &shape);
+    e = choose_shape(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points, P, use_r, &shape);
     if (e == cudaErrorInvalidConfiguration)
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_shape");
@@ -269,8 +296,9 @@ extern "C" int saf_program_export_packed(const saf_program *p, int points_per_th
                                          int32_t *param_off, int32_t *result_off, uint8_t *result_is_k,
                                          int32_t *result_off_even, int *double_buffered) {
     if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
-    if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4 && points_per_thread != 8)
-        return fail(SAF_ERR_INVALID_ARGUMENT, "points_per_thread must be 1, 2, 4 or 8");
+    if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4 && points_per_thread != 8 &&
+        points_per_thread != LAYOUT_R)
+        return fail(SAF_ERR_INVALID_ARGUMENT, "points_per_thread must be 1, 2, 4, 8 or 104 (register machine)");
     const PackedProgram *pk = nullptr;
     int rc = packed_for(const_cast<saf_program *>(p), points_per_thread, &pk);
     if (rc != SAF_OK) return rc;

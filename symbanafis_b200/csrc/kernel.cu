@@ -37,6 +37,7 @@
 // MulAdd (macros.rs:69-75 vs :128-138).  -fmad stays at its default because the CUDA math library
 // needs it (see devmath.cuh).
 #include "kernel.cuh"
+#include "ruop.h"
 
 #include <cstddef>
 #include <cstdio>
@@ -153,6 +154,7 @@ static_assert(BLOCK_THREADS * 16 == 2048, "store_if hard-codes the pair stride")
 // leaves into jump tables); the build rewrites the PTX of hot_run to ONE brx.idx over all micro-ops.  The
 // markers are PTX comments that carry the opcode register / the case value to the patcher.
 #define SAF_DISPATCH(u) asm volatile("// SAF_DISPATCH %0 %1;" ::"r"(u), "n"((int)U_COUNT));
+#define SAF_DISPATCH_N(u, n) asm volatile("// SAF_DISPATCH %0 %1;" ::"r"(u), "n"((int)(n)));
 #define SAF_CASE(v) asm volatile("// SAF_CASE %0;" ::"n"((int)(v)));
 #define SAF_CASE_DEFAULT asm volatile("// SAF_CASE default;");
 // end of a handler: the next dispatch happens right here (threaded code) -- the patcher replaces the jump back to
@@ -175,14 +177,15 @@ __device__ __forceinline__ unsigned long long point_index(unsigned long long til
 // pow, powi, 1/expm1, the builtins (61 FnOps of devmath.cuh), operand staging and the rare operand-kind
 // combinations: decoded at run time, out of line, memory to memory.  ACC is read from / written to the
 // reserved slot `acc_off`; hot_run stores ACC there before it returns and reloads it when re-entered.
-template <int P>
+template <int P, bool RM = false>
 __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int32_t acc_off, int32_t x0_off,
                                      int32_t x1_off) {
     using RF = Rf<P>;
     const uint32_t my = RF::mine(smem_base32());
     const unsigned long long *w = reinterpret_cast<const unsigned long long *>(img + cur);
     const uint2 q0 = split64(w[0]), q1 = split64(w[1]), q2 = split64(w[2]), q3 = split64(w[3]);
-    const uint32_t uop = q3.y, fa = q1.x, fb = q1.y, fc = q2.x, imm = q2.y, kinds = q3.x; // word 0 holds the NEXT opcode
+    // word 0 holds the NEXT opcode; register-machine images (ruop.h) carry the cold micro-op above the kinds
+    const uint32_t uop = RM ? (q3.x >> 8) : q3.y, fa = q1.x, fb = q1.y, fc = q2.x, imm = q2.y, kinds = q3.x & 0xffu;
     const int32_t fd = (int32_t)q0.y;
     auto konst = [&](uint32_t off) -> double { return *reinterpret_cast<const double *>(img + off); };
     auto any = [&](uint32_t kind, uint32_t f, Pt<P> &o) {
@@ -485,8 +488,14 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
     }
 }
 
+#ifndef SAF_R_THREADED
+#define SAF_R_THREADED false
+#endif
+#include "kernel_r.cuh"
+
 // ---- the kernel ------------------------------------------------------------------------------------------
-template <int P, bool K_SMEM>
+// RM: the register machine (ruop.h, kernel_r.cuh) runs the program; its image is packed by pack_r.cpp
+template <int P, bool K_SMEM, bool RM = false>
 __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     using RF = Rf<P>;
     const uint32_t smem32 = smem_base32();
@@ -557,11 +566,13 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
                 stage_window(smem32 + win_s, d.image_global + d.code_off, 0u, d.code_bytes);
             uint32_t pc = 0, it = 0;
             for (;;) {
-                const unsigned long long st = hot_run<P, K_SMEM>(smem32, ctx_off, d.image_global, pc, it, iters);
+                unsigned long long st;
+                if constexpr (RM) st = hot_run_r<K_SMEM, SAF_R_THREADED>(smem32, ctx_off, d.image_global, pc, it, iters);
+                else st = hot_run<P, K_SMEM>(smem32, ctx_off, d.image_global, pc, it, iters);
                 if (st == HOT_DONE) break;
                 pc = (uint32_t)st;
                 it = (uint32_t)(st >> 32);
-                cold_op<P>(d.image_global, d.code_off + pc, d.acc_off, d.x0_off, d.x1_off);
+                cold_op<P, RM>(d.image_global, d.code_off + pc, d.acc_off, d.x0_off, d.x1_off);
                 pc += UINSTR_BYTES;
             }
         }
@@ -601,6 +612,11 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     }
 // *_ksm: constant table staged in shared memory; *_kgm: read from global memory (very large tables)
 SAF_ENTRY(saf_interp_p4_ksm, 4, true, SAF_MINB_P4)
+#define SAF_ENTRY_R(NAME, SM, MINB)                                                                        \
+    extern "C" __global__ void __launch_bounds__(BLOCK_THREADS, MINB) NAME(const __grid_constant__ LaunchDesc d) { \
+        interp_body<R_POINTS, SM, true>(d);                                                                \
+    }
+SAF_ENTRY_R(saf_rinterp_ksm, true, SAF_MINB_R)
 #ifndef SAF_FAST_BUILD
 SAF_ENTRY(saf_interp_p4_kgm, 4, false, SAF_MINB_P4)
 SAF_ENTRY(saf_interp_p2_ksm, 2, true, SAF_MINB_P2)

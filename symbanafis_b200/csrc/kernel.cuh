@@ -16,6 +16,9 @@
 #ifndef SAF_MINB_P2
 #define SAF_MINB_P2 6
 #endif
+#ifndef SAF_MINB_R
+#define SAF_MINB_R 4
+#endif
 #ifndef SAF_MINB_P1
 #define SAF_MINB_P1 6
 #endif
@@ -56,6 +59,7 @@ struct LaunchShape {
     int grid;
     size_t smem_bytes;
     bool k_in_smem;        // the constant table is staged in shared memory (else read from global memory)
+    bool rmachine;         // register machine (ruop.h): saf_rinterp_ksm
 };
 
 // Launches the interpreter; desc.image_global must point at a device copy of the packed image.
@@ -67,7 +71,7 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
                                      int force_points_per_thread, int *points_per_thread);
 // Grid / shared memory / constant-table placement for the packed program.
 cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
-                         int points_per_thread, LaunchShape *shape);
+                         int points_per_thread, bool rmachine, LaunchShape *shape);
 // register file + block context + constant table (when staged) + code window
 size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes);
 

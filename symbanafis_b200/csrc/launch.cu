@@ -40,7 +40,7 @@ struct Driver {
 
 struct DeviceModule {
     CUmodule mod = nullptr;
-    CUfunction interp[8] = {};
+    CUfunction interp[9] = {}; // [8] = register machine
     CUfunction peak = nullptr;
     CUfunction clifford_probe = nullptr;
     bool ready = false;
@@ -88,12 +88,13 @@ cudaError_t module_for_current_device(DeviceModule **out) {
         }
         CUresult r = g_drv.module_load_data(&m.mod, saf_kernel_cubin);
         if (r != CUDA_SUCCESS) return as_cuda(r);
-        static const char *names[8] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
-                                       "saf_interp_p1_ksm", "saf_interp_p1_kgm", "saf_interp_p8_ksm", "saf_interp_p8_kgm"};
+        static const char *names[9] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
+                                       "saf_interp_p1_ksm", "saf_interp_p1_kgm", "saf_interp_p8_ksm", "saf_interp_p8_kgm",
+                                       "saf_rinterp_ksm"};
         int optin = 0;
         e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e != cudaSuccess) return e;
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 9; ++k) {
             r = g_drv.module_get_function(&m.interp[k], m.mod, names[k]);
             if (r != CUDA_SUCCESS) return as_cuda(r);
             // opt in to the full dynamic shared-memory carve-out
@@ -115,7 +116,8 @@ cudaError_t module_for_current_device(DeviceModule **out) {
 
 cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream) {
     const int li = shape.points_per_thread == 4 ? 0 : shape.points_per_thread == 2 ? 1 : shape.points_per_thread == 1 ? 2 : 3;
-    const int k = 2 * li + (shape.k_in_smem ? 0 : 1);
+    const int k = shape.rmachine ? 8 : 2 * li + (shape.k_in_smem ? 0 : 1);
+    if (shape.rmachine && !shape.k_in_smem) return cudaErrorInvalidConfiguration;
     DeviceModule *m = nullptr;
     cudaError_t e = module_for_current_device(&m);
     if (e != cudaSuccess) return e;
@@ -183,7 +185,7 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
 }
 
 cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
-                         int P, LaunchShape *shape) {
+                         int P, bool rmachine, LaunchShape *shape) {
     int sms = 0, smem_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -196,7 +198,7 @@ cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t co
         smem = interpreter_smem_bytes(n_slots, P, 0, code_bytes);
     }
     if (smem > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
-    size_t resident = (size_t)resident_blocks_for(P); // __launch_bounds__ register budget
+    size_t resident = rmachine ? (size_t)SAF_MINB_R : (size_t)resident_blocks_for(P); // __launch_bounds__ register budget
     const size_t by_smem = ((size_t)smem_optin + 1024) / (smem + 1024);
     if (by_smem < resident) resident = by_smem;
     if (resident < 1) resident = 1;
@@ -210,6 +212,7 @@ cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t co
     shape->grid = (int)grid;
     shape->smem_bytes = smem;
     shape->k_in_smem = k_in_smem;
+    shape->rmachine = rmachine;
     return cudaSuccess;
 }
 

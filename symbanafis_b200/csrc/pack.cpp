@@ -29,6 +29,7 @@ struct UI {
 int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string &err) {
     out = PackedProgram();
     out.points_per_thread = P;
+    out.layout_id = P;
     const uint32_t SB = slot_bytes(P);
 
     // ---- decode ----

@@ -12,6 +12,9 @@ namespace saf {
 
 struct PackedProgram {
     int points_per_thread = 0;
+    int layout_id = 0;                 // points_per_thread for the shared-memory machine, 100 + P for the register machine
+    bool can_iterate = true;           // the image loops in-kernel (saf_iterate_*); register-machine images of programs
+                                       // whose results do not pair with their parameters cannot
     // image = constant table (padded to 32 bytes), then the code: n_instr micro-instruction slots cut into
     // windows of CODE_WINDOW_BYTES (uop.h).  K operands are byte offsets into the image, program counters are
     // byte offsets into the code.
@@ -35,6 +38,8 @@ struct PackedProgram {
 constexpr uint32_t slot_bytes(int points_per_thread) { return (uint32_t)BLOCK_THREADS * 8u * (uint32_t)points_per_thread; }
 
 // Returns 0 or SAF_ERR_UNSUPPORTED (err filled).
+// Register machine (ruop.h, pack_r.cpp): four points per thread, live values in real registers.
+int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err);
 int pack_program(const DeviceProgram &dp, int points_per_thread, PackedProgram &out, std::string &err);
 
 } // namespace saf

@@ -353,3 +353,192 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
                 if int(off) >= 0:
                     store(int(off), result_value(j))
     return [result_value(k, final_off) for k in range(len(pk["result_off"]))]
+
+
+# ---- register-machine image (symbanafis_b200/csrc/ruop.h, produced by pack_r.cpp) ------------------------
+R_NREG, XK_K, XK_S, XK_COUNT = 8, 8, 9, 10
+RU_END, RU_EXIT, RU_NEXTWIN, RU_COLD, RU_MOV = 0, 1, 2, 3, 4
+RU_ST = RU_MOV + R_NREG * XK_COUNT
+RU_BIN = RU_ST + R_NREG
+RB_NAMES = ["add", "mul", "sub", "rsub", "negmul"]
+RU_UN = RU_BIN + len(RB_NAMES) * R_NREG * XK_COUNT
+RUN_NAMES = ["neg", "cube", "pow4"]
+R_NPAIR = R_NREG * (R_NREG + 1) // 2
+RU_FRR = RU_UN + len(RUN_NAMES) * R_NREG
+RU_FKA = RU_FRR + 4 * R_NREG * R_NPAIR
+RU_FKM = RU_FKA + 4 * R_NREG * R_NREG
+RU_H0 = RU_FKM + 4 * R_NREG * XK_COUNT
+RU_U0 = RU_H0 + 2 * N_H1
+RU0_NAMES = ["pow3_2", "invpow3_2", "invsqrt", "invsquare", "invcube", "recip", "sqrt"]
+RU_DIV = RU_U0 + len(RU0_NAMES)
+RU_RDIV = RU_DIV + XK_COUNT
+RU_COUNT = RU_RDIV + XK_COUNT
+R_PAIRS = [(a, b) for a in range(R_NREG) for b in range(a, R_NREG)]
+R_LAYOUT = 104  # points_per_thread value that selects the register-machine image in saf_program_export_packed
+
+
+def run_packed_r_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iters: int = 1) -> List[np.ndarray]:
+    """Executes a register-machine image exactly as kernel_r.cuh does: eight registers that are LOST whenever the
+    dispatch loop is left for a cold micro-op (they are poisoned with NaN here), slots addressed by byte offset,
+    the opcode of every instruction carried by its predecessor.  Leaf math is delegated to the oracle."""
+    image = np.asarray(pk["image"], dtype=np.uint64)
+    kview = image.view(np.float64)
+    P = 4
+    slot_bytes = 128 * 8 * P
+    rf_bytes = int(pk["n_slots"]) * slot_bytes
+    RF: Dict[int, np.ndarray] = {}
+    poison = np.full(n_points, np.nan)
+    R = [poison.copy() for _ in range(R_NREG)]
+
+    def K(off: int) -> np.ndarray:
+        assert off % 8 == 0 and off < int(pk["code_off"]), "constant operand outside the constant table"
+        return np.full(n_points, kview[off // 8])
+
+    def S(off: int) -> np.ndarray:
+        assert off % slot_bytes == 0 and 0 <= off < rf_bytes, "slot operand outside the register file"
+        return RF[off]
+
+    def store(off: int, v: np.ndarray):
+        assert off % slot_bytes == 0 and 0 <= off < rf_bytes, "slot store outside the register file"
+        RF[off] = v.copy()
+
+    def X(xk: int, off: int) -> np.ndarray:
+        return R[xk] if xk < R_NREG else K(off) if xk == XK_K else S(off)
+
+    def ref1(name, x):
+        return _leaf((name, 1, 0), 1).eval_batch([x], n_points)[0]
+
+    def ref2(name, x, y):
+        return _leaf((name, 2, 0, 1), 2).eval_batch([x, y], n_points)[0]
+
+    def ref3(name, x, y, z):
+        return _leaf((name, 3, 0, 1, 2), 3).eval_batch([x, y, z], n_points)[0]
+
+    def by_kind(kind: int, off: int) -> np.ndarray:
+        assert kind in (KIND_S, KIND_K), "cold micro-ops of the register machine read slots and constants only"
+        return S(off) if kind == KIND_S else K(off)
+
+    for j, off in enumerate(pk["param_off"]):
+        off = int(off)
+        if off < 0:
+            continue
+        if j < len(cols):
+            c = np.asarray(cols[j], dtype=np.float64)
+            store(off, c[np.minimum(np.arange(n_points), len(c) - 1)])
+        else:
+            store(off, np.zeros(n_points))
+
+    i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
+    code0 = int(pk["code_off"]) // 8
+    pc, it, carried, steps = 0, 0, None, 0
+    while True:
+        steps += 1
+        assert steps < 50_000_000, "runaway register-machine program"
+        w0, w1, w2, w3 = (int(x) for x in image[code0 + pc:code0 + pc + 4])
+        here = pc
+        pc += 4
+        uop_next, fd = w0 & 0xFFFFFFFF, i32(w0 >> 32)
+        fa, fb, imm, low3, uop = w1 & 0xFFFFFFFF, w1 >> 32, w2 >> 32, w3 & 0xFFFFFFFF, w3 >> 32
+        assert carried is None or carried == uop, "word 0 of the previous instruction does not carry this opcode"
+        carried = uop_next
+        assert uop < RU_COUNT
+        if uop == RU_NEXTWIN:
+            assert (pc * 8) % CODE_WINDOW_BYTES == 0, "RU_NEXTWIN must be the last slot of its window"
+            continue
+        assert (here * 8) % CODE_WINDOW_BYTES != CODE_WINDOW_BYTES - 32, "window's last slot must be RU_NEXTWIN"
+        if uop == RU_EXIT:
+            break
+        if uop == RU_END:
+            it += 1
+            if it < iters:
+                assert fa % 32 == 0
+                pc = fa // 8
+            carried = None  # the kernel re-reads the opcode after RU_END
+            continue
+        if uop == RU_COLD:
+            kinds, cold = low3 & 0xFF, low3 >> 8
+            name = G_NAMES[cold - U_G]
+            ka, kb = kinds & 3, (kinds >> 2) & 3
+            r = None
+            if name == "pow":
+                r = ref2("Pow", by_kind(ka, fa), by_kind(kb, fb))
+            elif name == "recipexpm1":
+                x = by_kind(ka, fa)
+                if fb != NO_PREFIX:
+                    x = ref3("MulAdd", x, K(fb), K(fb + 8))
+                r = ref1("RecipExpm1", x)
+            elif name == "powi":
+                r = _leaf(("Powi", 1, 0, i32(imm)), 1).eval_batch([by_kind(ka, fa)], n_points)[0]
+            elif name == "builtin1":
+                r = _leaf(("Builtin1", 1, imm, 0), 1).eval_batch([by_kind(ka, fa)], n_points)[0]
+            elif name == "builtin2":
+                r = _leaf(("Builtin2", 2, imm, 0, 1), 2).eval_batch([by_kind(ka, fa), by_kind(kb, fb)], n_points)[0]
+            elif name == "builtin3":
+                r = _leaf(("Builtin3", 3, imm, 0, 1, 2), 3).eval_batch(
+                    [S(int(pk["x_off"][0])), S(int(pk["x_off"][1])), by_kind(ka, fa)], n_points)[0]
+            elif name == "builtin4":
+                r = _leaf(("Builtin4", 4, imm, 0, 1, 2, 3), 4).eval_batch(
+                    [S(int(pk["x_off"][0])), S(int(pk["x_off"][1])), by_kind(ka, fa), by_kind(kb, fb)], n_points)[0]
+            elif name == "arg2":
+                x0, x1 = by_kind(ka, fa).copy(), by_kind(kb, fb).copy()
+                store(int(pk["x_off"][0]), x0)
+                store(int(pk["x_off"][1]), x1)
+            else:
+                raise AssertionError(f"cold micro-op {name} is not produced by pack_r.cpp")
+            if r is not None:
+                store(int(pk["x_off"][2]), r)
+                if fd >= 0:
+                    store(fd, r)
+            R = [poison.copy() for _ in range(R_NREG)]  # the dispatch loop's registers do not survive
+            carried = None
+            continue
+        if uop < RU_ST:
+            d, xk = divmod(uop - RU_MOV, XK_COUNT)
+            R[d] = X(xk, fa).copy()
+        elif uop < RU_BIN:
+            store(fa, R[uop - RU_ST])
+        elif uop < RU_UN:
+            od, xk = divmod(uop - RU_BIN, XK_COUNT)
+            o, d = divmod(od, R_NREG)
+            name, x = RB_NAMES[o], X(xk, fa)
+            R[d] = ref2("Sub", x, R[d]) if name == "rsub" else ref2(_BINARY_REF[name], R[d], x)
+        elif uop < RU_FRR:
+            u, d = divmod(uop - RU_UN, R_NREG)
+            R[d] = ref1(_UNARY_REF[RUN_NAMES[u]], R[d])
+        elif uop < RU_FKA:
+            sd, pair = divmod(uop - RU_FRR, R_NPAIR)
+            s_, d = divmod(sd, R_NREG)
+            a, b = R_PAIRS[pair]
+            R[d] = ref3(_TERNARY_REF[T_NAMES[s_]], R[a], R[b], R[d])
+        elif uop < RU_FKM:
+            sd, a = divmod(uop - RU_FKA, R_NREG)
+            s_, d = divmod(sd, R_NREG)
+            R[d] = ref3(_TERNARY_REF[T_NAMES[s_]], R[a], K(fa), R[d])
+        elif uop < RU_H0:
+            sd, xk = divmod(uop - RU_FKM, XK_COUNT)
+            s_, d = divmod(sd, R_NREG)
+            R[d] = ref3(_TERNARY_REF[T_NAMES[s_]], R[d], K(fa), X(xk, fb))
+        elif uop < RU_U0:
+            h, prefixed = divmod(uop - RU_H0, 2)
+            x = R[1]
+            if prefixed:
+                x = ref3("MulAdd", x, K(fb), K(fb + 8))
+            name = H1_NAMES[h]
+            if name == "expneg":
+                R[0] = _leaf(("Builtin1", 1, "exp_neg", 0), 1).eval_batch([x], n_points)[0]
+            elif name == "sincos":
+                R[0], R[2] = _leaf(("SinCos", 1, 2, 0), 1, 2).eval_batch([x], n_points)
+            else:
+                R[0] = ref1(_UNARY_REF[name], x)
+        elif uop < RU_DIV:
+            R[0] = ref1(_UNARY_REF[RU0_NAMES[uop - RU_U0]], R[0])
+        elif uop < RU_RDIV:
+            R[0] = ref2("Div", R[0], X(uop - RU_DIV, fa))
+        else:
+            R[0] = ref2("Div", X(uop - RU_RDIV, fa), R[0])
+
+    def result_value(k: int) -> np.ndarray:
+        off = int(pk["result_off"][k])
+        return K(off) if pk["result_is_k"][k] else S(off).copy()
+
+    return [result_value(k) for k in range(len(pk["result_off"]))]

@@ -6,7 +6,7 @@ leaf math) and compared with the oracle executing the original reference bytecod
 import numpy as np
 import pytest
 
-from dev_emulator import run_device_program, run_packed_program
+from dev_emulator import R_LAYOUT, run_device_program, run_packed_program, run_packed_r_program
 from oracle import OracleProgram
 from symbanafis_b200 import workloads
 from symbanafis_b200._lib import DeviceProgramHandle, SafError
@@ -31,6 +31,12 @@ def _check(prog, cols, n, iters=1):
         got = run_packed_program(h.export_packed(ppt), cols, n, iters)
         for k, (r, g) in enumerate(zip(ref, got)):
             assert bits_equal(g, r), f"packed image (P={ppt}): result {k} differs"
+    # the register machine's image (pack_r.cpp: register allocation, spills, state registers of iterated maps);
+    # it loops in-kernel only when results pair with parameters
+    if iters == 1 or (len(rfield) == prog.param_count and len(rfield) <= 5):
+        got = run_packed_r_program(h.export_packed(R_LAYOUT), cols, n, iters)
+        for k, (r, g) in enumerate(zip(ref, got)):
+            assert bits_equal(g, r), f"register-machine image: result {k} differs"
     return h
 
 
