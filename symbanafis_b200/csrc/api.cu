@@ -256,8 +256,10 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     if (aligned && forced_machine != 2 && dp.consts.size() * 8 + 64 <= K_SMEM_MAX &&
         (forced_machine == 1 || (dp.n_dev_instructions > 0 && dp.fp64_slots < 2.5 * dp.n_dev_instructions))) {
         const PackedProgram *rp = nullptr;
+        LaunchShape rs;
         if (packed_for(const_cast<saf_program *>(prog), LAYOUT_R, &rp) == SAF_OK && (d.iters == 1 || rp->can_iterate) &&
-            rp->code_off <= K_SMEM_MAX) {
+            choose_shape(device, rp->n_slots, rp->code_off, rp->code_bytes, n_points, R_POINTS, true, &rs) == cudaSuccess &&
+            rs.k_in_smem) {
             pk = rp;
             use_r = true;
             P = R_POINTS;

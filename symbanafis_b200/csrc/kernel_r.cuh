@@ -58,22 +58,23 @@ namespace {
 #define RF_E1(X, Y, Z) __fma_rn(X, Y, -(Z))
 #define RF_E2(X, Y, Z) __fma_rn(-(X), Y, Z)
 #define RF_E3(X, Y, Z) __fma_rn(-(X), Y, -(Z))
-#define R_FRR_P(a, b, d, s, E) R_H(RU_FRR + ((s) * 8 + (d)) * 36 + r_pair(a, b), SAF_FOR_P r##d.v[p] = E(r##a.v[p], r##b.v[p], r##d.v[p]);)
-#define R_FRR_D(d, s, E) R_FOR_PAIR(R_FRR_P, d, s, E)
-#define R_FKA_DX(x, d, s, E) R_H(RU_FKA + ((s) * 8 + (d)) * 8 + (x), { const double k_ = konst(fa); SAF_FOR_P r##d.v[p] = E(r##x.v[p], k_, r##d.v[p]); })
-#define R_FKA_D(d, s, E) R_FOR_X(R_FKA_DX, d, s, E)
-#define R_FKM_DX(x, d, s, E) R_H(RU_FKM + ((s) * 8 + (d)) * 10 + (x), { const double k_ = konst(fa); SAF_FOR_P r##d.v[p] = E(r##d.v[p], k_, r##x.v[p]); })
-#define R_FKM_D(d, s, E)                                                                                   \
-    R_FOR_X(R_FKM_DX, d, s, E)                                                                             \
-    R_H(RU_FKM + ((s) * 8 + (d)) * 10 + XK_K, { const double k_ = konst(fa), z_ = konst(fb); SAF_FOR_P r##d.v[p] = E(r##d.v[p], k_, z_); }) \
-    R_H(RU_FKM + ((s) * 8 + (d)) * 10 + XK_S, { const double k_ = konst(fa); R_X_S(z_, fb) SAF_FOR_P r##d.v[p] = E(r##d.v[p], k_, z_.v[p]); })
+// (on R0 only, see ruop.h)
+#define R_FRR_P(a, b, s, E) R_H(RU_FRR + (s) * 36 + r_pair(a, b), SAF_FOR_P r0.v[p] = E(r##a.v[p], r##b.v[p], r0.v[p]);)
+#define R_FRR_S(s, E) R_FOR_PAIR(R_FRR_P, s, E)
+#define R_FKA_X(x, s, E) R_H(RU_FKA + (s) * 8 + (x), { const double k_ = konst(fa); SAF_FOR_P r0.v[p] = E(r##x.v[p], k_, r0.v[p]); })
+#define R_FKA_S(s, E) R_FOR_X(R_FKA_X, s, E)
+#define R_FKM_X(x, s, E) R_H(RU_FKM + (s) * 10 + (x), { const double k_ = konst(fa); SAF_FOR_P r0.v[p] = E(r0.v[p], k_, r##x.v[p]); })
+#define R_FKM_S(s, E)                                                                                      \
+    R_FOR_X(R_FKM_X, s, E)                                                                                 \
+    R_H(RU_FKM + (s) * 10 + XK_K, { const double k_ = konst(fa), z_ = konst(fb); SAF_FOR_P r0.v[p] = E(r0.v[p], k_, z_); }) \
+    R_H(RU_FKM + (s) * 10 + XK_S, { const double k_ = konst(fa); R_X_S(z_, fb) SAF_FOR_P r0.v[p] = E(r0.v[p], k_, z_.v[p]); })
 // ---- heavy operations, in place on R0 ----
-// R0 = f(R1): argument and result in different registers -- the n-wide leanmath kernels re-read their argument on
+// R1 = f(R0): argument and result in different registers -- the n-wide leanmath kernels re-read their argument on
 // the slow path, and with an in-place form ptxas splits R0's live range at the loop head (8 moves per dispatch)
 #define R_H0PREFIX { const double k1_ = konst(fb), k2_ = konst(fb + 8); SAF_FOR_P a_.v[p] = __fma_rn(a_.v[p], k1_, k2_); }
 #define R_H0CASE(H, ...)                                                                                   \
-    R_H(RU_H0 + 2 * (H) + 0, const Pt<P> &a_ = r1; __VA_ARGS__)                                            \
-    R_H(RU_H0 + 2 * (H) + 1, Pt<P> a_ = r1; R_H0PREFIX __VA_ARGS__)
+    R_H(RU_H0 + 2 * (H) + 0, const Pt<P> &a_ = r0; __VA_ARGS__)                                            \
+    R_H(RU_H0 + 2 * (H) + 1, Pt<P> a_ = r0; R_H0PREFIX __VA_ARGS__)
 #define R_U0CASE(U, EXPR) R_H(RU_U0 + (U), SAF_FOR_P { const double x = r0.v[p]; r0.v[p] = (EXPR); })
 #define R_DIV_X(x, _) R_H(RU_DIV + (x), SAF_FOR_P r0.v[p] = __ddiv_rn(r0.v[p], r##x.v[p]);) \
                       R_H(RU_RDIV + (x), SAF_FOR_P r0.v[p] = __ddiv_rn(r##x.v[p], r0.v[p]);)
@@ -152,27 +153,27 @@ __device__ __noinline__ unsigned long long hot_run_r(uint32_t smem32, uint32_t c
         R_FOR_D(R_UN_D, RUN_NEG, -x)
         R_FOR_D(R_UN_D, RUN_CUBE, __dmul_rn(__dmul_rn(x, x), x))
         R_FOR_D(R_UN_D, RUN_POW4, __dmul_rn(__dmul_rn(x, x), __dmul_rn(x, x)))
-        R_FOR_D(R_FRR_D, T_FMA, RF_E0)
-        R_FOR_D(R_FRR_D, T_FMS, RF_E1)
-        R_FOR_D(R_FRR_D, T_FNMA, RF_E2)
-        R_FOR_D(R_FRR_D, T_FNMS, RF_E3)
-        R_FOR_D(R_FKA_D, T_FMA, RF_E0)
-        R_FOR_D(R_FKA_D, T_FMS, RF_E1)
-        R_FOR_D(R_FKA_D, T_FNMA, RF_E2)
-        R_FOR_D(R_FKA_D, T_FNMS, RF_E3)
-        R_FOR_D(R_FKM_D, T_FMA, RF_E0)
-        R_FOR_D(R_FKM_D, T_FMS, RF_E1)
-        R_FOR_D(R_FKM_D, T_FNMA, RF_E2)
-        R_FOR_D(R_FKM_D, T_FNMS, RF_E3)
+        R_FRR_S(T_FMA, RF_E0)
+        R_FRR_S(T_FMS, RF_E1)
+        R_FRR_S(T_FNMA, RF_E2)
+        R_FRR_S(T_FNMS, RF_E3)
+        R_FKA_S(T_FMA, RF_E0)
+        R_FKA_S(T_FMS, RF_E1)
+        R_FKA_S(T_FNMA, RF_E2)
+        R_FKA_S(T_FNMS, RF_E3)
+        R_FKM_S(T_FMA, RF_E0)
+        R_FKM_S(T_FMS, RF_E1)
+        R_FKM_S(T_FNMA, RF_E2)
+        R_FKM_S(T_FNMS, RF_E3)
 
-        R_H0CASE(H1_SIN, lm::sin_n<P>(a_.v, r0.v);)
-        R_H0CASE(H1_COS, lm::cos_n<P>(a_.v, r0.v);)
-        R_H0CASE(H1_EXP, lm::exp_n<P>(a_.v, r0.v);)
-        R_H0CASE(H1_LN, SAF_FOR_P r0.v[p] = log(a_.v[p]);)
-        R_H0CASE(H1_EXPSQR, Pt<P> b_; SAF_FOR_P b_.v[p] = __dmul_rn(a_.v[p], a_.v[p]); lm::exp_n<P>(b_.v, r0.v);)
-        R_H0CASE(H1_EXPSQRNEG, Pt<P> b_; SAF_FOR_P b_.v[p] = -__dmul_rn(a_.v[p], a_.v[p]); lm::exp_n<P>(b_.v, r0.v);)
-        R_H0CASE(H1_EXPNEG, Pt<P> b_; SAF_FOR_P b_.v[p] = -a_.v[p]; lm::exp_n<P>(b_.v, r0.v);)
-        R_H0CASE(H1_SINCOS, lm::sincos_n<P>(a_.v, r0.v, r2.v);)
+        R_H0CASE(H1_SIN, lm::sin_n<P>(a_.v, r1.v);)
+        R_H0CASE(H1_COS, lm::cos_n<P>(a_.v, r1.v);)
+        R_H0CASE(H1_EXP, lm::exp_n<P>(a_.v, r1.v);)
+        R_H0CASE(H1_LN, SAF_FOR_P r1.v[p] = log(a_.v[p]);)
+        R_H0CASE(H1_EXPSQR, Pt<P> b_; SAF_FOR_P b_.v[p] = __dmul_rn(a_.v[p], a_.v[p]); lm::exp_n<P>(b_.v, r1.v);)
+        R_H0CASE(H1_EXPSQRNEG, Pt<P> b_; SAF_FOR_P b_.v[p] = -__dmul_rn(a_.v[p], a_.v[p]); lm::exp_n<P>(b_.v, r1.v);)
+        R_H0CASE(H1_EXPNEG, Pt<P> b_; SAF_FOR_P b_.v[p] = -a_.v[p]; lm::exp_n<P>(b_.v, r1.v);)
+        R_H0CASE(H1_SINCOS, lm::sincos_n<P>(a_.v, r1.v, r2.v);)
 
         R_U0CASE(RU0_POW3_2, __dmul_rn(x, __dsqrt_rn(x)))
         R_U0CASE(RU0_INVPOW3_2, __ddiv_rn(1.0, __dmul_rn(x, __dsqrt_rn(x))))

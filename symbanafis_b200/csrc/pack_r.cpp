@@ -8,7 +8,8 @@
 //   * when no register is free the value with the furthest next use is evicted; it is stored to a shared-memory
 //     slot only if no valid copy of it is there already (parameters arrive in slots), and spilled values are read
 //     straight from their slot as the X operand of later operations;
-//   * heavy operations have fixed registers (R0 = f(R1), sincos also R2; division and square root in place on R0);
+//   * heavy operations have fixed registers (R1 = f(R0), sincos also R2; the fused multiply-add family, division
+//     and square root work in place on R0);
 //   * cold micro-ops (pow, powi, the builtins) work slot to slot outside the dispatch loop, whose registers do not
 //     survive: everything live is stored in front of them;
 //   * programs whose results feed back into their parameters (saf_iterate_*) keep the state in registers R7, R6, ...
@@ -265,7 +266,8 @@ int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err
     };
     auto mask_of = [&](const Opnd &o) -> uint32_t { return (o.kind == O_VAL && V[o.id].reg >= 0) ? 1u << V[o.id].reg : 0u; };
     // a free register outside `exclude`; evicts the value with the furthest next use when none is free
-    auto get_free = [&](uint32_t exclude, int32_t j) -> int {
+    auto get_free = [&](uint32_t exclude, int32_t j, int prefer = -1) -> int {
+        if (prefer >= 0 && !((exclude >> prefer) & 1u) && reg_val[prefer] < 0) return prefer;
         for (int r = R_NREG - 1; r >= 0; --r)
             if (!((exclude >> r) & 1u) && reg_val[r] < 0) return r;
         int best = -1;
@@ -317,6 +319,28 @@ int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err
     };
     auto dies = [&](const Opnd &o, int32_t j) { return o.kind == O_VAL && next_use(o.id, j) == INF; };
     auto in_reg = [&](const Opnd &o) { return o.kind == O_VAL && V[o.id].reg >= 0; };
+    // the register the next use of the value defined at j wants it in: R0 for the operand an R0-only operation
+    // overwrites (fused family, division, square root ...) and for the argument of a transcendental
+    auto wanted_reg = [&](int32_t v, int32_t j) -> int {
+        if (v < 0) return -1;
+        const int32_t u = next_use(v, j);
+        if (u == INF || u >= NE) return -1;
+        const DI &n = I[u];
+        auto is = [&](const Opnd &o) { return o.kind == O_VAL && o.id == v; };
+        if (n.op >= D_FIRST_TERNARY && n.op < D_FIRST_TERNARY + D_N_TERNARY) {
+            const bool has_k = n.s[0].kind == O_K || n.s[1].kind == O_K;
+            if (has_k) return (is(n.s[0]) || is(n.s[1])) ? 0 : -1; // R0 = +-(R0 * K) +- X
+            return is(n.s[2]) ? 0 : -1;                             // R0 = +-(Ra * Rb) +- R0
+        }
+        if (n.op == D_DIV) return is(n.s[0]) ? 0 : -1;
+        if (n.op == D_POW3_2 || n.op == D_INVPOW3_2 || n.op == D_INVSQRT || n.op == D_INVSQUARE || n.op == D_INVCUBE ||
+            n.op == D_RECIP || n.op == D_SQRT)
+            return 0;
+        if (n.op == D_SIN || n.op == D_COS || n.op == D_EXP || n.op == D_LN || n.op == D_EXPSQR || n.op == D_EXPSQRNEG ||
+            n.op == D_EXPNEG || n.op == D_SINCOS)
+            return 0;
+        return -1;
+    };
     // spilled value read often from now on and a register is idle: bring it back
     auto promote = [&](const Opnd &o, uint32_t exclude, int32_t j) {
         if (o.kind != O_VAL || V[o.id].reg >= 0 || uses_left(o.id, j - 1) < 3) return;
@@ -327,9 +351,9 @@ int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err
         V[o.id].reg = f;
     };
     // the register an in-place operation on operand o may overwrite: o's own when it dies here, else a copy
-    auto inplace_reg = [&](const Opnd &o, uint32_t exclude, int32_t j) -> int {
+    auto inplace_reg = [&](const Opnd &o, uint32_t exclude, int32_t j, int prefer) -> int {
         if (in_reg(o) && dies(o, j)) return V[o.id].reg;
-        const int d = get_free(exclude | mask_of(o), j);
+        const int d = get_free(exclude | mask_of(o), j, prefer);
         emit_mov(d, loc_of(o));
         return d;
     };
@@ -393,7 +417,7 @@ int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err
                 if (!comm) rop = RB_RSUB;
             } else {
                 promote(B, opmask, j);
-                d = get_free(opmask | mask_of(B), j);
+                d = get_free(opmask | mask_of(B), j, wanted_reg(di.def, j));
                 emit_mov(d, loc_of(A));
                 X = B;
             }
@@ -405,12 +429,12 @@ int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err
             if (in_reg(A) && dies(A, j)) {
                 define(di.def, V[A.id].reg);
             } else {
-                const int d = get_free(opmask, j);
+                const int d = get_free(opmask, j, wanted_reg(di.def, j));
                 emit_mov(d, loc_of(A));
                 define(di.def, d);
             }
         } else if (op == D_NEG || op == D_CUBE || op == D_POW4 || op == D_SQUARE) {
-            const int d = inplace_reg(A, opmask, j);
+            const int d = inplace_reg(A, opmask, j, wanted_reg(di.def, j));
             if (op == D_SQUARE) emit(RU_BIN + (RB_MUL * 8u + (uint32_t)d) * 10u + (uint32_t)d);
             else emit(RU_UN + (op == D_NEG ? RUN_NEG : op == D_CUBE ? RUN_CUBE : RUN_POW4) * 8u + (uint32_t)d);
             define(di.def, d);
@@ -424,22 +448,22 @@ int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err
             define(di.def, 0);
         } else if (op == D_SIN || op == D_COS || op == D_EXP || op == D_LN || op == D_EXPSQR || op == D_EXPSQRNEG ||
                    op == D_EXPNEG || op == D_SINCOS) {
-            // R0 = f(R1) (R2 = cos for sincos); the argument register is only read
+            // R1 = f(R0) (R2 = cos for sincos); the argument register is only read
             const uint32_t fixed = 3u | (op == D_SINCOS ? 4u : 0u);
-            if (!(A.kind == O_VAL && V[A.id].reg == 1)) {
-                vacate(1, opmask | fixed, j);
-                emit_mov(1, loc_of(A));
-                if (in_reg(A) && (V[A.id].reg == 0 || (op == D_SINCOS && V[A.id].reg == 2))) {
-                    reg_val[V[A.id].reg] = -1; // the value now lives in R1
-                    V[A.id].reg = 1;
-                    reg_val[1] = A.id;
+            if (!(A.kind == O_VAL && V[A.id].reg == 0)) {
+                vacate(0, opmask | fixed, j);
+                emit_mov(0, loc_of(A));
+                if (in_reg(A) && (V[A.id].reg == 1 || (op == D_SINCOS && V[A.id].reg == 2))) {
+                    reg_val[V[A.id].reg] = -1; // the value now lives in R0
+                    V[A.id].reg = 0;
+                    reg_val[0] = A.id;
                 }
             }
-            vacate(0, opmask | fixed, j);
+            vacate(1, opmask | fixed, j);
             if (op == D_SINCOS) vacate(2, opmask | fixed, j);
             const uint32_t pre = prefix_off(di);
             emit(RU_H0 + 2u * H_OF[op - D_SIN] + (pre != NO_PREFIX ? 1u : 0u), 0u, pre);
-            define(di.def, 0);
+            define(di.def, 1);
             if (op == D_SINCOS && di.def2 >= 0) define(di.def2, 2);
         } else if (op == D_DIV) {
             if (A.kind == O_VAL && V[A.id].reg == 0 && dies(A, j)) {
@@ -455,30 +479,32 @@ int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err
             }
             define(di.def, 0);
         } else if (op >= D_FIRST_TERNARY && op < D_FIRST_TERNARY + D_N_TERNARY) {
+            // the fused family works on R0: R0 = +-(R0 * K) +- X,  R0 = +-(Ra * K) +- R0,  R0 = +-(Ra * Rb) +- R0
             const uint32_t s = op - D_FIRST_TERNARY; // FMA FMS FNMA FNMS
             Opnd M = A, Kc = B;                       // product = M * Kc with Kc constant, if any
             if (M.kind == O_K && Kc.kind != O_K) std::swap(M, Kc);
+            auto same = [](const Opnd &x, const Opnd &y) { return x.kind == O_VAL && y.kind == O_VAL && x.id == y.id; };
             if (Kc.kind == O_K) {
-                if (in_reg(M) && dies(M, j) && !(C.kind == O_VAL && C.id == M.id)) {
-                    const int d = V[M.id].reg;
-                    const Loc lc = loc_of(C);
-                    emit(RU_FKM + (s * 8u + (uint32_t)d) * 10u + lc.xk, (uint32_t)Kc.id * 8u, lc.off);
-                    define(di.def, d);
-                } else if (in_reg(C) && dies(C, j) && in_reg(M)) {
-                    const int d = V[C.id].reg;
-                    emit(RU_FKA + (s * 8u + (uint32_t)d) * 8u + (uint32_t)V[M.id].reg, (uint32_t)Kc.id * 8u);
-                    define(di.def, d);
+                if (C.kind == O_VAL && V[C.id].reg == 0 && dies(C, j) && in_reg(M)) {
+                    emit(RU_FKA + s * 8u + (uint32_t)V[M.id].reg, (uint32_t)Kc.id * 8u);
                 } else {
-                    const int d = get_free(opmask, j);
-                    emit_mov(d, loc_of(M));
-                    const Loc lc = loc_of(C);
-                    emit(RU_FKM + (s * 8u + (uint32_t)d) * 10u + lc.xk, (uint32_t)Kc.id * 8u, lc.off);
-                    define(di.def, d);
+                    if (same(M, C)) { // x * K +- x: the addend must survive the move of the factor into R0
+                        to_fixed_inplace(M, 0, opmask, j);
+                        // R0 now holds the bits of M; the value itself (if it lives on) sits elsewhere, or it dies
+                        // here: read the addend from R0 itself
+                        emit(RU_FKM + s * 10u + 0u, (uint32_t)Kc.id * 8u, 0u);
+                    } else {
+                        to_fixed_inplace(M, 0, opmask, j);
+                        const Loc lc = loc_of(C);
+                        emit(RU_FKM + s * 10u + lc.xk, (uint32_t)Kc.id * 8u, lc.off);
+                    }
                 }
             } else {
-                uint32_t busy = opmask;
+                to_fixed_inplace(C, 0, opmask, j); // the addend; a factor that shared R0 has moved (or dies here)
+                uint32_t busy = 1u | mask_of(A) | mask_of(B);
                 auto ensure_reg = [&](const Opnd &o) -> int {
                     if (in_reg(o)) return V[o.id].reg;
+                    if (same(o, C)) return 0; // dies here, its bits are in R0
                     const int r = get_free(busy, j);
                     emit_mov(r, loc_of(o));
                     busy |= 1u << r;
@@ -489,18 +515,11 @@ int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err
                     return r;
                 };
                 const int ra = ensure_reg(A);
-                const int rb = (B.kind == O_VAL && A.kind == O_VAL && B.id == A.id) ? ra : ensure_reg(B);
-                busy |= (1u << ra) | (1u << rb);
-                int d;
-                if (in_reg(C) && dies(C, j)) {
-                    d = V[C.id].reg; // also when the addend is one of the factors: a handler reads all operands first
-                } else {
-                    d = get_free(busy | mask_of(C), j);
-                    emit_mov(d, loc_of(C));
-                }
-                emit(RU_FRR + (s * 8u + (uint32_t)d) * R_NPAIR + r_pair((uint32_t)std::min(ra, rb), (uint32_t)std::max(ra, rb)));
-                define(di.def, d);
+                busy |= 1u << ra;
+                const int rb = same(A, B) ? ra : ensure_reg(B);
+                emit(RU_FRR + s * R_NPAIR + r_pair((uint32_t)std::min(ra, rb), (uint32_t)std::max(ra, rb)));
             }
+            define(di.def, 0);
         } else {
             cold = true;
         }

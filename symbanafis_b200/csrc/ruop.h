@@ -25,10 +25,13 @@
 //   RU_ST   + d                         S[a] = Rd
 //   RU_BIN  + (op*8 + d)*10 + xk        Rd = Rd op X       op: ADD MUL SUB RSUB(X - Rd) NEGMUL
 //   RU_UN   + u*8 + d                   Rd = f(Rd)         u: NEG CUBE POW4            (square = MUL d, d)
-//   RU_FRR  + (s*8 + d)*36 + pair(a<=b) Rd = +-(Ra * Rb) +- Rd      s: FMA FMS FNMA FNMS (saf_isa.h)
-//   RU_FKA  + (s*8 + d)*8 + ra          Rd = +-(Ra * K[a]) +- Rd
-//   RU_FKM  + (s*8 + d)*10 + xk         Rd = +-(Rd * K[a]) +- X[b]
-//   RU_H0   + 2*h + prefixed            R0 = f(R1)  (h: uop.h H1_*; sincos also writes R2 = cos);  prefix pair at b
+//   RU_FRR  + s*36 + pair(a<=b)         R0 = +-(Ra * Rb) +- R0      s: FMA FMS FNMA FNMS (saf_isa.h)
+//   RU_FKA  + s*8 + ra                  R0 = +-(Ra * K[a]) +- R0
+//   RU_FKM  + s*10 + xk                 R0 = +-(R0 * K[a]) +- X[b]
+//                                       (the fused family works on R0 only: per-register variants of it made the jump
+//                                       table 9 KB, and its lookups missed the constant cache on every dispatch)
+//   RU_H0   + 2*h + prefixed            R1 = f(R0)  (h: uop.h H1_*; sincos also writes R2 = cos);  prefix pair at b
+//                                       (argument in R0, where the fused family and division leave their results)
 //   RU_U0   + u                         R0 = f(R0)         u: POW3_2 INVPOW3_2 INVSQRT INVSQUARE INVCUBE RECIP SQRT
 //   RU_DIV  + xk                        R0 = R0 / X
 //   RU_RDIV + xk                        R0 = X / R0
@@ -51,10 +54,10 @@ constexpr uint32_t RU_BIN = RU_ST + R_NREG;                       // + (op*8 + d
 constexpr uint32_t RUN_NEG = 0, RUN_CUBE = 1, RUN_POW4 = 2, RUN_COUNT = 3;
 constexpr uint32_t RU_UN = RU_BIN + RB_COUNT * R_NREG * XK_COUNT; // + u*8 + d
 constexpr uint32_t R_NPAIR = R_NREG * (R_NREG + 1) / 2;           // 36 unordered register pairs
-constexpr uint32_t RU_FRR = RU_UN + RUN_COUNT * R_NREG;           // + (s*8 + d)*36 + pair
-constexpr uint32_t RU_FKA = RU_FRR + 4 * R_NREG * R_NPAIR;        // + (s*8 + d)*8 + ra
-constexpr uint32_t RU_FKM = RU_FKA + 4 * R_NREG * R_NREG;         // + (s*8 + d)*10 + xk
-constexpr uint32_t RU_H0 = RU_FKM + 4 * R_NREG * XK_COUNT;        // + 2*h + prefixed
+constexpr uint32_t RU_FRR = RU_UN + RUN_COUNT * R_NREG;           // + s*36 + pair
+constexpr uint32_t RU_FKA = RU_FRR + 4 * R_NPAIR;                 // + s*8 + ra
+constexpr uint32_t RU_FKM = RU_FKA + 4 * R_NREG;                  // + s*10 + xk
+constexpr uint32_t RU_H0 = RU_FKM + 4 * XK_COUNT;                 // + 2*h + prefixed
 constexpr uint32_t RU0_POW3_2 = 0, RU0_INVPOW3_2 = 1, RU0_INVSQRT = 2, RU0_INVSQUARE = 3, RU0_INVCUBE = 4,
                    RU0_RECIP = 5, RU0_SQRT = 6, RU0_COUNT = 7;
 constexpr uint32_t RU_U0 = RU_H0 + 2 * H1_COUNT;                  // + u

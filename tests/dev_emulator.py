@@ -365,9 +365,9 @@ RU_UN = RU_BIN + len(RB_NAMES) * R_NREG * XK_COUNT
 RUN_NAMES = ["neg", "cube", "pow4"]
 R_NPAIR = R_NREG * (R_NREG + 1) // 2
 RU_FRR = RU_UN + len(RUN_NAMES) * R_NREG
-RU_FKA = RU_FRR + 4 * R_NREG * R_NPAIR
-RU_FKM = RU_FKA + 4 * R_NREG * R_NREG
-RU_H0 = RU_FKM + 4 * R_NREG * XK_COUNT
+RU_FKA = RU_FRR + 4 * R_NPAIR  # the fused family works on R0 only
+RU_FKM = RU_FKA + 4 * R_NREG
+RU_H0 = RU_FKM + 4 * XK_COUNT
 RU_U0 = RU_H0 + 2 * N_H1
 RU0_NAMES = ["pow3_2", "invpow3_2", "invsqrt", "invsquare", "invcube", "recip", "sqrt"]
 RU_DIV = RU_U0 + len(RU0_NAMES)
@@ -506,30 +506,27 @@ def run_packed_r_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, it
             u, d = divmod(uop - RU_UN, R_NREG)
             R[d] = ref1(_UNARY_REF[RUN_NAMES[u]], R[d])
         elif uop < RU_FKA:
-            sd, pair = divmod(uop - RU_FRR, R_NPAIR)
-            s_, d = divmod(sd, R_NREG)
+            s_, pair = divmod(uop - RU_FRR, R_NPAIR)
             a, b = R_PAIRS[pair]
-            R[d] = ref3(_TERNARY_REF[T_NAMES[s_]], R[a], R[b], R[d])
+            R[0] = ref3(_TERNARY_REF[T_NAMES[s_]], R[a], R[b], R[0])
         elif uop < RU_FKM:
-            sd, a = divmod(uop - RU_FKA, R_NREG)
-            s_, d = divmod(sd, R_NREG)
-            R[d] = ref3(_TERNARY_REF[T_NAMES[s_]], R[a], K(fa), R[d])
+            s_, a = divmod(uop - RU_FKA, R_NREG)
+            R[0] = ref3(_TERNARY_REF[T_NAMES[s_]], R[a], K(fa), R[0])
         elif uop < RU_H0:
-            sd, xk = divmod(uop - RU_FKM, XK_COUNT)
-            s_, d = divmod(sd, R_NREG)
-            R[d] = ref3(_TERNARY_REF[T_NAMES[s_]], R[d], K(fa), X(xk, fb))
+            s_, xk = divmod(uop - RU_FKM, XK_COUNT)
+            R[0] = ref3(_TERNARY_REF[T_NAMES[s_]], R[0], K(fa), X(xk, fb))
         elif uop < RU_U0:
             h, prefixed = divmod(uop - RU_H0, 2)
-            x = R[1]
+            x = R[0]  # R1 = f(R0), sincos: R1 = sin, R2 = cos
             if prefixed:
                 x = ref3("MulAdd", x, K(fb), K(fb + 8))
             name = H1_NAMES[h]
             if name == "expneg":
-                R[0] = _leaf(("Builtin1", 1, "exp_neg", 0), 1).eval_batch([x], n_points)[0]
+                R[1] = _leaf(("Builtin1", 1, "exp_neg", 0), 1).eval_batch([x], n_points)[0]
             elif name == "sincos":
-                R[0], R[2] = _leaf(("SinCos", 1, 2, 0), 1, 2).eval_batch([x], n_points)
+                R[1], R[2] = _leaf(("SinCos", 1, 2, 0), 1, 2).eval_batch([x], n_points)
             else:
-                R[0] = ref1(_UNARY_REF[name], x)
+                R[1] = ref1(_UNARY_REF[name], x)
         elif uop < RU_DIV:
             R[0] = ref1(_UNARY_REF[RU0_NAMES[uop - RU_U0]], R[0])
         elif uop < RU_RDIV:
