@@ -404,6 +404,16 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
     case U_T + 10 * (T) + T_KAS: SAF_ENTER(U_T + 10 * (T) + T_KAS) { const uint32_t fc = FC; LS(c, fc) const double x = konst(fa); SAF_FOR_P { const double y = acc.v[p], z = c.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_KAS) \
     case U_T + 10 * (T) + T_KAK: SAF_ENTER(U_T + 10 * (T) + T_KAK) { const uint32_t fc = FC; const double x = konst(fa), z = konst(fc); SAF_FOR_P { const double y = acc.v[p]; acc.v[p] = (EXPR); } } SAF_NEXT(U_T + 10 * (T) + T_KAK)
 
+// fused chains (uop.h U_FM / U_FQ): LOADS fetches the operands of the multiply, PROD is the product expression
+#define FI (img32(cur + 20)) /* imm field: slot operand of an ADDS suffix */
+#define FMCASE(V, LOADS, PROD)                                                                             \
+    case U_FM + 3 * (V) + F_MULK: SAF_ENTER(U_FM + 3 * (V) + F_MULK) { const double k_ = konst(FC); LOADS SAF_FOR_P { acc.v[p] = __dmul_rn(k_, (PROD)); } } SAF_NEXT(U_FM + 3 * (V) + F_MULK) \
+    case U_FM + 3 * (V) + F_ADDS: SAF_ENTER(U_FM + 3 * (V) + F_ADDS) { const uint32_t fs = FI; LS(c, fs) LOADS SAF_FOR_P { acc.v[p] = __dadd_rn(c.v[p], (PROD)); } } SAF_NEXT(U_FM + 3 * (V) + F_ADDS) \
+    case U_FM + 3 * (V) + F_MULK_ADDS: SAF_ENTER(U_FM + 3 * (V) + F_MULK_ADDS) { const uint32_t fs = FI; const double k_ = konst(FC); LS(c, fs) LOADS SAF_FOR_P { acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(k_, (PROD))); } } SAF_NEXT(U_FM + 3 * (V) + F_MULK_ADDS)
+#define FQCASE(Q, LOADS, SRC)                                                                              \
+    case U_FQ + 2 * (Q) + F_MULK: SAF_ENTER(U_FQ + 2 * (Q) + F_MULK) { const double k_ = konst(FC); LOADS SAF_FOR_P { const double x = SRC.v[p]; acc.v[p] = __dmul_rn(k_, __dmul_rn(x, x)); } } SAF_NEXT(U_FQ + 2 * (Q) + F_MULK) \
+    case U_FQ + 2 * (Q) + F_ADDS: SAF_ENTER(U_FQ + 2 * (Q) + F_ADDS) { const uint32_t fs = FI; LS(c, fs) LOADS SAF_FOR_P { const double x = SRC.v[p]; acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(x, x)); } } SAF_NEXT(U_FQ + 2 * (Q) + F_ADDS)
+
             SAF_DISPATCH(uop_now)
             switch (uop_now) {
             case U_END: SAF_CASE(U_END) { // a = code offset where the next iteration starts
@@ -473,6 +483,14 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
             BCCASE(BC_NEGMUL, -__dmul_rn(x, y))
             BNCASE(BN_SUB, __dsub_rn(x, y))
             BNCASE(BN_DIV, __ddiv_rn(x, y))
+
+            FMCASE(BC_SS, LS(a, fa) LS(b, fb), __dmul_rn(a.v[p], b.v[p]))
+            FMCASE(BC_SK, LS(a, fa) const double y_ = konst(fb);, __dmul_rn(a.v[p], y_))
+            FMCASE(BC_SA, LS(a, fa), __dmul_rn(a.v[p], acc.v[p]))
+            FMCASE(BC_KA, const double x_ = konst(fa);, __dmul_rn(x_, acc.v[p]))
+            FMCASE(BC_AA, , __dmul_rn(acc.v[p], acc.v[p]))
+            FQCASE(0, LS(a, fa), a)
+            FQCASE(1, , acc)
 
             TCASE(T_FMA, __fma_rn(x, y, z))
             TCASE(T_FMS, __fma_rn(x, y, -z))

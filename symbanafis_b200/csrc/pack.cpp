@@ -253,9 +253,60 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
     return SAF_OK;
     }; // build
 
+    // ---- fused chains (uop.h U_FM / U_FQ): multiply | square, then "K * ACC" and / or "S + ACC" ----
+    static const bool fuse_chains = []() {
+        const char *v = getenv("SAF_FUSE"); // tuning knob: SAF_FUSE=0 keeps one micro-op per device instruction
+        return !(v && v[0] == '0');
+    }();
+    auto fuse = [&](std::vector<UI> &U) {
+        if (!fuse_chains) return;
+        const uint32_t MULKA = U_BC + 5 * BC_MUL + BC_KA, ADDSA = U_BC + 5 * BC_ADD + BC_SA;
+        const uint32_t SQ = U_U1 + 2 * (D_SQUARE - D_FIRST_LIGHT_UNARY);
+        std::vector<UI> F;
+        F.reserve(U.size());
+        for (size_t i = 0; i < U.size();) {
+            const UI &p = U[i];
+            const bool is_mul = p.uop >= U_BC + 5 * BC_MUL && p.uop < U_BC + 5 * BC_MUL + 5;
+            const bool is_sq = p.uop == SQ || p.uop == SQ + 1;
+            if ((is_mul || is_sq) && p.d == NO_DEST && i + 1 < U.size()) {
+                const UI &q = U[i + 1];
+                UI f = p;
+                size_t used = 0;
+                if (q.uop == MULKA) {
+                    if (is_mul && q.d == NO_DEST && i + 2 < U.size() && U[i + 2].uop == ADDSA) {
+                        f.uop = U_FM + 3 * (p.uop - (U_BC + 5 * BC_MUL)) + F_MULK_ADDS;
+                        f.c = q.a;
+                        f.imm = U[i + 2].a;
+                        f.d = U[i + 2].d;
+                        used = 3;
+                    } else {
+                        f.uop = is_mul ? U_FM + 3 * (p.uop - (U_BC + 5 * BC_MUL)) + F_MULK : U_FQ + 2 * (p.uop - SQ) + F_MULK;
+                        f.c = q.a;
+                        f.d = q.d;
+                        used = 2;
+                    }
+                } else if (q.uop == ADDSA) {
+                    f.uop = is_mul ? U_FM + 3 * (p.uop - (U_BC + 5 * BC_MUL)) + F_ADDS : U_FQ + 2 * (p.uop - SQ) + F_ADDS;
+                    f.imm = q.a;
+                    f.d = q.d;
+                    used = 2;
+                }
+                if (used) {
+                    F.push_back(f);
+                    i += used;
+                    continue;
+                }
+            }
+            F.push_back(p);
+            ++i;
+        }
+        U.swap(F);
+    };
+
     std::vector<UI> U;
     int rc = build(U);
     if (rc != SAF_OK) return rc;
+    fuse(U);
 
     // ---- double buffering for iterated maps --------------------------------------------------------------
     // Between two iterations of saf_iterate_* parameter j must receive result j.  Instead of copying slots,
@@ -284,8 +335,11 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
             slot_map[q] = r;
             slot_map[r] = q;
         }
-        rc = build(U);
+        std::vector<UI> B;
+        rc = build(B);
         if (rc != SAF_OK) return rc;
+        fuse(B);
+        U.insert(U.end(), B.begin(), B.end());
     }
 
     // ---- windows: the last slot of every code window is U_NEXTWIN (uop.h) ----

@@ -63,7 +63,14 @@ constexpr uint32_t U_T = U_BN + 8 * BN_COUNT;                 // + 10 * t + vari
 constexpr uint32_t T_FMA = 0, T_FMS = 1, T_FNMA = 2, T_FNMS = 3, T_COUNT = 4;
 constexpr uint32_t T_SSS = 0, T_SSK = 1, T_SSA = 2, T_SKS = 3, T_SKK = 4, T_SKA = 5, T_SAS = 6, T_SAK = 7,
                    T_KAS = 8, T_KAK = 9;
-constexpr uint32_t U_G = U_T + 10 * T_COUNT;                  // generic micro-ops
+// Fused chains (pack.cpp peephole): a multiply or a square whose result is only forwarded through ACC, followed by
+// "ACC = K[c] * ACC" and/or "ACC = S[imm] + ACC" -- the shapes `(x * y) * K`, `x * y + S`, `(x * y) * K + S` of every
+// term of a long sum.  The same correctly rounded operations run in the same order; one dispatch instead of two or
+// three (the dispatch, not the arithmetic, is what a light micro-op costs).  Suffix operands: c = constant, imm = slot.
+constexpr uint32_t U_FM = U_T + 10 * T_COUNT;                 // + 3 * BC variant of the multiply + suffix
+constexpr uint32_t F_MULK = 0, F_ADDS = 1, F_MULK_ADDS = 2;
+constexpr uint32_t U_FQ = U_FM + 3 * 5;                       // + 2 * (square operand is A) + suffix (F_MULK / F_ADDS)
+constexpr uint32_t U_G = U_FQ + 2 * 2;                        // generic micro-ops
 constexpr uint32_t G_POW = 0, G_POWI = 1, G_BUILTIN1 = 2, G_BUILTIN2 = 3, G_BUILTIN3 = 4, G_BUILTIN4 = 5,
                    G_ARG2 = 6, G_FMA = 7, G_FMS = 8, G_FNMA = 9, G_FNMS = 10, G_DIV = 11, G_RECIPEXPM1 = 12, G_COUNT = 13;
 constexpr uint32_t NO_PREFIX = 0xffffffffu; // field b of G_RECIPEXPM1 when there is no affine prefix

@@ -191,7 +191,9 @@ U_H1 = U_U1 + 2 * N_LIGHT_UNARY
 U_BC = U_H1 + 2 * N_H1
 U_BN = U_BC + 5 * 3
 U_T = U_BN + 8 * 2
-U_G = U_T + 10 * 4
+U_FM = U_T + 10 * 4  # fused chains: multiply (5 operand-kind variants) + {mulK, addS, mulK then addS}
+U_FQ = U_FM + 3 * 5  # square {S, A} + {mulK, addS}
+U_G = U_FQ + 2 * 2
 H1_NAMES = ["sin", "cos", "exp", "ln", "expsqr", "expsqrneg", "expneg", "sincos"]
 BC_NAMES = ["add", "mul", "negmul"]
 BC_KINDS = ["SS", "SK", "SA", "KA", "AA"]
@@ -310,10 +312,22 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
                 i, v = divmod(uop - U_BN, 8)
                 kk = BN_KINDS[v]
                 r = ref2(_BINARY_REF[BN_NAMES[i]], by_letter(kk[0], fa), by_letter(kk[1], fb))
-            elif uop < U_G:
+            elif uop < U_FM:
                 t, v = divmod(uop - U_T, 10)
                 kk = T_KINDS[v]
                 r = ref3(_TERNARY_REF[T_NAMES[t]], by_letter(kk[0], fa), by_letter(kk[1], fb), by_letter(kk[2], fc))
+            elif uop < U_G:  # fused chains: the same operations, one dispatch (suffix operands: c = constant, imm = slot)
+                if uop < U_FQ:
+                    v, sfx = divmod(uop - U_FM, 3)
+                    kk = BC_KINDS[v]
+                    r = ref2("Mul", by_letter(kk[0], fa), by_letter(kk[1], fb))
+                else:
+                    q, sfx = divmod(uop - U_FQ, 2)
+                    r = ref1("Square", acc if q else S(fa))
+                if sfx in (0, 2):
+                    r = ref2("Mul", K(fc), r)
+                if sfx in (1, 2):
+                    r = ref2("Add", S(imm), r)
             else:
                 name = G_NAMES[uop - U_G]
                 ka, kb, kc = kinds & 3, (kinds >> 2) & 3, (kinds >> 4) & 3
