@@ -245,16 +245,16 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     if (e != cudaSuccess) return cuda_fail(e, "choose_points_per_thread");
     const PackedProgram *pk = nullptr;
     int rc = SAF_OK;
-    // Register machine (ruop.h): live values in real registers, four points per thread.  It pays for programs made
-    // of plain arithmetic; transcendental-heavy programs keep the shared-memory machine, whose heavy handlers take
-    // their operand from any slot (SAF_MACHINE=r / s forces one of them: tuning knob).
+    // Register machine (ruop.h): live values in real registers, four points per thread.  Opt-in (SAF_MACHINE=r):
+    // measured slower than the shared-memory machine on all five named workloads this round -- two-address code
+    // needs 1.5-1.8x the micro-ops, and a dispatch (indexed constant load + three taken branches) costs more than
+    // the shared-memory operand loads it saves (profiles/r01_h_*).  SAF_MACHINE=s forces the default.
     static const int forced_machine = []() {
         const char *v = getenv("SAF_MACHINE");
         return !v ? 0 : v[0] == 'r' ? 1 : v[0] == 's' ? 2 : 0;
     }();
     bool use_r = false;
-    if (aligned && forced_machine != 2 && dp.consts.size() * 8 + 64 <= K_SMEM_MAX &&
-        (forced_machine == 1 || (dp.n_dev_instructions > 0 && dp.fp64_slots < 2.5 * dp.n_dev_instructions))) {
+    if (aligned && forced_machine == 1 && dp.consts.size() * 8 + 64 <= K_SMEM_MAX) {
         const PackedProgram *rp = nullptr;
         LaunchShape rs;
         if (packed_for(const_cast<saf_program *>(prog), LAYOUT_R, &rp) == SAF_OK && (d.iters == 1 || rp->can_iterate) &&
