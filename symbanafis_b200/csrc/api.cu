@@ -444,7 +444,15 @@ static int eval_host_range(const saf_program *prog, const double *const *cols, c
     const size_t total = end - begin;
     // iterated maps keep their state on chip: one chunk per stream is enough, but chunks must be
     // whole launches, so the same chunking applies.
-    const size_t chunk = std::min(total, kChunkPoints);
+    size_t chunk = std::min(total, kChunkPoints);
+    if (total <= kChunkPoints) {
+        // mid-sized batches: up to four chunks of at least 256 Ki points (enough for four points per thread on every
+        // SM), so that the copies of one chunk overlap the kernel of another -- what a long in-kernel iteration
+        // over one million points would otherwise wait for at both ends
+        size_t c = (total + 3) / 4;
+        c = (c + 1023) & ~(size_t)1023;
+        chunk = std::min(total, std::max<size_t>(c, 256 * 1024));
+    }
     const int n_buf = (int)std::min<size_t>(3, (total + chunk - 1) / chunk);
 
     StreamSet ss;
