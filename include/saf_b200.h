@@ -120,8 +120,10 @@ SAF_API int saf_program_export(const saf_program *prog, uint64_t *code, size_t c
  * a constant whose offset points into the image.  Iterated maps are double buffered when possible
  * (*double_buffered = 1): the image then holds the program twice, the second copy with parameter and result slots
  * swapped, each U_END continuing with the other copy, and after an EVEN number of iterations the results sit at
- * result_off_even.  For the CPU emulator of the test-suite and for tooling.
- * Any pointer may be NULL; n_words always receives the full size. */
+ * result_off_even.  points_per_thread = 104 exports the image of the opt-in REGISTER machine instead (four points per
+ * thread, live values in real registers; layout: symbanafis_b200/csrc/ruop.h; never double buffered -- the image
+ * loops in-kernel by itself when results pair with parameters).  For the CPU emulators of the test-suite and for
+ * tooling.  Any pointer may be NULL; n_words always receives the full size. */
 SAF_API int saf_program_export_packed(const saf_program *prog, int points_per_thread,
                               uint64_t *image, size_t cap_words, size_t *n_words,
                               uint32_t *code_off, uint32_t *n_slots, int32_t *x_off /* [3]: x0, x1, acc */,
