@@ -112,3 +112,23 @@ def test_validator_rejects_malformed_programs():
         assert ei.value.code == 2
         with pytest.raises(Exception):
             OracleProgram(flat, [], [], pc, ws, res)
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_register_machine_random_programs_with_feedback(seed):
+    # pack_r.cpp: register pressure (up to 90 instructions over 8 registers), cold micro-ops with every live register
+    # stored, state registers + parallel move at the end of the body when results pair with parameters
+    rng = np.random.default_rng(seed)
+    n_params = int(rng.integers(1, 7))
+    n_results = n_params if seed % 2 else int(rng.integers(1, 5))
+    prog = random_program(rng, n_params=n_params, n_instr=int(rng.integers(5, 90)), n_results=n_results,
+                          builtins=bool(seed % 3))
+    n = 40
+    cols = [rng.uniform(-2, 2, n) for _ in range(n_params)]
+    pk = _handle(prog).export_packed(R_LAYOUT)
+    o = OracleProgram.from_program(prog)
+    for iters in ((1, 2, 3) if (n_results == n_params and n_results <= 5) else (1,)):
+        ref = o.eval_batch(cols, n) if iters == 1 else o.iterate([c.copy() for c in cols], iters)
+        got = run_packed_r_program(pk, cols, n, iters)
+        for k, (r, g) in enumerate(zip(ref, got)):
+            assert bits_equal(g, r), f"register-machine image, {iters} iterations: result {k} differs"
