@@ -414,6 +414,9 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
     case U_FQ + 2 * (Q) + F_MULK: SAF_ENTER(U_FQ + 2 * (Q) + F_MULK) { const double k_ = konst(FC); LOADS SAF_FOR_P { const double x = SRC.v[p]; acc.v[p] = __dmul_rn(k_, __dmul_rn(x, x)); } } SAF_NEXT(U_FQ + 2 * (Q) + F_MULK) \
     case U_FQ + 2 * (Q) + F_ADDS: SAF_ENTER(U_FQ + 2 * (Q) + F_ADDS) { const uint32_t fs = FI; LS(c, fs) LOADS SAF_FOR_P { const double x = SRC.v[p]; acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(x, x)); } } SAF_NEXT(U_FQ + 2 * (Q) + F_ADDS)
 
+// t = S[a] + K[b], kept in the slot named by the kinds word when that is >= 0, then squared / scaled twice (uop.h U_FS)
+#define FSHEAD const int32_t d1_ = (int32_t)img32(cur + 24); LS(a, fa) { const double y_ = konst(fb); SAF_FOR_P a.v[p] = __dadd_rn(a.v[p], y_); } store_if<P>(my, d1_, a);
+
             SAF_DISPATCH(uop_now)
             switch (uop_now) {
             case U_END: SAF_CASE(U_END) { // a = code offset where the next iteration starts
@@ -491,6 +494,9 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
             FMCASE(BC_AA, , __dmul_rn(acc.v[p], acc.v[p]))
             FQCASE(0, LS(a, fa), a)
             FQCASE(1, , acc)
+            case U_FS + FS_SQ: SAF_ENTER(U_FS + FS_SQ) { FSHEAD SAF_FOR_P acc.v[p] = __dmul_rn(a.v[p], a.v[p]); } SAF_NEXT(U_FS + FS_SQ)
+            case U_FS + FS_SQ_ADDS: SAF_ENTER(U_FS + FS_SQ_ADDS) { const uint32_t fs = FI; FSHEAD LS(c, fs) /* after the store: S[imm] may be the kept slot */ SAF_FOR_P acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(a.v[p], a.v[p])); } SAF_NEXT(U_FS + FS_SQ_ADDS)
+            case U_FS + FS_MULK2: SAF_ENTER(U_FS + FS_MULK2) { const double k1_ = konst(FC), k2_ = konst(FI); FSHEAD SAF_FOR_P acc.v[p] = __dmul_rn(k2_, __dmul_rn(k1_, a.v[p])); } SAF_NEXT(U_FS + FS_MULK2)
 
             TCASE(T_FMA, __fma_rn(x, y, z))
             TCASE(T_FMS, __fma_rn(x, y, -z))

@@ -268,6 +268,36 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
             const UI &p = U[i];
             const bool is_mul = p.uop >= U_BC + 5 * BC_MUL && p.uop < U_BC + 5 * BC_MUL + 5;
             const bool is_sq = p.uop == SQ || p.uop == SQ + 1;
+            // t = S + K (kept or not), then t * t [+ S] or K * (K * t)
+            if (p.uop == U_BC + 5 * BC_ADD + BC_SK && i + 1 < U.size()) {
+                const UI &q = U[i + 1];
+                UI f = p;
+                f.kinds = (uint32_t)p.d; // where t itself is kept
+                size_t used = 0;
+                if (q.uop == SQ + 1) {
+                    if (q.d == NO_DEST && i + 2 < U.size() && U[i + 2].uop == ADDSA) {
+                        f.uop = U_FS + FS_SQ_ADDS;
+                        f.imm = U[i + 2].a;
+                        f.d = U[i + 2].d;
+                        used = 3;
+                    } else {
+                        f.uop = U_FS + FS_SQ;
+                        f.d = q.d;
+                        used = 2;
+                    }
+                } else if (q.uop == MULKA && q.d == NO_DEST && i + 2 < U.size() && U[i + 2].uop == MULKA) {
+                    f.uop = U_FS + FS_MULK2;
+                    f.c = q.a;
+                    f.imm = U[i + 2].a;
+                    f.d = U[i + 2].d;
+                    used = 3;
+                }
+                if (used) {
+                    F.push_back(f);
+                    i += used;
+                    continue;
+                }
+            }
             if ((is_mul || is_sq) && p.d == NO_DEST && i + 1 < U.size()) {
                 const UI &q = U[i + 1];
                 UI f = p;

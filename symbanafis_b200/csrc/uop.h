@@ -70,7 +70,12 @@ constexpr uint32_t T_SSS = 0, T_SSK = 1, T_SSA = 2, T_SKS = 3, T_SKK = 4, T_SKA 
 constexpr uint32_t U_FM = U_T + 10 * T_COUNT;                 // + 3 * BC variant of the multiply + suffix
 constexpr uint32_t F_MULK = 0, F_ADDS = 1, F_MULK_ADDS = 2;
 constexpr uint32_t U_FQ = U_FM + 3 * 5;                       // + 2 * (square operand is A) + suffix (F_MULK / F_ADDS)
-constexpr uint32_t U_G = U_FQ + 2 * 2;                        // generic micro-ops
+// "t = S[a] + K[b]" whose result is also kept (slot offset in the `kinds` word, < 0 = not kept), followed by its square
+// (optionally + S[imm]) or by two constant multiplies K[imm] * (K[c] * t): the (x - c)^2 and -2 (x - c) / w of a Gaussian
+// term and of its gradient
+constexpr uint32_t U_FS = U_FQ + 2 * 2;
+constexpr uint32_t FS_SQ = 0, FS_SQ_ADDS = 1, FS_MULK2 = 2, FS_COUNT = 3;
+constexpr uint32_t U_G = U_FS + FS_COUNT;                     // generic micro-ops
 constexpr uint32_t G_POW = 0, G_POWI = 1, G_BUILTIN1 = 2, G_BUILTIN2 = 3, G_BUILTIN3 = 4, G_BUILTIN4 = 5,
                    G_ARG2 = 6, G_FMA = 7, G_FMS = 8, G_FNMA = 9, G_FNMS = 10, G_DIV = 11, G_RECIPEXPM1 = 12, G_COUNT = 13;
 constexpr uint32_t NO_PREFIX = 0xffffffffu; // field b of G_RECIPEXPM1 when there is no affine prefix

@@ -193,7 +193,8 @@ U_BN = U_BC + 5 * 3
 U_T = U_BN + 8 * 2
 U_FM = U_T + 10 * 4  # fused chains: multiply (5 operand-kind variants) + {mulK, addS, mulK then addS}
 U_FQ = U_FM + 3 * 5  # square {S, A} + {mulK, addS}
-U_G = U_FQ + 2 * 2
+U_FS = U_FQ + 2 * 2  # t = S + K (kept in the slot of the kinds word when >= 0), then t*t [+ S] or K * (K * t)
+U_G = U_FS + 3
 H1_NAMES = ["sin", "cos", "exp", "ln", "expsqr", "expsqrneg", "expneg", "sincos"]
 BC_NAMES = ["add", "mul", "negmul"]
 BC_KINDS = ["SS", "SK", "SA", "KA", "AA"]
@@ -317,7 +318,19 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
                 kk = T_KINDS[v]
                 r = ref3(_TERNARY_REF[T_NAMES[t]], by_letter(kk[0], fa), by_letter(kk[1], fb), by_letter(kk[2], fc))
             elif uop < U_G:  # fused chains: the same operations, one dispatch (suffix operands: c = constant, imm = slot)
-                if uop < U_FQ:
+                if uop >= U_FS:
+                    t_ = ref2("Add", S(fa), K(fb))
+                    if i32(kinds) >= 0:
+                        store(i32(kinds), t_)
+                    which = uop - U_FS
+                    if which == 2:
+                        r = ref2("Mul", K(imm), ref2("Mul", K(fc), t_))
+                    else:
+                        r = ref1("Square", t_)
+                        if which == 1:
+                            r = ref2("Add", S(imm), r)
+                    sfx = -1
+                elif uop < U_FQ:
                     v, sfx = divmod(uop - U_FM, 3)
                     kk = BC_KINDS[v]
                     r = ref2("Mul", by_letter(kk[0], fa), by_letter(kk[1], fb))
