@@ -417,6 +417,14 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
 // t = S[a] + K[b], kept in the slot named by the kinds word when that is >= 0, then squared / scaled twice (uop.h U_FS)
 #define FSHEAD const int32_t d1_ = (int32_t)img32(cur + 24); LS(a, fa) { const double y_ = konst(fb); SAF_FOR_P a.v[p] = __dadd_rn(a.v[p], y_); } store_if<P>(my, d1_, a);
 
+// sin / cos + "S[imm] + ACC" / "fma(S[imm], K[c], ACC)" (uop.h U_FT; P == 4 only, other layouts never receive them)
+#define FTBODY(TRIG, PRE, TAIL) if constexpr (P == 4) { const uint32_t fs = FI; LS(a, fa) LS(c, fs) PRE Pt<P> t_; TRIG(a.v, t_.v); TAIL }
+#define FTCASE(T, TRIG)                                                                                    \
+    case U_FT + 4 * (T) + 0: SAF_ENTER(U_FT + 4 * (T) + 0) { FTBODY(TRIG, , SAF_FOR_P acc.v[p] = __dadd_rn(c.v[p], t_.v[p]);) } SAF_NEXT(U_FT + 4 * (T) + 0) \
+    case U_FT + 4 * (T) + 1: SAF_ENTER(U_FT + 4 * (T) + 1) { FTBODY(TRIG, H1PREFIX, SAF_FOR_P acc.v[p] = __dadd_rn(c.v[p], t_.v[p]);) } SAF_NEXT(U_FT + 4 * (T) + 1) \
+    case U_FT + 4 * (T) + 2: SAF_ENTER(U_FT + 4 * (T) + 2) { FTBODY(TRIG, , const double k_ = konst(FC); SAF_FOR_P acc.v[p] = __fma_rn(c.v[p], k_, t_.v[p]);) } SAF_NEXT(U_FT + 4 * (T) + 2) \
+    case U_FT + 4 * (T) + 3: SAF_ENTER(U_FT + 4 * (T) + 3) { FTBODY(TRIG, H1PREFIX, const double k_ = konst(FC); SAF_FOR_P acc.v[p] = __fma_rn(c.v[p], k_, t_.v[p]);) } SAF_NEXT(U_FT + 4 * (T) + 3)
+
             SAF_DISPATCH(uop_now)
             switch (uop_now) {
             case U_END: SAF_CASE(U_END) { // a = code offset where the next iteration starts
@@ -494,6 +502,8 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
             FMCASE(BC_AA, , __dmul_rn(acc.v[p], acc.v[p]))
             FQCASE(0, LS(a, fa), a)
             FQCASE(1, , acc)
+            FTCASE(0, lm::sin_n<P>)
+            FTCASE(1, lm::cos_n<P>)
             case U_FS + FS_SQ: SAF_ENTER(U_FS + FS_SQ) { FSHEAD SAF_FOR_P acc.v[p] = __dmul_rn(a.v[p], a.v[p]); } SAF_NEXT(U_FS + FS_SQ)
             case U_FS + FS_SQ_ADDS: SAF_ENTER(U_FS + FS_SQ_ADDS) { const uint32_t fs = FI; FSHEAD LS(c, fs) /* after the store: S[imm] may be the kept slot */ SAF_FOR_P acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(a.v[p], a.v[p])); } SAF_NEXT(U_FS + FS_SQ_ADDS)
             case U_FS + FS_MULK2: SAF_ENTER(U_FS + FS_MULK2) { const double k1_ = konst(FC), k2_ = konst(FI); FSHEAD SAF_FOR_P acc.v[p] = __dmul_rn(k2_, __dmul_rn(k1_, a.v[p])); } SAF_NEXT(U_FS + FS_MULK2)

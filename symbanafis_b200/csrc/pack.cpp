@@ -268,6 +268,22 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
             const UI &p = U[i];
             const bool is_mul = p.uop >= U_BC + 5 * BC_MUL && p.uop < U_BC + 5 * BC_MUL + 5;
             const bool is_sq = p.uop == SQ || p.uop == SQ + 1;
+            // sin / cos then S + ACC or fma(S, K, ACC): four-points-per-thread layout only (uop.h U_FT)
+            if (P == 4 && p.d == NO_DEST && i + 1 < U.size() && p.uop >= U_H1 + 2 * H1_SIN && p.uop < U_H1 + 2 * H1_COS + 2) {
+                const UI &q = U[i + 1];
+                const uint32_t trig = (p.uop - U_H1) / 2 == H1_SIN ? 0u : 1u, prefixed = (p.uop - U_H1) & 1u;
+                const uint32_t FMASKA = U_T + 10 * T_FMA + T_SKA;
+                if (q.uop == ADDSA || q.uop == FMASKA) {
+                    UI f = p;
+                    f.uop = U_FT + 4 * trig + 2 * (q.uop == FMASKA ? FT_FMA : FT_ADDS) + prefixed;
+                    f.imm = q.a;
+                    if (q.uop == FMASKA) f.c = q.b;
+                    f.d = q.d;
+                    F.push_back(f);
+                    i += 2;
+                    continue;
+                }
+            }
             // t = S + K (kept or not), then t * t [+ S] or K * (K * t)
             if (p.uop == U_BC + 5 * BC_ADD + BC_SK && i + 1 < U.size()) {
                 const UI &q = U[i + 1];

@@ -75,7 +75,13 @@ constexpr uint32_t U_FQ = U_FM + 3 * 5;                       // + 2 * (square o
 // term and of its gradient
 constexpr uint32_t U_FS = U_FQ + 2 * 2;
 constexpr uint32_t FS_SQ = 0, FS_SQ_ADDS = 1, FS_MULK2 = 2, FS_COUNT = 3;
-constexpr uint32_t U_G = U_FS + FS_COUNT;                     // generic micro-ops
+// sin / cos (plain or with affine prefix) followed by "ACC = S[imm] + ACC" or "ACC = fma(S[imm], K[c], ACC)": the two
+// output expressions of a map step such as Clifford's `sin(a y) + c cos(a x)`.  Four-points-per-thread layout only
+// (its single dispatch does not replicate handler code; the threaded layouts lost more to the extra heavy handlers
+// than they saved in dispatches).
+constexpr uint32_t U_FT = U_FS + FS_COUNT;                    // + 4 * {sin, cos} + 2 * {adds, fma} + prefixed
+constexpr uint32_t FT_ADDS = 0, FT_FMA = 1, FT_COUNT = 8;
+constexpr uint32_t U_G = U_FT + FT_COUNT;                     // generic micro-ops
 constexpr uint32_t G_POW = 0, G_POWI = 1, G_BUILTIN1 = 2, G_BUILTIN2 = 3, G_BUILTIN3 = 4, G_BUILTIN4 = 5,
                    G_ARG2 = 6, G_FMA = 7, G_FMS = 8, G_FNMA = 9, G_FNMS = 10, G_DIV = 11, G_RECIPEXPM1 = 12, G_COUNT = 13;
 constexpr uint32_t NO_PREFIX = 0xffffffffu; // field b of G_RECIPEXPM1 when there is no affine prefix

@@ -194,7 +194,8 @@ U_T = U_BN + 8 * 2
 U_FM = U_T + 10 * 4  # fused chains: multiply (5 operand-kind variants) + {mulK, addS, mulK then addS}
 U_FQ = U_FM + 3 * 5  # square {S, A} + {mulK, addS}
 U_FS = U_FQ + 2 * 2  # t = S + K (kept in the slot of the kinds word when >= 0), then t*t [+ S] or K * (K * t)
-U_G = U_FS + 3
+U_FT = U_FS + 3  # {sin, cos} x {S[imm] + ACC, fma(S[imm], K[c], ACC)} x {plain, affine prefix}
+U_G = U_FT + 8
 H1_NAMES = ["sin", "cos", "exp", "ln", "expsqr", "expsqrneg", "expneg", "sincos"]
 BC_NAMES = ["add", "mul", "negmul"]
 BC_KINDS = ["SS", "SK", "SA", "KA", "AA"]
@@ -318,7 +319,16 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
                 kk = T_KINDS[v]
                 r = ref3(_TERNARY_REF[T_NAMES[t]], by_letter(kk[0], fa), by_letter(kk[1], fb), by_letter(kk[2], fc))
             elif uop < U_G:  # fused chains: the same operations, one dispatch (suffix operands: c = constant, imm = slot)
-                if uop >= U_FS:
+                if uop >= U_FT:
+                    trig, rest = divmod(uop - U_FT, 4)
+                    tail, prefixed = divmod(rest, 2)
+                    x = S(fa)
+                    if prefixed:
+                        x = ref3("MulAdd", x, K(fb), K(fb + 8))
+                    t_ = ref1("Sin" if trig == 0 else "Cos", x)
+                    r = ref2("Add", S(imm), t_) if tail == 0 else ref3("MulAdd", S(imm), K(fc), t_)
+                    sfx = -1
+                elif uop >= U_FS:
                     t_ = ref2("Add", S(fa), K(fb))
                     if i32(kinds) >= 0:
                         store(i32(kinds), t_)
