@@ -55,6 +55,8 @@ struct saf_program {
     PackedProgram packed[5];          // [4] = register machine (ruop.h)
     bool packed_ready[5] = {false, false, false, false, false};
     int r_pack_rc = 0;                // result of the register-machine packing (kept: failures are not retried)
+    PackedProgram packed_wide;        // wide one-block-per-SM layout (P = 2), packed for packed_wide_threads
+    int packed_wide_threads = 0;
     std::map<std::pair<int, int>, unsigned char *> copies; // (device, P) -> global-memory image for big programs
 };
 
@@ -267,6 +269,32 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     }
     if (!use_r) rc = packed_for(const_cast<saf_program *>(prog), P, &pk);
     if (rc != SAF_OK) return rc;
+    // Programs with many live values fit two 128-thread blocks per SM at most (shared-memory register file): one
+    // wide block holds more warps in the same shared memory (SAF_WIDE=0 disables: tuning knob).
+    int block_threads = BLOCK_THREADS;
+    static const bool wide_ok = []() {
+        const char *v = getenv("SAF_WIDE");
+        return !(v && v[0] == '0');
+    }();
+    if (!use_r && P == 2 && wide_ok) {
+        const int t = wide_block_threads(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points);
+        if (t > 0) {
+            saf_program *mp = const_cast<saf_program *>(prog);
+            std::lock_guard<std::mutex> lk(mp->mu);
+            if (mp->packed_wide_threads != t) {
+                std::string err;
+                PackedProgram w;
+                if (pack_program(mp->dev, 2, w, err, t) == SAF_OK) {
+                    mp->packed_wide = std::move(w);
+                    mp->packed_wide_threads = t;
+                }
+            }
+            if (mp->packed_wide_threads == t) {
+                pk = &mp->packed_wide;
+                block_threads = t;
+            }
+        }
+    }
     d.code_off = pk->code_off;
     d.n_slots = pk->n_slots;
     d.acc_off = pk->acc_off;
@@ -283,7 +311,7 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     if (rc != SAF_OK) return rc;
     d.code_bytes = pk->code_bytes;
     LaunchShape shape;
-    e = choose_shape(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points, P, use_r, &shape);
+    e = choose_shape(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points, P, use_r, &shape, block_threads);
     if (e == cudaErrorInvalidConfiguration)
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_shape");

@@ -276,7 +276,7 @@ __device__ __forceinline__ void stage_window(uint32_t win_sm, const unsigned cha
     const uint32_t bytes = min(CODE_WINDOW_BYTES, code_bytes - win_g);
     const uint4 *src = reinterpret_cast<const uint4 *>(code_g + win_g);
     __syncthreads(); // everybody is done with the previous window
-    for (uint32_t i = threadIdx.x; i < bytes / 16u; i += BLOCK_THREADS) {
+    for (uint32_t i = threadIdx.x; i < bytes / 16u; i += blockDim.x) {
         const uint4 v = __ldg(src + i);
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(win_sm + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
@@ -529,14 +529,19 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
 
 // ---- the kernel ------------------------------------------------------------------------------------------
 // RM: the register machine (ruop.h, kernel_r.cuh) runs the program; its image is packed by pack_r.cpp
-template <int P, bool K_SMEM, bool RM = false>
+// WIDE (P <= 2 only): one block of blockDim.x > BLOCK_THREADS threads per SM -- programs with many live values fit
+// two 128-thread blocks per SM at most, and one wide block holds more warps in the same shared memory (the code
+// window and the constant table exist once)
+template <int P, bool K_SMEM, bool RM = false, bool WIDE = false>
 __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
+    static_assert(!WIDE || P <= 2, "the pair stride of the wider layouts is a compile-time constant");
+    const uint32_t block_threads = WIDE ? blockDim.x : (uint32_t)BLOCK_THREADS;
     using RF = Rf<P>;
     const uint32_t smem32 = smem_base32();
     const uint32_t my = RF::mine(smem32);
 
     // ---- behind the register file: block context, constant table (K_SMEM), code window ----
-    const uint32_t ctx_off = d.n_slots * (uint32_t)(BLOCK_THREADS * P * 8);
+    const uint32_t ctx_off = d.n_slots * (block_threads * (uint32_t)(P * 8));
     const uint32_t k_s = ctx_off + (uint32_t)sizeof(BlockCtx);
     const uint32_t win_s = k_s + (K_SMEM ? d.code_off : 0u);
     {
@@ -553,14 +558,14 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
         if constexpr (K_SMEM) {
             const uint4 *src = reinterpret_cast<const uint4 *>(d.image_global);
             uint4 *dst = reinterpret_cast<uint4 *>(saf_smem + k_s);
-            for (uint32_t i = threadIdx.x; i < d.code_off / 16u; i += BLOCK_THREADS) dst[i] = __ldg(src + i);
+            for (uint32_t i = threadIdx.x; i < d.code_off / 16u; i += block_threads) dst[i] = __ldg(src + i);
         }
         stage_window(smem32 + win_s, d.image_global + d.code_off, 0u, d.code_bytes); // barriers inside
     }
     const bool multi_window = d.code_bytes > CODE_WINDOW_BYTES;
     const uint32_t iters = (uint32_t)d.iters;
 
-    constexpr unsigned long long TILE = (unsigned long long)BLOCK_THREADS * P;
+    const unsigned long long TILE = (unsigned long long)block_threads * P;
     const unsigned long long n_tiles = (d.n_points + TILE - 1) / TILE;
 
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -651,10 +656,16 @@ SAF_ENTRY(saf_interp_p4_ksm, 4, true, SAF_MINB_P4)
         interp_body<R_POINTS, SM, true>(d);                                                                \
     }
 SAF_ENTRY_R(saf_rinterp_ksm, true, SAF_MINB_R)
+#define SAF_ENTRY_W(NAME, SM)                                                                              \
+    extern "C" __global__ void __launch_bounds__(WIDE_MAX_THREADS, 1) NAME(const __grid_constant__ LaunchDesc d) { \
+        interp_body<2, SM, false, true>(d);                                                                \
+    }
 #ifndef SAF_FAST_BUILD
 SAF_ENTRY(saf_interp_p4_kgm, 4, false, SAF_MINB_P4)
 SAF_ENTRY(saf_interp_p2_ksm, 2, true, SAF_MINB_P2)
 SAF_ENTRY(saf_interp_p2_kgm, 2, false, SAF_MINB_P2)
+SAF_ENTRY_W(saf_interp_p2w_ksm, true)
+SAF_ENTRY_W(saf_interp_p2w_kgm, false)
 SAF_ENTRY(saf_interp_p1_ksm, 1, true, SAF_MINB_P1)
 SAF_ENTRY(saf_interp_p1_kgm, 1, false, SAF_MINB_P1)
 SAF_ENTRY(saf_interp_p8_ksm, 8, true, SAF_MINB_P8)

@@ -55,7 +55,7 @@ constexpr size_t K_SMEM_MAX = 24 * 1024;
 
 struct LaunchShape {
     int points_per_thread; // 1, 2, 4 or 8
-    int block;             // threads per block (always BLOCK_THREADS)
+    int block;             // threads per block: BLOCK_THREADS, or more for the wide one-block-per-SM layout (P = 2)
     int grid;
     size_t smem_bytes;
     bool k_in_smem;        // the constant table is staged in shared memory (else read from global memory)
@@ -71,9 +71,13 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
                                      int force_points_per_thread, int *points_per_thread);
 // Grid / shared memory / constant-table placement for the packed program.
 cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
-                         int points_per_thread, bool rmachine, LaunchShape *shape);
+                         int points_per_thread, bool rmachine, LaunchShape *shape, int block_threads = BLOCK_THREADS);
 // register file + block context + constant table (when staged) + code window
-size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes);
+size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes,
+                              int block_threads = BLOCK_THREADS);
+// Threads of the wide one-block-per-SM layout (two points per thread) for a packed program with n_slots slots, or 0
+// when it would not hold more warps per SM than 128-thread blocks do.
+int wide_block_threads(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points);
 
 // Per-block context behind the register file in shared memory: what hot_run needs besides the image.
 struct alignas(16) BlockCtx { // a multiple of 16 bytes: the constant table and the code window follow it

@@ -40,7 +40,7 @@ struct Driver {
 
 struct DeviceModule {
     CUmodule mod = nullptr;
-    CUfunction interp[9] = {}; // [8] = register machine
+    CUfunction interp[11] = {}; // [8] = register machine, [9] [10] = wide blocks (P = 2)
     CUfunction peak = nullptr;
     CUfunction clifford_probe = nullptr;
     bool ready = false;
@@ -88,13 +88,13 @@ cudaError_t module_for_current_device(DeviceModule **out) {
         }
         CUresult r = g_drv.module_load_data(&m.mod, saf_kernel_cubin);
         if (r != CUDA_SUCCESS) return as_cuda(r);
-        static const char *names[9] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
+        static const char *names[11] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
                                        "saf_interp_p1_ksm", "saf_interp_p1_kgm", "saf_interp_p8_ksm", "saf_interp_p8_kgm",
-                                       "saf_rinterp_ksm"};
+                                       "saf_rinterp_ksm", "saf_interp_p2w_ksm", "saf_interp_p2w_kgm"};
         int optin = 0;
         e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e != cudaSuccess) return e;
-        for (int k = 0; k < 9; ++k) {
+        for (int k = 0; k < 11; ++k) {
             r = g_drv.module_get_function(&m.interp[k], m.mod, names[k]);
             if (r != CUDA_SUCCESS) return as_cuda(r);
             // opt in to the full dynamic shared-memory carve-out
@@ -116,7 +116,9 @@ cudaError_t module_for_current_device(DeviceModule **out) {
 
 cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream) {
     const int li = shape.points_per_thread == 4 ? 0 : shape.points_per_thread == 2 ? 1 : shape.points_per_thread == 1 ? 2 : 3;
-    const int k = shape.rmachine ? 8 : 2 * li + (shape.k_in_smem ? 0 : 1);
+    const bool wide = shape.block != BLOCK_THREADS;
+    if (wide && (shape.points_per_thread != 2 || shape.rmachine)) return cudaErrorInvalidConfiguration;
+    const int k = shape.rmachine ? 8 : wide ? (shape.k_in_smem ? 9 : 10) : 2 * li + (shape.k_in_smem ? 0 : 1);
     if (shape.rmachine && !shape.k_in_smem) return cudaErrorInvalidConfiguration;
     DeviceModule *m = nullptr;
     cudaError_t e = module_for_current_device(&m);
@@ -147,9 +149,10 @@ cudaError_t launch_clifford_probe(double *xs, double *ys, unsigned long long n, 
 }
 
 // register file + block context + constant table (when staged) + code window
-size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes) {
+size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes,
+                              int block_threads) {
     const size_t window = code_bytes < CODE_WINDOW_BYTES ? code_bytes : CODE_WINDOW_BYTES;
-    return (size_t)n_slots * (size_t)BLOCK_THREADS * (size_t)points_per_thread * 8 + sizeof(BlockCtx) +
+    return (size_t)n_slots * (size_t)block_threads * (size_t)points_per_thread * 8 + sizeof(BlockCtx) +
            ((k_bytes_in_smem + 15) & ~(size_t)15) + ((window + 15) & ~(size_t)15);
 }
 
@@ -184,31 +187,53 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
     return cudaSuccess;
 }
 
+int wide_block_threads(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points) {
+    int sms = 0, smem_optin = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
+    const size_t k_smem = k_bytes <= K_SMEM_MAX ? k_bytes : 0;
+    // warps per SM with 128-thread blocks
+    const size_t small = interpreter_smem_bytes(n_slots, 2, k_smem, code_bytes);
+    size_t blocks = ((size_t)smem_optin + 1024) / (small + 1024);
+    if (blocks > (size_t)SAF_MINB_P2) blocks = SAF_MINB_P2;
+    const int warps_small = (int)blocks * (BLOCK_THREADS / 32);
+    int threads = 0;
+    for (int t = WIDE_MAX_THREADS; t > BLOCK_THREADS; t -= 32)
+        if (interpreter_smem_bytes(n_slots, 2, k_smem, code_bytes, t) <= (size_t)smem_optin) {
+            threads = t;
+            break;
+        }
+    if (threads / 32 <= warps_small) return 0;
+    // every SM must still get whole tiles to work on
+    if (n_points < (unsigned long long)sms * 2ull * (unsigned long long)threads * 2ull) return 0;
+    return threads;
+}
+
 cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
-                         int P, bool rmachine, LaunchShape *shape) {
+                         int P, bool rmachine, LaunchShape *shape, int block_threads) {
     int sms = 0, smem_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
     bool k_in_smem = k_bytes <= K_SMEM_MAX;
-    size_t smem = interpreter_smem_bytes(n_slots, P, k_in_smem ? k_bytes : 0, code_bytes);
+    size_t smem = interpreter_smem_bytes(n_slots, P, k_in_smem ? k_bytes : 0, code_bytes, block_threads);
     if (smem > (size_t)smem_optin && k_in_smem) {
         k_in_smem = false;
-        smem = interpreter_smem_bytes(n_slots, P, 0, code_bytes);
+        smem = interpreter_smem_bytes(n_slots, P, 0, code_bytes, block_threads);
     }
     if (smem > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
     size_t resident = rmachine ? (size_t)SAF_MINB_R : (size_t)resident_blocks_for(P); // __launch_bounds__ register budget
     const size_t by_smem = ((size_t)smem_optin + 1024) / (smem + 1024);
     if (by_smem < resident) resident = by_smem;
-    if (resident < 1) resident = 1;
-    const unsigned long long tile = (unsigned long long)BLOCK_THREADS * P;
+    if (resident < 1 || block_threads != BLOCK_THREADS) resident = 1;
+    const unsigned long long tile = (unsigned long long)block_threads * P;
     const unsigned long long n_tiles = (n_points + tile - 1) / tile;
     unsigned long long grid = (unsigned long long)sms * resident;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     shape->points_per_thread = P;
-    shape->block = BLOCK_THREADS;
+    shape->block = block_threads;
     shape->grid = (int)grid;
     shape->smem_bytes = smem;
     shape->k_in_smem = k_in_smem;

@@ -12,6 +12,7 @@ namespace saf {
 
 struct PackedProgram {
     int points_per_thread = 0;
+    int block_threads = BLOCK_THREADS; // threads per block the slot stride was computed for
     int layout_id = 0;                 // points_per_thread for the shared-memory machine, 100 + P for the register machine
     bool can_iterate = true;           // the image loops in-kernel (saf_iterate_*); register-machine images of programs
                                        // whose results do not pair with their parameters cannot
@@ -35,11 +36,15 @@ struct PackedProgram {
 };
 
 // Byte stride of one slot for P points per thread.
-constexpr uint32_t slot_bytes(int points_per_thread) { return (uint32_t)BLOCK_THREADS * 8u * (uint32_t)points_per_thread; }
+constexpr uint32_t slot_bytes(int points_per_thread, int block_threads = BLOCK_THREADS) {
+    return (uint32_t)block_threads * 8u * (uint32_t)points_per_thread;
+}
 
 // Returns 0 or SAF_ERR_UNSUPPORTED (err filled).
 // Register machine (ruop.h, pack_r.cpp): four points per thread, live values in real registers.
 int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err);
-int pack_program(const DeviceProgram &dp, int points_per_thread, PackedProgram &out, std::string &err);
+// block_threads != BLOCK_THREADS: the wide one-block-per-SM layout (points_per_thread <= 2), layout_id = 2000 + threads.
+int pack_program(const DeviceProgram &dp, int points_per_thread, PackedProgram &out, std::string &err,
+                 int block_threads = BLOCK_THREADS);
 
 } // namespace saf

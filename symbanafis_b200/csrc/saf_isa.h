@@ -153,5 +153,7 @@ constexpr int MAX_OUTS = 32;
 // Threads per block of the interpreter kernel: fixed, so that the slot stride is a compile-time
 // constant (one IMAD per shared-memory operand address).
 constexpr int BLOCK_THREADS = 128;
+// Widest block of the one-block-per-SM layout for programs with many live values (kernel.cu: WIDE).
+constexpr int WIDE_MAX_THREADS = 512;
 
 } // namespace saf
