@@ -33,9 +33,40 @@ np.savez(sys.argv[1], **out)
 """
 
 
-def _run_child(machine: str, path: str) -> None:
-    env = dict(os.environ, SAF_MACHINE=machine)
+def _run_child(machine: str, path: str, **extra_env) -> None:
+    env = dict(os.environ, SAF_MACHINE=machine, **extra_env)
     subprocess.run([sys.executable, "-c", _CHILD.format(root=ROOT), path], check=True, env=env, timeout=600)
+
+
+_CHILD_WIDE = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from symbanafis_b200 import workloads
+from symbanafis_b200._lib import DeviceProgramHandle
+w = workloads.get("terrain_gradient"); p = w.program
+h = DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size, p.result_regs)
+n = 600_001  # enough points for the wide one-block-per-SM layout, ragged last tile
+cols = w.make_inputs(n, 8)
+res = [np.empty(n) for _ in p.result_regs]
+h.eval_host(cols, res, n)
+np.savez(sys.argv[1], **{{f"r{{k}}": r for k, r in enumerate(res)}})
+"""
+
+
+@pytest.mark.gpu
+def test_layout_and_fusion_knobs_do_not_change_results(tmp_path):
+    # wide blocks (kernel.cu WIDE), the fused-chain peephole (pack.cpp) and the number of points per thread only
+    # change HOW the same correctly rounded operations are dispatched
+    outs = {}
+    for tag, env in (("default", {}), ("narrow", {"SAF_WIDE": "0"}), ("unfused", {"SAF_FUSE": "0"}),
+                     ("p1", {"SAF_POINTS_PER_THREAD": "1"})):
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", _CHILD_WIDE.format(root=ROOT), path], check=True,
+                       env=dict(os.environ, **env), timeout=900)
+        outs[tag] = np.load(path)
+    for tag in ("narrow", "unfused", "p1"):
+        for k in outs["default"].files:
+            assert np.array_equal(outs["default"][k].view(np.uint64), outs[tag][k].view(np.uint64)), f"{tag}: {k} differs"
 
 
 @pytest.mark.gpu
