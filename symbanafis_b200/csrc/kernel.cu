@@ -1,6 +1,6 @@
 // kernel.cu -- the sm_100a interpreter kernel for SymbAnaFis device programs.
 //
-// One thread evaluates P points (P = 1, 2, 4 or 8), 128 threads per block.  Every lane of every warp runs
+// One thread evaluates P points (P = 1, 2, 4 or 8), 128 threads per block (up to 512 in the wide two-points layout).  Every lane of every warp runs
 // the SAME program on different points, so the program counter, the fetched micro-instruction and the
 // opcode branch are warp-uniform: there is no divergence in the dispatch, only inside the data-dependent
 // slow paths of a few special functions.
@@ -17,9 +17,11 @@
 //   accumulator                 : the result of the previous instruction stays in real registers; the
 //                                 lowering (lower.cpp) routes single-use values through it so they
 //                                 never touch shared memory
-//   dispatch                    : one dense switch (ptxas emits BRX jump tables for it) over micro-ops that
-//                                 are specialised by operand kind (S slot / K constant / A accumulator):
-//                                 handlers contain no operand decoding; P points per thread amortise it
+//   dispatch                    : one jump table (brx.idx, written into the PTX by tools/patch_brx.py) over micro-ops
+//                                 that are specialised by operand kind (S slot / K constant / A accumulator):
+//                                 handlers contain no operand decoding; P points per thread amortise it.  Chains
+//                                 of light operations are fused into single micro-ops by the packer (uop.h U_FM,
+//                                 U_FQ, U_FS, U_FT): a dispatch costs more than the arithmetic it leads to
 //   hot / cold split            : the dispatch loop (hot_run) is a function of its own that contains only
 //                                 the arithmetic micro-ops and the lean transcendentals -- ~70 registers, no
 //                                 spills; pow, powi, the 61 builtins and the rare operand-kind combinations

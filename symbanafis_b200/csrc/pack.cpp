@@ -1,6 +1,7 @@
 // pack.cpp -- device program (indices, run-time kinds) -> micro-instruction image (byte offsets,
 // kind-specialised micro-ops).  Pure re-encoding: the same operations run on the same values in the
-// same order; commutative operands may swap places (IEEE add/mul commute bit for bit).
+// same order; commutative operands may swap places (IEEE add/mul commute bit for bit).  A peephole then fuses
+// chains of micro-ops whose intermediate results only travel through the accumulator (uop.h U_FM .. U_FT).
 #include "pack.h"
 
 #include <algorithm>
