@@ -12,6 +12,9 @@ extern "C" {
                           pool: *const u32, n_pool: usize, param_count: u32, workspace_size: u32,
                           result_regs: *const u32, n_results: u32, out: *mut *mut SafProgram) -> c_int;
     fn saf_program_destroy(p: *mut SafProgram);
+    fn saf_program_intern(flat: *const u32, n_words: usize, consts: *const f64, n_consts: usize,
+                          pool: *const u32, n_pool: usize, param_count: u32, workspace_size: u32,
+                          result_regs: *const u32, n_results: u32, out: *mut *mut SafProgram) -> c_int;
     fn saf_eval_host(p: *const SafProgram, cols: *const *const f64, col_lens: *const usize, n_cols: usize,
                      outs: *const *mut f64, n_points: usize, flags: c_uint) -> c_int;
     fn saf_last_error() -> *const c_char;
@@ -37,6 +40,22 @@ impl B200Program {
         if rc != 0 { return Err(last_error(rc)); }
         Ok(Self(h))
     }
+}
+
+/// `eval_f64` compiles its expressions inside every call (drivers/batch.rs:28-30): there is no long-lived
+/// `CompiledEvaluator` to attach a `B200Program` to.  That path takes its handle from the library's content-addressed
+/// cache instead (`saf_program_intern`: same payload, same handle; owned by the cache, never destroyed here).
+pub fn interned_program(ev: &CompiledEvaluator) -> Result<*const SafProgram, DiffError> {
+    let mut h = std::ptr::null_mut();
+    let rc = unsafe {
+        saf_program_intern(ev.flat_bytecode.as_ptr(), ev.flat_bytecode.len(),
+                           ev.constants.as_ptr(), ev.constants.len(),
+                           ev.arg_pool.as_ptr(), ev.arg_pool.len(),
+                           ev.param_count as u32, ev.workspace_size as u32,
+                           &ev.result_reg, 1, &mut h)
+    };
+    if rc != 0 { return Err(last_error(rc)); }
+    Ok(h as *const SafProgram)
 }
 
 /// Same signature and error behaviour as `run_chunked_evaluator` (batch.rs:37-78).

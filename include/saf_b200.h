@@ -100,6 +100,20 @@ SAF_API int saf_program_fuse(const saf_program *const *programs, size_t n_progra
 
 SAF_API void saf_program_destroy(saf_program *prog);
 
+/* Same arguments as saf_program_create, but the handle comes from a per-process cache keyed by the CONTENT of the
+ * payload: the reference compiles inside every eval_f64 call (drivers/batch.rs:28-30), so a caller that rebuilds its
+ * CompiledEvaluator per call still reuses the lowered program, its packed images and their device copies.  The handle
+ * belongs to the cache: do not pass it to saf_program_destroy; it stays valid until saf_program_cache_clear (which
+ * the caller must not run concurrently with evaluations on interned handles).  Thread-safe.  The cache holds at most
+ * 4096 programs; beyond that the call fails with SAF_ERR_ALLOC. */
+SAF_API int saf_program_intern(const uint32_t *flat_bytecode, size_t n_words,
+                       const double *constants, size_t n_constants,
+                       const uint32_t *arg_pool, size_t n_arg_pool,
+                       uint32_t param_count, uint32_t workspace_size,
+                       const uint32_t *result_regs, uint32_t n_results,
+                       saf_program **out);
+SAF_API void saf_program_cache_clear(void);
+
 SAF_API int saf_program_get_info(const saf_program *prog, saf_program_info *info);
 
 /* Human-readable listing of the lowered device program (cf. CompiledEvaluator::disassemble,

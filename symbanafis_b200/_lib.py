@@ -60,7 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 _lib: Optional[C.CDLL] = None
 
 EXPORTED_SYMBOLS = [
-    "saf_program_create", "saf_program_fuse", "saf_program_destroy", "saf_program_get_info",
+    "saf_program_create", "saf_program_fuse", "saf_program_destroy", "saf_program_intern", "saf_program_cache_clear",
+    "saf_program_get_info",
     "saf_program_disassemble", "saf_program_export", "saf_program_export_packed", "saf_eval_device", "saf_eval_host",
     "saf_eval_host_multi", "saf_iterate_device", "saf_iterate_host", "saf_last_error",
     "saf_device_count", "saf_kernel_launch_count", "saf_version", "saf_measure_fp64_peak",
@@ -81,6 +82,10 @@ def lib() -> C.CDLL:
     PP = C.POINTER(C.c_void_p)
     L.saf_program_create.argtypes = [vp, sz, vp, sz, vp, sz, u32, u32, vp, u32, PP]
     L.saf_program_create.restype = C.c_int
+    L.saf_program_intern.argtypes = [vp, sz, vp, sz, vp, sz, u32, u32, vp, u32, PP]
+    L.saf_program_intern.restype = C.c_int
+    L.saf_program_cache_clear.argtypes = []
+    L.saf_program_cache_clear.restype = None
     L.saf_program_fuse.argtypes = [PP, sz, PP]
     L.saf_program_fuse.restype = C.c_int
     L.saf_program_destroy.argtypes = [vp]

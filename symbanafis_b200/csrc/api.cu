@@ -128,6 +128,79 @@ extern "C" void saf_program_destroy(saf_program *p) {
     delete p;
 }
 
+// ---- content-addressed program cache (saf_program_intern) ------------------------------------------------------
+namespace {
+std::mutex g_intern_mu;
+std::multimap<uint64_t, saf_program *> g_interned;
+constexpr size_t kInternCapacity = 4096;
+
+uint64_t fnv1a(uint64_t h, const void *data, size_t n) {
+    const unsigned char *b = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < n; ++i) {
+        h ^= b[i];
+        h *= 0x100000001b3ull;
+    }
+    return h;
+}
+uint64_t payload_hash(const RefProgram &r) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    const uint64_t sizes[4] = {r.flat.size(), r.consts.size(), r.pool.size(), r.result_regs.size()};
+    h = fnv1a(h, sizes, sizeof sizes);
+    h = fnv1a(h, r.flat.data(), r.flat.size() * 4);
+    h = fnv1a(h, r.consts.data(), r.consts.size() * 8);
+    h = fnv1a(h, r.pool.data(), r.pool.size() * 4);
+    h = fnv1a(h, r.result_regs.data(), r.result_regs.size() * 4);
+    h = fnv1a(h, &r.param_count, 4);
+    return fnv1a(h, &r.workspace_size, 4);
+}
+bool same_payload(const RefProgram &a, const RefProgram &b) {
+    return a.param_count == b.param_count && a.workspace_size == b.workspace_size && a.flat == b.flat && a.pool == b.pool &&
+           a.result_regs == b.result_regs && a.consts.size() == b.consts.size() &&
+           (a.consts.empty() || std::memcmp(a.consts.data(), b.consts.data(), a.consts.size() * 8) == 0); // bitwise: NaN, -0.0
+}
+} // namespace
+
+extern "C" int saf_program_intern(const uint32_t *flat, size_t n_words, const double *consts, size_t n_consts,
+                                  const uint32_t *pool, size_t n_pool, uint32_t param_count,
+                                  uint32_t workspace_size, const uint32_t *result_regs, uint32_t n_results,
+                                  saf_program **out) {
+    if (!out) return fail(SAF_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!flat || n_words == 0) return fail(SAF_ERR_INVALID_ARGUMENT, "empty bytecode");
+    if ((n_consts && !consts) || (n_pool && !pool) || !result_regs || n_results == 0)
+        return fail(SAF_ERR_INVALID_ARGUMENT, "NULL program component");
+    RefProgram r;
+    r.flat.assign(flat, flat + n_words);
+    if (n_consts) r.consts.assign(consts, consts + n_consts);
+    if (n_pool) r.pool.assign(pool, pool + n_pool);
+    r.param_count = param_count;
+    r.workspace_size = workspace_size;
+    r.result_regs.assign(result_regs, result_regs + n_results);
+    const uint64_t h = payload_hash(r);
+    std::lock_guard<std::mutex> lk(g_intern_mu); // lowering under the lock: concurrent callers of one program wait for one lowering
+    for (auto range = g_interned.equal_range(h); range.first != range.second; ++range.first)
+        if (range.first->second->refs.size() == 1 && same_payload(range.first->second->refs[0], r)) {
+            *out = range.first->second;
+            return SAF_OK;
+        }
+    if (g_interned.size() >= kInternCapacity)
+        return fail(SAF_ERR_ALLOC, "program cache is full (4096 programs): call saf_program_cache_clear");
+    std::vector<RefProgram> v;
+    v.push_back(std::move(r));
+    saf_program *p = nullptr;
+    const int rc = build_program(std::move(v), &p);
+    if (rc != SAF_OK) return rc;
+    g_interned.emplace(h, p);
+    *out = p;
+    return SAF_OK;
+}
+
+extern "C" void saf_program_cache_clear(void) {
+    std::lock_guard<std::mutex> lk(g_intern_mu);
+    for (auto &kv : g_interned) saf_program_destroy(kv.second);
+    g_interned.clear();
+}
+
 extern "C" int saf_program_get_info(const saf_program *p, saf_program_info *info) {
     if (!p || !info) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL argument");
     info->param_count = p->dev.param_count;

@@ -79,3 +79,35 @@ def test_evaluation_fails_loudly_without_a_device():
     from symbanafis_b200.evaluator import CompiledEvaluator
     with pytest.raises(Exception):
         CompiledEvaluator("x^2", ["x"]).eval_batch([x])
+
+
+def test_program_cache_is_keyed_by_content():
+    # batch.rs:28-30: the reference compiles per call; saf_program_intern returns the same handle for the same payload
+    import ctypes as C
+    from symbanafis_b200 import workloads
+    L = _lib.lib()
+
+    def intern(p, consts=None):
+        flat = np.ascontiguousarray(p.flat, dtype=np.uint32)
+        k = np.ascontiguousarray(p.consts if consts is None else consts, dtype=np.float64)
+        pool = np.ascontiguousarray(p.arg_pool, dtype=np.uint32)
+        rr = np.ascontiguousarray(p.result_regs, dtype=np.uint32)
+        out = C.c_void_p()
+        rc = L.saf_program_intern(flat.ctypes.data, flat.size, k.ctypes.data if k.size else None, k.size,
+                                  pool.ctypes.data if pool.size else None, pool.size, int(p.param_count),
+                                  int(p.workspace_size), rr.ctypes.data, rr.size, C.byref(out))
+        assert rc == 0, L.saf_last_error()
+        return out.value
+
+    L.saf_program_cache_clear()
+    a, b = workloads.get("aizawa").program, workloads.get("clifford").program
+    h1, h2, h3 = intern(a), intern(a), intern(b)
+    assert h1 == h2 and h1 != h3
+    changed = np.array(a.consts, dtype=np.float64).copy()
+    changed[0] = -changed[0]
+    assert intern(a, changed) not in (h1, h3)  # same bytecode, another constant: another program
+    info = _lib.ProgramInfo()
+    assert L.saf_program_get_info(C.c_void_p(h1), C.byref(info)) == 0 and info.param_count == 3
+    L.saf_program_cache_clear()
+    assert intern(a) is not None
+    L.saf_program_cache_clear()
