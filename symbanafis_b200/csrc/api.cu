@@ -399,12 +399,22 @@ extern "C" int saf_program_export_packed(const saf_program *p, int points_per_th
                                          int32_t *param_off, int32_t *result_off, uint8_t *result_is_k,
                                          int32_t *result_off_even, int *double_buffered) {
     if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
-    if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4 && points_per_thread != 8 &&
-        points_per_thread != LAYOUT_R)
-        return fail(SAF_ERR_INVALID_ARGUMENT, "points_per_thread must be 1, 2, 4, 8 or 104 (register machine)");
     const PackedProgram *pk = nullptr;
-    int rc = packed_for(const_cast<saf_program *>(p), points_per_thread, &pk);
-    if (rc != SAF_OK) return rc;
+    PackedProgram wide; // 2000 + threads: the wide one-block-per-SM layout (two points per thread), packed on the spot
+    int rc;
+    if (points_per_thread > 2000 && points_per_thread <= 2000 + WIDE_MAX_THREADS && points_per_thread % 32 == 2000 % 32) {
+        std::string err;
+        rc = pack_program(p->dev, 2, wide, err, points_per_thread - 2000);
+        if (rc != SAF_OK) return fail(rc, err);
+        pk = &wide;
+    } else {
+        if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4 && points_per_thread != 8 &&
+            points_per_thread != LAYOUT_R)
+            return fail(SAF_ERR_INVALID_ARGUMENT,
+                        "points_per_thread must be 1, 2, 4, 8, 104 (register machine) or 2000 + threads (wide blocks)");
+        rc = packed_for(const_cast<saf_program *>(p), points_per_thread, &pk);
+        if (rc != SAF_OK) return rc;
+    }
     if (n_words) *n_words = pk->image.size();
     if (image) std::memcpy(image, pk->image.data(), std::min(cap_words, pk->image.size()) * 8);
     if (code_off) *code_off = pk->code_off;

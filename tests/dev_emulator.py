@@ -214,7 +214,7 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
     image = np.asarray(pk["image"], dtype=np.uint64)
     kview = image.view(np.float64)
     P = int(pk["points_per_thread"])
-    slot_bytes = 128 * 8 * P
+    slot_bytes = int(pk.get("block_threads", 128)) * 8 * P
     rf_bytes = int(pk["n_slots"]) * slot_bytes
     RF: Dict[int, np.ndarray] = {}
 
