@@ -111,3 +111,33 @@ def test_program_cache_is_keyed_by_content():
     L.saf_program_cache_clear()
     assert intern(a) is not None
     L.saf_program_cache_clear()
+
+
+def test_program_cache_is_thread_safe():
+    import ctypes as C
+    import threading
+    from symbanafis_b200 import workloads
+    L = _lib.lib()
+    L.saf_program_cache_clear()
+    p = workloads.get("double_pendulum").program
+    flat = np.ascontiguousarray(p.flat, dtype=np.uint32)
+    k = np.ascontiguousarray(p.consts, dtype=np.float64)
+    pool = np.ascontiguousarray(p.arg_pool, dtype=np.uint32)
+    rr = np.ascontiguousarray(p.result_regs, dtype=np.uint32)
+    got, errs = [None] * 8, []
+
+    def work(i):
+        out = C.c_void_p()
+        rc = L.saf_program_intern(flat.ctypes.data, flat.size, k.ctypes.data, k.size, pool.ctypes.data if pool.size else None,
+                                  pool.size, int(p.param_count), int(p.workspace_size), rr.ctypes.data, rr.size, C.byref(out))
+        if rc != 0:
+            errs.append(rc)
+        got[i] = out.value
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs and len(set(got)) == 1 and got[0]
+    L.saf_program_cache_clear()
