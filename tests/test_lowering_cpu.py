@@ -132,3 +132,16 @@ def test_register_machine_random_programs_with_feedback(seed):
         got = run_packed_r_program(pk, cols, n, iters)
         for k, (r, g) in enumerate(zip(ref, got)):
             assert bits_equal(g, r), f"register-machine image, {iters} iterations: result {k} differs"
+
+
+def test_fused_chains_cut_the_dispatch_count():
+    # pack.cpp peephole (uop.h U_FM / U_FQ / U_FS / U_FT): regression guard on the micro-op counts the round measured
+    def micro_ops(name, ppt):
+        pk = _handle(workloads.get(name).program).export_packed(ppt)
+        n = (len(pk["image"]) - pk["code_off"] // 8) // 4
+        return n // 2 if pk["double_buffered"] else n  # incl. the U_END of one copy
+
+    assert micro_ops("clifford", 4) == 5 and micro_ops("clifford", 2) == 7  # sin/cos + add/fma fusion: P = 4 layout only
+    assert micro_ops("terrain_gradient", 2) <= 1300  # 2666 device instructions
+    assert micro_ops("double_pendulum", 1) <= 155    # 182
+    assert micro_ops("aizawa", 4) <= 20              # 25
