@@ -427,6 +427,17 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
     case U_FT + 4 * (T) + 2: SAF_ENTER(U_FT + 4 * (T) + 2) { FTBODY(TRIG, , const double k_ = konst(FC); SAF_FOR_P acc.v[p] = __fma_rn(c.v[p], k_, t_.v[p]);) } SAF_NEXT(U_FT + 4 * (T) + 2) \
     case U_FT + 4 * (T) + 3: SAF_ENTER(U_FT + 4 * (T) + 3) { FTBODY(TRIG, H1PREFIX, const double k_ = konst(FC); SAF_FOR_P acc.v[p] = __fma_rn(c.v[p], k_, t_.v[p]);) } SAF_NEXT(U_FT + 4 * (T) + 3)
 
+// trig1(S[a] prefix b) (+ | fma K[c]) trig2(S[imm] prefix kinds-word)  (uop.h U_FD; P == 4 only)
+#define FDBODY(TRIG1, TRIG2, TAIL) if constexpr (P == 4) {                                                 \
+        const uint32_t f2_ = FI, pb2_ = img32(cur + 24);                                                   \
+        LS(a, fa) LS(b, f2_)                                                                               \
+        { const double k1_ = konst(fb), k2_ = konst(fb + 8); SAF_FOR_P a.v[p] = __fma_rn(a.v[p], k1_, k2_); } \
+        { const double k1_ = konst(pb2_), k2_ = konst(pb2_ + 8); SAF_FOR_P b.v[p] = __fma_rn(b.v[p], k1_, k2_); } \
+        Pt<P> u_, v_; TRIG1(a.v, u_.v); TRIG2(b.v, v_.v); TAIL }
+#define FDCASE(T1, T2, TRIG1, TRIG2)                                                                       \
+    case U_FD + 4 * (T1) + 2 * (T2) + 0: SAF_ENTER(U_FD + 4 * (T1) + 2 * (T2) + 0) { FDBODY(TRIG1, TRIG2, SAF_FOR_P acc.v[p] = __dadd_rn(u_.v[p], v_.v[p]);) } SAF_NEXT(U_FD + 4 * (T1) + 2 * (T2) + 0) \
+    case U_FD + 4 * (T1) + 2 * (T2) + 1: SAF_ENTER(U_FD + 4 * (T1) + 2 * (T2) + 1) { FDBODY(TRIG1, TRIG2, const double k_ = konst(FC); SAF_FOR_P acc.v[p] = __fma_rn(u_.v[p], k_, v_.v[p]);) } SAF_NEXT(U_FD + 4 * (T1) + 2 * (T2) + 1)
+
             SAF_DISPATCH(uop_now)
             switch (uop_now) {
             case U_END: SAF_CASE(U_END) { // a = code offset where the next iteration starts
@@ -506,6 +517,10 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
             FQCASE(1, , acc)
             FTCASE(0, lm::sin_n<P>)
             FTCASE(1, lm::cos_n<P>)
+            FDCASE(0, 0, lm::sin_n<P>, lm::sin_n<P>)
+            FDCASE(0, 1, lm::sin_n<P>, lm::cos_n<P>)
+            FDCASE(1, 0, lm::cos_n<P>, lm::sin_n<P>)
+            FDCASE(1, 1, lm::cos_n<P>, lm::cos_n<P>)
             case U_FS + FS_SQ: SAF_ENTER(U_FS + FS_SQ) { FSHEAD SAF_FOR_P acc.v[p] = __dmul_rn(a.v[p], a.v[p]); } SAF_NEXT(U_FS + FS_SQ)
             case U_FS + FS_SQ_ADDS: SAF_ENTER(U_FS + FS_SQ_ADDS) { const uint32_t fs = FI; FSHEAD LS(c, fs) /* after the store: S[imm] may be the kept slot */ SAF_FOR_P acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(a.v[p], a.v[p])); } SAF_NEXT(U_FS + FS_SQ_ADDS)
             case U_FS + FS_MULK2: SAF_ENTER(U_FS + FS_MULK2) { const double k1_ = konst(FC), k2_ = konst(FI); FSHEAD SAF_FOR_P acc.v[p] = __dmul_rn(k2_, __dmul_rn(k1_, a.v[p])); } SAF_NEXT(U_FS + FS_MULK2)

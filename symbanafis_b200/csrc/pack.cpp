@@ -274,6 +274,24 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
             const UI &p = U[i];
             const bool is_mul = p.uop >= U_BC + 5 * BC_MUL && p.uop < U_BC + 5 * BC_MUL + 5;
             const bool is_sq = p.uop == SQ || p.uop == SQ + 1;
+            // S = trig1(pre), then trig2(pre) combined with that S by an add / fma that overwrites it (uop.h U_FD)
+            if (P == 4 && i + 2 < U.size() && p.d != NO_DEST && (p.uop == U_H1 + 2 * H1_SIN + 1 || p.uop == U_H1 + 2 * H1_COS + 1)) {
+                const UI &q = U[i + 1], &r = U[i + 2];
+                const uint32_t FMASKA = U_T + 10 * T_FMA + T_SKA;
+                if ((q.uop == U_H1 + 2 * H1_SIN + 1 || q.uop == U_H1 + 2 * H1_COS + 1) && q.d == NO_DEST &&
+                    (r.uop == ADDSA || r.uop == FMASKA) && r.a == (uint32_t)p.d && r.d == p.d && q.a != (uint32_t)p.d) {
+                    UI f = p;
+                    const uint32_t t1 = (p.uop - U_H1) / 2 == H1_SIN ? 0u : 1u, t2 = (q.uop - U_H1) / 2 == H1_SIN ? 0u : 1u;
+                    f.uop = U_FD + 4 * t1 + 2 * t2 + (r.uop == FMASKA ? 1u : 0u);
+                    f.imm = q.a;
+                    f.kinds = q.b;
+                    if (r.uop == FMASKA) f.c = r.b;
+                    f.d = r.d;
+                    F.push_back(f);
+                    i += 3;
+                    continue;
+                }
+            }
             // sin / cos then S + ACC or fma(S, K, ACC): four-points-per-thread layout only (uop.h U_FT)
             if (P == 4 && p.d == NO_DEST && i + 1 < U.size() && p.uop >= U_H1 + 2 * H1_SIN && p.uop < U_H1 + 2 * H1_COS + 2) {
                 const UI &q = U[i + 1];

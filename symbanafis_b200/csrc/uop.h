@@ -81,7 +81,12 @@ constexpr uint32_t FS_SQ = 0, FS_SQ_ADDS = 1, FS_MULK2 = 2, FS_COUNT = 3;
 // than they saved in dispatches).
 constexpr uint32_t U_FT = U_FS + FS_COUNT;                    // + 4 * {sin, cos} + 2 * {adds, fma} + prefixed
 constexpr uint32_t FT_ADDS = 0, FT_FMA = 1, FT_COUNT = 8;
-constexpr uint32_t U_G = U_FT + FT_COUNT;                     // generic micro-ops
+// Two prefixed sin / cos of different slots combined by an add or an fma: `S = trig1(..)` kept only for the following
+// U_FT that consumes and overwrites it -- one output expression of a map step (`sin(a y) + c cos(a x)`) in ONE dispatch.
+// Fields: a, b = operand and prefix pair of trig1; imm, kinds word = operand and prefix pair of trig2; c = K of the fma.
+constexpr uint32_t U_FD = U_FT + FT_COUNT;                    // + 4 * trig1 + 2 * trig2 + {adds, fma}
+constexpr uint32_t FD_COUNT = 8;
+constexpr uint32_t U_G = U_FD + FD_COUNT;                     // generic micro-ops
 constexpr uint32_t G_POW = 0, G_POWI = 1, G_BUILTIN1 = 2, G_BUILTIN2 = 3, G_BUILTIN3 = 4, G_BUILTIN4 = 5,
                    G_ARG2 = 6, G_FMA = 7, G_FMS = 8, G_FNMA = 9, G_FNMS = 10, G_DIV = 11, G_RECIPEXPM1 = 12, G_COUNT = 13;
 constexpr uint32_t NO_PREFIX = 0xffffffffu; // field b of G_RECIPEXPM1 when there is no affine prefix

@@ -141,7 +141,7 @@ def test_fused_chains_cut_the_dispatch_count():
         n = (len(pk["image"]) - pk["code_off"] // 8) // 4
         return n // 2 if pk["double_buffered"] else n  # incl. the U_END of one copy
 
-    assert micro_ops("clifford", 4) == 5 and micro_ops("clifford", 2) == 7  # sin/cos + add/fma fusion: P = 4 layout only
+    assert micro_ops("clifford", 4) == 3 and micro_ops("clifford", 2) == 7  # sin/cos + add/fma fusion: P = 4 layout only
     assert micro_ops("terrain_gradient", 2) <= 1300  # 2666 device instructions
     assert micro_ops("double_pendulum", 1) <= 155    # 182
     assert micro_ops("aizawa", 4) <= 20              # 25
