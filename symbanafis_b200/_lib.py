@@ -253,6 +253,11 @@ class DeviceProgramHandle:
     # -- evaluation ----------------------------------------------------------------------------
     def eval_host(self, cols: Sequence[np.ndarray], outs: Sequence[np.ndarray], n_points: int,
                   broadcast: bool = False, devices: Optional[Sequence[int]] = None) -> None:
+        for a in list(cols) + list(outs):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 1 and a.flags.c_contiguous):
+                raise ValueError("eval_host: columns and outputs must be 1-D contiguous float64 arrays")
+        if any(o.size < n_points or not o.flags.writeable for o in outs):
+            raise ValueError("eval_host: every output array must be writable and hold n_points values")
         cp = ptr_array([c.ctypes.data for c in cols])
         cl = size_array([c.size for c in cols])
         op = ptr_array([o.ctypes.data for o in outs])
@@ -271,6 +276,10 @@ class DeviceProgramHandle:
 
     def iterate_host(self, state: Sequence[np.ndarray], iters: int) -> None:
         n = state[0].size if state else 0
+        for s in state:  # one length goes to C for every pointer
+            if not (isinstance(s, np.ndarray) and s.dtype == np.float64 and s.ndim == 1 and s.flags.c_contiguous
+                    and s.flags.writeable and s.size == n):
+                raise ValueError("iterate_host: state columns must be writable 1-D contiguous float64 arrays of one length")
         check(lib().saf_iterate_host(self._h, ptr_array([s.ctypes.data for s in state]), len(state), n, iters))
 
     def iterate_device(self, state_ptrs: Sequence[int], n_points: int, iters: int, stream: int = 0) -> None:

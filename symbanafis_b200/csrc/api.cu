@@ -55,8 +55,10 @@ struct saf_program {
     PackedProgram packed[5];          // [4] = register machine (ruop.h)
     bool packed_ready[5] = {false, false, false, false, false};
     int r_pack_rc = 0;                // result of the register-machine packing (kept: failures are not retried)
-    PackedProgram packed_wide;        // wide one-block-per-SM layout (P = 2), packed for packed_wide_threads
-    int packed_wide_threads = 0;
+    // wide one-block-per-SM layout, keyed by 1000 * points-per-thread + block threads.  std::map never moves its
+    // entries: a pointer handed out under `mu` stays valid after the lock is released (devices with different
+    // shared-memory sizes may ask for different widths concurrently, saf_eval_host_multi)
+    std::map<int, PackedProgram> packed_wide;
     std::map<std::pair<int, int>, unsigned char *> copies; // (device, P) -> global-memory image for big programs
 };
 
@@ -273,7 +275,15 @@ static int ensure_device_image(saf_program *p, int device, const PackedProgram &
     }
     unsigned char *dptr = nullptr;
     SAF_CUDA(cudaMalloc(&dptr, pk.image.size() * 8));
-    SAF_CUDA(cudaMemcpy(dptr, pk.image.data(), pk.image.size() * 8, cudaMemcpyHostToDevice));
+    // The image is pageable host memory: cudaMemcpy may return once the bytes are staged, before the DMA has reached
+    // device memory, and the first launch goes onto a non-blocking stream that is not ordered after the legacy
+    // default stream.  Wait for the copy itself before the pointer is published.
+    cudaError_t ce = cudaMemcpy(dptr, pk.image.data(), pk.image.size() * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(cudaStreamLegacy);
+    if (ce != cudaSuccess) {
+        cudaFree(dptr);
+        return cuda_fail(ce, "program image upload");
+    }
     p->copies[key] = dptr;
     *out = dptr;
     return SAF_OK;
@@ -354,16 +364,15 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
         if (t > 0) {
             saf_program *mp = const_cast<saf_program *>(prog);
             std::lock_guard<std::mutex> lk(mp->mu);
-            if (mp->packed_wide_threads != t) {
+            const int key = 1000 * P + t;
+            auto it = mp->packed_wide.find(key);
+            if (it == mp->packed_wide.end()) {
                 std::string err;
                 PackedProgram w;
-                if (pack_program(mp->dev, 2, w, err, t) == SAF_OK) {
-                    mp->packed_wide = std::move(w);
-                    mp->packed_wide_threads = t;
-                }
+                if (pack_program(mp->dev, P, w, err, t) == SAF_OK) it = mp->packed_wide.emplace(key, std::move(w)).first;
             }
-            if (mp->packed_wide_threads == t) {
-                pk = &mp->packed_wide;
+            if (it != mp->packed_wide.end()) {
+                pk = &it->second; // map entries never move: valid after the lock is released
                 block_threads = t;
             }
         }
@@ -706,16 +715,29 @@ extern "C" int saf_device_count(int *count) {
     return SAF_OK;
 }
 
+namespace {
+// releases the probes' events and device buffers on every return path (SAF_CUDA returns early)
+struct ProbeGuard {
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    void *mem[2] = {nullptr, nullptr};
+    ~ProbeGuard() {
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+        for (auto m : mem) if (m) cudaFree(m);
+    }
+};
+} // namespace
+
 extern "C" int saf_measure_fp64_peak(double *dfma_lanes_per_second) {
     if (!dfma_lanes_per_second) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL argument");
     int dev = 0, sms = 0;
     SAF_CUDA(cudaGetDevice(&dev));
     SAF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    double *sink = nullptr;
-    SAF_CUDA(cudaMalloc(&sink, 8));
-    cudaEvent_t e0, e1;
-    SAF_CUDA(cudaEventCreate(&e0));
-    SAF_CUDA(cudaEventCreate(&e1));
+    ProbeGuard g;
+    SAF_CUDA(cudaMalloc(&g.mem[0], 8));
+    double *sink = static_cast<double *>(g.mem[0]);
+    SAF_CUDA(cudaEventCreate(&g.ev[0]));
+    SAF_CUDA(cudaEventCreate(&g.ev[1]));
+    const cudaEvent_t e0 = g.ev[0], e1 = g.ev[1];
     const int blocks = sms * 8, iters = 4096;
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
@@ -728,9 +750,6 @@ extern "C" int saf_measure_fp64_peak(double *dfma_lanes_per_second) {
         const double lanes = (double)blocks * 256.0 * (double)iters * 64.0;
         if (rep > 0 && ms > 0.f) best = std::max(best, lanes / (ms * 1e-3));
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(sink);
     *dfma_lanes_per_second = best;
     return SAF_OK;
 }
@@ -740,14 +759,15 @@ extern "C" int saf_measure_clifford_probe(size_t n_points, int iters, double *se
     int dev = 0, sms = 0;
     SAF_CUDA(cudaGetDevice(&dev));
     SAF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    double *xs = nullptr, *ys = nullptr;
-    SAF_CUDA(cudaMalloc(&xs, n_points * 8));
-    SAF_CUDA(cudaMalloc(&ys, n_points * 8));
+    ProbeGuard g;
+    SAF_CUDA(cudaMalloc(&g.mem[0], n_points * 8));
+    SAF_CUDA(cudaMalloc(&g.mem[1], n_points * 8));
+    double *xs = static_cast<double *>(g.mem[0]), *ys = static_cast<double *>(g.mem[1]);
     std::vector<double> h(n_points);
     for (size_t i = 0; i < n_points; ++i) h[i] = -2.0 + 4.0 * (double)((i * 2654435761ull) % 1000003ull) / 1000003.0;
-    cudaEvent_t e0, e1;
-    SAF_CUDA(cudaEventCreate(&e0));
-    SAF_CUDA(cudaEventCreate(&e1));
+    SAF_CUDA(cudaEventCreate(&g.ev[0]));
+    SAF_CUDA(cudaEventCreate(&g.ev[1]));
+    const cudaEvent_t e0 = g.ev[0], e1 = g.ev[1];
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         SAF_CUDA(cudaMemcpy(xs, h.data(), n_points * 8, cudaMemcpyHostToDevice));
@@ -760,10 +780,6 @@ extern "C" int saf_measure_clifford_probe(size_t n_points, int iters, double *se
         SAF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0 && (best == 0.0 || ms * 1e-3 < best)) best = ms * 1e-3;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(xs);
-    cudaFree(ys);
     *seconds = best;
     return SAF_OK;
 }

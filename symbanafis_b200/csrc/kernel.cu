@@ -56,13 +56,16 @@ struct Pt {
     double v[P];
 };
 
+// Plain (coherent) loads with a streaming hint, not ld.global.nc: saf_iterate_device and in-place evaluation pass
+// the same buffers as columns and outputs, and PTX leaves a non-coherent read of an address the same kernel writes
+// undefined (a broadcast column that aliases an output is re-read by later tiles).
 __device__ __forceinline__ double ld_stream(const double *p) {
     double r;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
     return r;
 }
 __device__ __forceinline__ void ld_stream2(const double *p, double &a, double &b) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void st_stream(double *p, double v) {
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");

@@ -447,6 +447,238 @@ std::vector<int32_t> follow_chains(const Graph &g, const std::vector<uint8_t> &l
     return out;
 }
 
+// (c) Term-aligned merge of the long sums.  The lockstep of (a) aligns the sums by FRACTION of completion; when the
+// sums of different outputs have different lengths (the positive and negative parts of d/dx and d/dy of one terrain:
+// 97 / 119 / 102 / 124 terms) that drifts, and a subexpression shared by term k of two sums (sin/cos of one argument,
+// one Gaussian bump) waits several terms for its second consumer.  This order advances the top-level sums ONE TERM AT A
+// TIME and picks, among the next terms of all sums, the one whose emission changes the number of live values the
+// least -- counting as already paid the values whose other consumer is the next term of another sum.  Two sums that
+// visit their shared subexpressions in the same order (they do when they come from one symbolic expression) then
+// pair up term by term and a shared value lives for one term.  Everything outside the sums is emitted on demand.
+std::vector<int32_t> schedule_spine_merge(const Graph &g, const std::vector<uint8_t> &live,
+                                          const std::vector<int32_t> &results) {
+    const int32_t N = (int32_t)g.nodes.size();
+    auto is_instr = [&](int32_t v) { return g.nodes[v].op < V_PARAM; };
+    auto producer = [&](int32_t v) -> int32_t {
+        uint8_t op = g.nodes[v].op;
+        if (op == V_COSPART) return g.nodes[v].a;
+        return op < V_PARAM ? v : -1;
+    };
+    auto operands = [&](int32_t n, int32_t out_vals[4]) -> int { // distinct register-file operand values
+        const Node &nd = g.nodes[n];
+        int k = 0;
+        for (int32_t s : {nd.a, nd.b, nd.c, nd.e}) {
+            if (s < 0 || producer(s) < 0) continue;
+            bool dup = false;
+            for (int i = 0; i < k; ++i) dup |= out_vals[i] == s;
+            if (!dup) out_vals[k++] = s;
+        }
+        return k;
+    };
+    std::vector<int32_t> n_consumers(N, 0), uses_left(N, 0);
+    std::vector<std::vector<int32_t>> consumers(N);
+    for (int32_t n = 0; n < N; ++n) {
+        if (!live[n] || !is_instr(n)) continue;
+        const Node &nd = g.nodes[n];
+        for (int32_t s : {nd.a, nd.b, nd.c, nd.e})
+            if (s >= 0) ++n_consumers[s];
+        int32_t ov[4];
+        const int k = operands(n, ov);
+        for (int i = 0; i < k; ++i) {
+            ++uses_left[ov[i]];
+            consumers[ov[i]].push_back(n);
+        }
+    }
+    std::vector<uint8_t> is_result(N, 0);
+    for (int32_t r : results) {
+        ++n_consumers[r];
+        is_result[r] = 1;
+    }
+
+    // ---- top-level spines: left-deep add / mul chains of >= 3 nodes met on the way down from the results ----
+    struct Spine { std::vector<int32_t> nodes; size_t ptr = 0; }; // bottom-up
+    std::vector<Spine> spines;
+    std::vector<int32_t> spine_of(N, -1);
+    {
+        std::vector<uint8_t> seen(N, 0);
+        std::vector<int32_t> stack;
+        for (int32_t r : results) {
+            const int32_t pr = producer(r);
+            if (pr >= 0) stack.push_back(pr);
+        }
+        std::vector<int32_t> sp;
+        while (!stack.empty()) {
+            const int32_t n = stack.back();
+            stack.pop_back();
+            if (seen[n]) continue;
+            seen[n] = 1;
+            const Node &nd = g.nodes[n];
+            if (nd.op == D_ADD || nd.op == D_MUL) {
+                sp.clear();
+                int32_t cur = n;
+                for (;;) {
+                    sp.push_back(cur);
+                    const Node &c = g.nodes[cur];
+                    int32_t next = -1;
+                    for (int32_t s : {c.a, c.b})
+                        if (s >= 0 && g.nodes[s].op == nd.op && n_consumers[s] == 1 && producer(s) == s && !seen[s]) {
+                            next = s;
+                            break;
+                        }
+                    if (next < 0) break;
+                    cur = next;
+                }
+                if (sp.size() >= 3) {
+                    Spine S;
+                    S.nodes.assign(sp.rbegin(), sp.rend());
+                    for (int32_t x : S.nodes) {
+                        spine_of[x] = (int32_t)spines.size();
+                        seen[x] = 1;
+                    }
+                    spines.push_back(std::move(S));
+                    continue; // the terms of a spine are opaque cones: no spines are looked for inside them
+                }
+            }
+            for (int32_t s : {nd.a, nd.b, nd.c, nd.e}) {
+                if (s < 0) continue;
+                const int32_t pr = producer(s);
+                if (pr >= 0 && !seen[pr]) stack.push_back(pr);
+            }
+        }
+    }
+
+    std::vector<uint8_t> emitted(N, 0);
+    std::vector<int32_t> order;
+    auto emit_node = [&](int32_t n) {
+        emitted[n] = 1;
+        order.push_back(n);
+        int32_t ov[4];
+        const int k = operands(n, ov);
+        for (int i = 0; i < k; ++i) --uses_left[ov[i]];
+    };
+    // unemitted dependency cone of an instruction, post-order
+    std::vector<int32_t> stamp(N, -1), stack;
+    int32_t stamp_id = 0;
+    auto build_cone = [&](int32_t c, std::vector<int32_t> &cone) {
+        cone.clear();
+        stack.clear();
+        ++stamp_id;
+        stack.push_back(c);
+        while (!stack.empty()) {
+            int32_t x = stack.back();
+            stack.pop_back();
+            if (x < 0) {
+                cone.push_back(~x);
+                continue;
+            }
+            if (emitted[x] || stamp[x] == stamp_id) continue;
+            stamp[x] = stamp_id;
+            stack.push_back(~x);
+            const Node &nd = g.nodes[x];
+            const int32_t ops[4] = {nd.e, nd.c, nd.b, nd.a}; // reversed: a is visited first
+            for (int32_t s : ops) {
+                if (s < 0) continue;
+                const int32_t pr = producer(s);
+                if (pr >= 0 && !emitted[pr] && stamp[pr] != stamp_id) stack.push_back(pr);
+            }
+        }
+    };
+    std::vector<int32_t> cnt_in(N, 0), cnt_kill(N, 0), touched;
+    // change in the number of live values if `cone` were emitted; `remaining` receives the values made inside the
+    // cone that stay live after it
+    auto cone_net = [&](const std::vector<int32_t> &cone, std::vector<int32_t> &remaining) -> int {
+        int produced = 0, killed = 0;
+        touched.clear();
+        remaining.clear();
+        for (int32_t n : cone) {
+            int32_t ov[4];
+            const int k = operands(n, ov);
+            for (int i = 0; i < k; ++i) {
+                const int32_t v = ov[i];
+                if (cnt_in[v] == 0 && cnt_kill[v] == 0) touched.push_back(v);
+                if (emitted[producer(v)]) ++cnt_kill[v];
+                else ++cnt_in[v];
+            }
+        }
+        for (int32_t v : touched)
+            if (cnt_kill[v] > 0 && cnt_kill[v] == uses_left[v] && !is_result[v]) ++killed;
+        for (int32_t n : cone) {
+            auto remains = [&](int32_t v) { return is_result[v] || uses_left[v] - cnt_in[v] > 0; };
+            if (remains(n)) { ++produced; remaining.push_back(n); }
+            auto it = g.cos_of.find(n);
+            if (it != g.cos_of.end() && live[it->second] && remains(it->second)) { ++produced; remaining.push_back(it->second); }
+        }
+        for (int32_t v : touched) cnt_in[v] = cnt_kill[v] = 0;
+        return produced - killed;
+    };
+
+    const size_t S = spines.size();
+    std::vector<std::vector<int32_t>> cones(S), remaining(S);
+    std::vector<int> net(S, 0);
+    std::vector<uint8_t> eligible(S, 0);
+    std::vector<int32_t> in_cone_of(N, -1); // head candidate whose cone holds the node (this round)
+    for (;;) {
+        bool any = false;
+        for (size_t s = 0; s < S; ++s) {
+            Spine &sp = spines[s];
+            while (sp.ptr < sp.nodes.size() && emitted[sp.nodes[sp.ptr]]) ++sp.ptr;
+            cones[s].clear();
+            eligible[s] = 0;
+            if (sp.ptr >= sp.nodes.size()) continue;
+            any = true;
+            build_cone(sp.nodes[sp.ptr], cones[s]);
+            eligible[s] = 1;
+            for (int32_t n : cones[s])
+                if (spine_of[n] >= 0 && spine_of[n] != (int32_t)s) eligible[s] = 0; // waits for another sum
+            net[s] = cone_net(cones[s], remaining[s]);
+        }
+        if (!any) break;
+        for (size_t s = 0; s < S; ++s)
+            for (int32_t n : cones[s]) in_cone_of[n] = -1;
+        for (size_t s = 0; s < S; ++s)
+            if (eligible[s])
+                for (int32_t n : cones[s])
+                    if (in_cone_of[n] < 0) in_cone_of[n] = (int32_t)s; // shared nodes: first head wins
+        int best = -1;
+        double best_key = 0.0, best_progress = 0.0;
+        for (size_t s = 0; s < S; ++s) {
+            if (cones[s].empty()) continue;
+            // values this term leaves behind whose (other) consumer is the next term of another sum are about to be
+            // consumed: they do not count against it
+            int paired = 0;
+            for (int32_t v : remaining[s]) {
+                if (is_result[v]) continue;
+                bool hit = false;
+                for (int32_t c : consumers[v])
+                    if (!emitted[c] && in_cone_of[c] >= 0 && in_cone_of[c] != (int32_t)s) hit = true;
+                paired += hit;
+            }
+            const double progress = (double)spines[s].ptr / (double)spines[s].nodes.size();
+            // ineligible candidates (their term needs another sum's result) only run when nothing else can
+            const double key = (eligible[s] ? 0.0 : 1e6) + (double)(net[s] - paired);
+            if (best < 0 || key < best_key || (key == best_key && progress < best_progress)) {
+                best = (int)s;
+                best_key = key;
+                best_progress = progress;
+            }
+        }
+        const std::vector<int32_t> todo = cones[best];
+        for (int32_t n : todo)
+            if (!emitted[n]) emit_node(n);
+    }
+    // ---- everything else, on demand from the results ----
+    std::vector<int32_t> cone;
+    for (int32_t r : results) {
+        const int32_t pr = producer(r);
+        if (pr < 0 || emitted[pr]) continue;
+        build_cone(pr, cone);
+        const std::vector<int32_t> todo = cone;
+        for (int32_t n : todo)
+            if (!emitted[n]) emit_node(n);
+    }
+    return order;
+}
+
 std::vector<int32_t> schedule_nodes(const Graph &g, const std::vector<uint8_t> &live,
                                     const std::vector<int32_t> &results) {
     const int32_t N = (int32_t)g.nodes.size();
@@ -1060,6 +1292,27 @@ int lower(const std::vector<const RefProgram *> &progs, DeviceProgram &out, std:
         rc_b = emit_program(schedule_nodes(g, live, results), cand_b);
         err_b = err;
         err = saved;
+        // (c) term-aligned merge of the long sums (+ chain following); replaces (a) when it needs clearly fewer slots
+        // (more resident warps: the interpreter is latency-bound at the occupancy big register files leave)
+        const char *no_merge = getenv("SAF_SCHED");
+        if (!(no_merge && no_merge[0] == 'n')) {
+            DeviceProgram cand_c, cand_c2;
+            const std::vector<int32_t> base_c = schedule_spine_merge(g, live, results);
+            int rc_c = emit_program(base_c, cand_c);
+            const int rc_c2 = emit_program(follow_chains(g, live, results, base_c), cand_c2);
+            if (rc_c2 == SAF_OK && (rc_c != SAF_OK || (cand_c2.n_slots <= cand_c.n_slots &&
+                                                       cand_c2.n_acc_forwards > cand_c.n_acc_forwards))) {
+                cand_c = std::move(cand_c2);
+                rc_c = rc_c2;
+            }
+            const bool force_c = no_merge && no_merge[0] == 'm';
+            if (rc_c == SAF_OK && (force_c || rc_a != SAF_OK || cand_c.n_slots * 8 <= cand_a.n_slots * 7)) {
+                cand_a = std::move(cand_c);
+                rc_a = rc_c;
+                err_a = err;
+            }
+            err = saved;
+        }
     }
     const char *force = getenv("SAF_SCHED");
     bool pick_a;

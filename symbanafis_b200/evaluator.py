@@ -167,6 +167,11 @@ class CompiledEvaluator:
     def iterate(self, state: Sequence[np.ndarray], iters: int) -> List[np.ndarray]:
         """state_j <- result_j, ``iters`` times on chip; returns new host arrays."""
         st = [np.array(s, dtype=np.float64, copy=True) for s in state]
+        if len(st) != self.program.param_count or len(st) != self.n_results:
+            raise ValueError("iterate needs one state column per parameter and per result")
+        # the C ABI takes ONE length for all state pointers: a shorter later array would be read and written out of bounds
+        if any(a.ndim != 1 for a in st) or any(a.size != st[0].size for a in st):
+            raise ValueError("All evaluation columns must have the same length")
         try:
             self._h.iterate_host(st, iters)
         except _lib.SafError as e:
@@ -178,12 +183,16 @@ class CompiledEvaluator:
         """Columns are 1-D float64 CUDA tensors; returns (or fills) one CUDA tensor per result."""
         import torch
         n = columns[0].numel() if columns else 1
-        for c in columns:
-            if not (c.is_cuda and c.dtype == torch.float64 and c.is_contiguous()):
-                raise TypeError("device columns must be contiguous float64 CUDA tensors")
-        dev = columns[0].device if columns else torch.device("cuda")
+        dev = columns[0].device if columns else torch.device("cuda", torch.cuda.current_device())
+        _check_device_columns(columns, dev, None, "device columns")
+        if any(c.numel() != n for c in columns):
+            raise ValueError("All evaluation columns must have the same length")
         if outs is None:
             outs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(self.n_results)]
+        else:  # user buffers are written by the kernel: a short or foreign one is an out-of-bounds device write
+            if len(outs) != self.n_results:
+                raise ValueError(f"expected {self.n_results} output tensors, got {len(outs)}")
+            _check_device_columns(outs, dev, n, "output tensors")
         s = (stream or torch.cuda.current_stream(dev)).cuda_stream
         try:
             with torch.cuda.device(dev):
@@ -196,8 +205,11 @@ class CompiledEvaluator:
     def iterate_device(self, state, iters: int, stream=None):
         """In-place iterated map on CUDA tensors."""
         import torch
+        if len(state) != self.program.param_count or len(state) != self.n_results:
+            raise ValueError("iterate needs one state tensor per parameter and per result")
         n = state[0].numel()
         dev = state[0].device
+        _check_device_columns(state, dev, n, "state tensors")
         s = (stream or torch.cuda.current_stream(dev)).cuda_stream
         try:
             with torch.cuda.device(dev):
@@ -207,13 +219,30 @@ class CompiledEvaluator:
         return state
 
 
+def _check_device_columns(tensors, dev, n, what: str) -> None:
+    """1-D contiguous float64 CUDA tensors on ``dev`` (and exactly ``n`` long when n is given): the C ABI takes raw
+    pointers and one length, so anything else is an out-of-bounds device access, not an exception."""
+    import torch
+    for t in tensors:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float64:
+            raise TypeError(f"{what} must be float64 CUDA tensors")
+        if t.dim() != 1 or not t.is_contiguous():
+            raise ValueError(f"{what} must be 1-D and contiguous")
+        if t.device != dev:
+            raise ValueError(f"{what} must all live on {dev}")
+        if n is not None and t.numel() != n:
+            raise ValueError("All evaluation columns must have the same length")
+
+
 # ------------------------------------------------------------------------------------------------------
 _PROGRAM_CACHE: Dict[tuple, CompiledEvaluator] = {}
 
 
 def _cached_evaluator(exprs: Sequence[Expr], names: Sequence[str]) -> CompiledEvaluator:
     # The reference compiles inside every eval_f64 call (batch.rs:28-30); handles are cached here.
-    key = (tuple(id(e) for e in exprs), tuple(names))
+    # keyed on the structural key of each expression (expr.Expr._key), not on id(): ids are only unique while the node
+    # is alive, and the cache must not depend on the interning table keeping every node alive forever
+    key = (tuple(e._key for e in exprs), tuple(names))
     ev = _PROGRAM_CACHE.get(key)
     if ev is None:
         ev = CompiledEvaluator(list(exprs), list(names))

@@ -13,6 +13,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """GPU-marked tests are SKIPPED (not failed) on a box without a CUDA device, so that the CPU suite's signal is not
+    buried under cudaErrorInsufficientDriver failures.  On a GPU box nothing is skipped: the product path has no
+    CPU fallback to hide behind."""
+    try:
+        from symbanafis_b200 import _lib
+        have_gpu = os.path.exists(_lib.LIB_PATH) and _lib.device_count() > 0
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _build_native():
     """The oracle (gcc) is rebuilt if stale; the CUDA library must already be built in-tree."""
