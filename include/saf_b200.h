@@ -136,8 +136,8 @@ SAF_API int saf_program_export(const saf_program *prog, uint64_t *code, size_t c
  * swapped, each U_END continuing with the other copy, and after an EVEN number of iterations the results sit at
  * result_off_even.  points_per_thread = 104 exports the image of the opt-in REGISTER machine instead (four points per
  * thread, live values in real registers; layout: symbanafis_b200/csrc/ruop.h; never double buffered -- the image
- * loops in-kernel by itself when results pair with parameters); points_per_thread = 2000 + T (T a multiple of 32,
- * 160..512) the two-points-per-thread image for one wide block of T threads per SM.  For the CPU emulators of the test-suite and for
+ * loops in-kernel by itself when results pair with parameters); points_per_thread = 1000 * P + T (P = 2 or 4, T a multiple of 32,
+ * 160..512) the P-points-per-thread image for one wide block of T threads per SM.  For the CPU emulators of the test-suite and for
  * tooling.  Any pointer may be NULL; n_words always receives the full size. */
 SAF_API int saf_program_export_packed(const saf_program *prog, int points_per_thread,
                               uint64_t *image, size_t cap_words, size_t *n_words,

@@ -246,8 +246,8 @@ class DeviceProgramHandle:
         return {"image": image, "code_off": co.value, "n_slots": ns.value, "x_off": x_off,
                 "param_off": poff[:info.param_count], "result_off": roff[:info.n_results],
                 "result_is_k": rk[:info.n_results],
-                "points_per_thread": 2 if points_per_thread > 2000 else points_per_thread,
-                "block_threads": points_per_thread - 2000 if points_per_thread > 2000 else 128,
+                "points_per_thread": points_per_thread // 1000 if points_per_thread > 1000 else points_per_thread,
+                "block_threads": points_per_thread % 1000 if points_per_thread > 1000 else 128,
                 "result_off_even": roff_even[:info.n_results], "double_buffered": bool(dbuf.value)}
 
     # -- evaluation ----------------------------------------------------------------------------

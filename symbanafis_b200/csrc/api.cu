@@ -359,8 +359,8 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
         const char *v = getenv("SAF_WIDE");
         return !(v && v[0] == '0');
     }();
-    if (!use_r && P == 2 && wide_ok) {
-        const int t = wide_block_threads(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points);
+    if (!use_r && (P == 2 || P == 4) && wide_ok) {
+        const int t = wide_block_threads(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points, P);
         if (t > 0) {
             saf_program *mp = const_cast<saf_program *>(prog);
             std::lock_guard<std::mutex> lk(mp->mu);
@@ -409,18 +409,19 @@ extern "C" int saf_program_export_packed(const saf_program *p, int points_per_th
                                          int32_t *result_off_even, int *double_buffered) {
     if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
     const PackedProgram *pk = nullptr;
-    PackedProgram wide; // 2000 + threads: the wide one-block-per-SM layout (two points per thread), packed on the spot
+    PackedProgram wide; // 1000 * P + threads: the wide one-block-per-SM layout (P = 2 or 4), packed on the spot
     int rc;
-    if (points_per_thread > 2000 && points_per_thread <= 2000 + WIDE_MAX_THREADS && points_per_thread % 32 == 2000 % 32) {
+    const int wide_p = points_per_thread / 1000, wide_t = points_per_thread % 1000;
+    if ((wide_p == 2 || wide_p == 4) && wide_t > 0 && wide_t <= WIDE_MAX_THREADS && wide_t % 32 == 0) {
         std::string err;
-        rc = pack_program(p->dev, 2, wide, err, points_per_thread - 2000);
+        rc = pack_program(p->dev, wide_p, wide, err, wide_t);
         if (rc != SAF_OK) return fail(rc, err);
         pk = &wide;
     } else {
         if (points_per_thread != 1 && points_per_thread != 2 && points_per_thread != 4 && points_per_thread != 8 &&
             points_per_thread != LAYOUT_R)
             return fail(SAF_ERR_INVALID_ARGUMENT,
-                        "points_per_thread must be 1, 2, 4, 8, 104 (register machine) or 2000 + threads (wide blocks)");
+                        "points_per_thread must be 1, 2, 4, 8, 104 (register machine) or 1000 * P + threads (wide blocks, P = 2 or 4)");
         rc = packed_for(const_cast<saf_program *>(p), points_per_thread, &pk);
         if (rc != SAF_OK) return rc;
     }

@@ -105,9 +105,11 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
 }
 __device__ __forceinline__ uint32_t smem_base32() { return (uint32_t)__cvta_generic_to_shared(saf_smem); }
 
-template <int P>
+// WIDE (one block of blockDim.x threads per SM): the stride between a thread's pairs is the block's width, a
+// run-time value -- the accesses use [register + uniform register] addressing, no extra instruction.
+template <int P, bool WIDE = false>
 struct Rf {
-    static constexpr uint32_t PAIR_BYTES = BLOCK_THREADS * 16;
+    __device__ __forceinline__ static uint32_t pair_bytes() { return WIDE ? blockDim.x * 16u : (uint32_t)BLOCK_THREADS * 16u; }
     __device__ __forceinline__ static uint32_t mine(uint32_t smem32) { return smem32 + threadIdx.x * (P == 1 ? 8u : 16u); }
     __device__ __forceinline__ static void load(uint32_t my, uint32_t off, Pt<P> &o) {
         const uint32_t p = my + off;
@@ -115,7 +117,7 @@ struct Rf {
             lds64(p, o.v[0]);
         } else {
 #pragma unroll
-            for (int g = 0; g < P / 2; ++g) lds128(p + g * PAIR_BYTES, o.v[2 * g], o.v[2 * g + 1]);
+            for (int g = 0; g < P / 2; ++g) lds128(p + g * pair_bytes(), o.v[2 * g], o.v[2 * g + 1]);
         }
     }
     __device__ __forceinline__ static void store(uint32_t my, uint32_t off, const Pt<P> &o) {
@@ -124,16 +126,21 @@ struct Rf {
             sts64(p, o.v[0]);
         } else {
 #pragma unroll
-            for (int g = 0; g < P / 2; ++g) sts128(p + g * PAIR_BYTES, o.v[2 * g], o.v[2 * g + 1]);
+            for (int g = 0; g < P / 2; ++g) sts128(p + g * pair_bytes(), o.v[2 * g], o.v[2 * g + 1]);
         }
     }
 };
 
 // destination store of a micro-instruction: predicated, not branched (d < 0 = result stays in ACC only)
-template <int P>
+template <int P, bool WIDE = false>
 __device__ __forceinline__ void store_if(uint32_t my, int32_t fd, const Pt<P> &o) {
     const uint32_t p = my + (uint32_t)fd;
-    if constexpr (P == 1) {
+    if constexpr (WIDE && P == 4) {
+        const uint32_t p2 = p + Rf<P, WIDE>::pair_bytes();
+        asm volatile("{ .reg .pred q; setp.ge.s32 q, %0, 0; @q st.shared.v2.f64 [%1], {%3, %4}; @q st.shared.v2.f64 [%2], {%5, %6}; }" ::"r"(fd),
+                     "r"(p), "r"(p2), "d"(o.v[0]), "d"(o.v[1]), "d"(o.v[2]), "d"(o.v[3])
+                     : "memory");
+    } else if constexpr (P == 1) {
         asm volatile("{ .reg .pred q; setp.ge.s32 q, %0, 0; @q st.shared.f64 [%1], %2; }" ::"r"(fd), "r"(p), "d"(o.v[0]) : "memory");
     } else if constexpr (P == 2) {
         asm volatile("{ .reg .pred q; setp.ge.s32 q, %0, 0; @q st.shared.v2.f64 [%1], {%2, %3}; }" ::"r"(fd), "r"(p), "d"(o.v[0]),
@@ -151,7 +158,7 @@ __device__ __forceinline__ void store_if(uint32_t my, int32_t fd, const Pt<P> &o
                      : "memory");
     }
 }
-static_assert(BLOCK_THREADS * 16 == 2048, "store_if hard-codes the pair stride");
+static_assert(BLOCK_THREADS * 16 == 2048, "store_if hard-codes the pair stride of 128-thread blocks");
 
 #define SAF_FOR_P _Pragma("unroll") for (int p = 0; p < P; ++p)
 
@@ -172,20 +179,32 @@ __device__ __forceinline__ uint2 split64(unsigned long long w) { return make_uin
 
 // Points of a thread.  P == 1: i = tile_base + tid.  P >= 2: pair g covers points
 // tile_base + g * 2 * BLOCK + 2 * tid + {0, 1}: every 128-bit access of a warp is fully coalesced.
-template <int P>
+template <int P, bool WIDE = false>
 __device__ __forceinline__ unsigned long long point_index(unsigned long long tile_base, int p) {
     if constexpr (P == 1) return tile_base + threadIdx.x;
-    else return tile_base + (unsigned long long)(p >> 1) * (2 * BLOCK_THREADS) + 2 * threadIdx.x + (p & 1);
+    else return tile_base + (unsigned long long)(p >> 1) * (2 * (WIDE ? blockDim.x : (unsigned)BLOCK_THREADS)) + 2 * threadIdx.x + (p & 1);
 }
 
 // ---- cold micro-ops ---------------------------------------------------------------------------------
 // pow, powi, 1/expm1, the builtins (61 FnOps of devmath.cuh), operand staging and the rare operand-kind
 // combinations: decoded at run time, out of line, memory to memory.  ACC is read from / written to the
 // reserved slot `acc_off`; hot_run stores ACC there before it returns and reloads it when re-entered.
-template <int P, bool RM = false>
+// The special functions themselves are ONE out-of-line copy each for the whole module (every layout's cold_op and
+// every entry point calls the same code): inlined per layout and per point they made up most of a 20 MB image.
+__device__ __noinline__ double cold_builtin1(uint32_t fn, double a) { return dm::builtin1(fn, a).v; }
+__device__ __noinline__ double cold_builtin2(uint32_t fn, double a, double b) { return dm::builtin2(fn, a, b).v; }
+__device__ __noinline__ double cold_builtin3(uint32_t fn, double a, double b, double c) { return dm::builtin3(fn, a, b, c).v; }
+__device__ __noinline__ double cold_builtin4(uint32_t fn, double a, double b, double c, double d) {
+    return dm::builtin4(fn, a, b, c, d).v;
+}
+__device__ __noinline__ double cold_pow(double a, double b) { return pow(a, b); }
+__device__ __noinline__ double cold_powi(double a, int n) { return dm::powi(a, n).v; }
+__device__ __noinline__ double cold_recip_expm1(double a) { return __ddiv_rn(1.0, expm1(a)); }
+
+template <int P, bool RM = false, bool WIDE = false>
 __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int32_t acc_off, int32_t x0_off,
                                      int32_t x1_off) {
-    using RF = Rf<P>;
+    using RF = Rf<P, WIDE && P == 4>;
     const uint32_t my = RF::mine(smem_base32());
     const unsigned long long *w = reinterpret_cast<const unsigned long long *>(img + cur);
     const uint2 q0 = split64(w[0]), q1 = split64(w[1]), q2 = split64(w[2]), q3 = split64(w[3]);
@@ -207,7 +226,7 @@ __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int
     switch (uop) {
     case U_G + G_POW:
         any(kinds & 3u, fa, a); any((kinds >> 2) & 3u, fb, b);
-        SAF_FOR_P r.v[p] = pow(a.v[p], b.v[p]);
+        SAF_FOR_P r.v[p] = cold_pow(a.v[p], b.v[p]);
         break;
     case U_G + G_DIV:
         any(kinds & 3u, fa, a); any((kinds >> 2) & 3u, fb, b);
@@ -215,7 +234,7 @@ __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int
         break;
     case U_G + G_POWI:
         any(kinds & 3u, fa, a);
-        SAF_FOR_P r.v[p] = dm::powi(a.v[p], (int)imm).v;
+        SAF_FOR_P r.v[p] = cold_powi(a.v[p], (int)imm);
         break;
     case U_G + G_RECIPEXPM1:
         any(kinds & 3u, fa, a);
@@ -223,29 +242,29 @@ __device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int
             const double k1 = konst(fb), k2 = konst(fb + 8);
             SAF_FOR_P a.v[p] = __fma_rn(a.v[p], k1, k2);
         }
-        SAF_FOR_P r.v[p] = __ddiv_rn(1.0, expm1(a.v[p]));
+        SAF_FOR_P r.v[p] = cold_recip_expm1(a.v[p]);
         break;
     case U_G + G_BUILTIN1:
         any(kinds & 3u, fa, a);
-        SAF_FOR_P r.v[p] = dm::builtin1(imm, a.v[p]).v;
+        SAF_FOR_P r.v[p] = cold_builtin1(imm, a.v[p]);
         break;
     case U_G + G_BUILTIN2:
         any(kinds & 3u, fa, a); any((kinds >> 2) & 3u, fb, b);
-        SAF_FOR_P r.v[p] = dm::builtin2(imm, a.v[p], b.v[p]).v;
+        SAF_FOR_P r.v[p] = cold_builtin2(imm, a.v[p], b.v[p]);
         break;
     case U_G + G_BUILTIN3: {
         any(kinds & 3u, fa, a);
         Pt<P> x0;
         RF::load(my, (uint32_t)x0_off, x0);
         RF::load(my, (uint32_t)x1_off, c);
-        SAF_FOR_P r.v[p] = dm::builtin3(imm, x0.v[p], c.v[p], a.v[p]).v;
+        SAF_FOR_P r.v[p] = cold_builtin3(imm, x0.v[p], c.v[p], a.v[p]);
     } break;
     case U_G + G_BUILTIN4: {
         any(kinds & 3u, fa, a); any((kinds >> 2) & 3u, fb, b);
         Pt<P> x0;
         RF::load(my, (uint32_t)x0_off, x0);
         RF::load(my, (uint32_t)x1_off, c);
-        SAF_FOR_P r.v[p] = dm::builtin4(imm, x0.v[p], c.v[p], a.v[p], b.v[p]).v;
+        SAF_FOR_P r.v[p] = cold_builtin4(imm, x0.v[p], c.v[p], a.v[p], b.v[p]);
     } break;
     case U_G + G_ARG2: // stages two operands for the next Builtin3/4: ACC untouched
         any(kinds & 3u, fa, a); any((kinds >> 2) & 3u, fb, b);
@@ -288,10 +307,11 @@ __device__ __forceinline__ void stage_window(uint32_t win_sm, const unsigned cha
     __syncthreads();
 }
 
-template <int P, bool K_SMEM>
+template <int P, bool K_SMEM, bool WIDE4 = false>
 __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx_off, const unsigned char *img_g,
                                                    uint32_t pc_code, uint32_t it, uint32_t iters) {
-    using RF = Rf<P>;
+    static_assert(!WIDE4 || P == 4, "the wide layouts of one / two points per thread need no pair stride");
+    using RF = Rf<P, WIDE4>;
     const uint32_t my = RF::mine(smem32);
     const uint32_t ctx = smem32 + ctx_off;                           // BlockCtx
     const uint32_t k_sm = ctx + (uint32_t)sizeof(BlockCtx);           // constant table (K_SMEM)
@@ -420,7 +440,7 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
     case U_FQ + 2 * (Q) + F_ADDS: SAF_ENTER(U_FQ + 2 * (Q) + F_ADDS) { const uint32_t fs = FI; LS(c, fs) LOADS SAF_FOR_P { const double x = SRC.v[p]; acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(x, x)); } } SAF_NEXT(U_FQ + 2 * (Q) + F_ADDS)
 
 // t = S[a] + K[b], kept in the slot named by the kinds word when that is >= 0, then squared / scaled twice (uop.h U_FS)
-#define FSHEAD const int32_t d1_ = (int32_t)img32(cur + 24); LS(a, fa) { const double y_ = konst(fb); SAF_FOR_P a.v[p] = __dadd_rn(a.v[p], y_); } store_if<P>(my, d1_, a);
+#define FSHEAD const int32_t d1_ = (int32_t)img32(cur + 24); LS(a, fa) { const double y_ = konst(fb); SAF_FOR_P a.v[p] = __dadd_rn(a.v[p], y_); } store_if<P, WIDE4>(my, d1_, a);
 
 // sin / cos + "S[imm] + ACC" / "fma(S[imm], K[c], ACC)" (uop.h U_FT; P == 4 only, other layouts never receive them)
 #define FTBODY(TRIG, PRE, TAIL) if constexpr (P == 4) { const uint32_t fs = FI; LS(a, fa) LS(c, fs) PRE Pt<P> t_; TRIG(a.v, t_.v); TAIL }
@@ -545,7 +565,15 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
 #ifndef SAF_R_THREADED
 #define SAF_R_THREADED false
 #endif
+// The opt-in register machine (SAF_MACHINE=r) is compiled into a cubin of its own (Makefile: kernel_r.cubin, built
+// from this file with -DSAF_BUILD_R) that launch.cu loads only when it is asked for: its 775 handlers made the default
+// image 22.7 MB and cold instruction fetch is what a 1 M-point single pass pays for.
+#ifdef SAF_BUILD_R
 #include "kernel_r.cuh"
+#else
+template <bool K_SMEM, bool THREADED>
+__device__ unsigned long long hot_run_r(uint32_t, uint32_t, const unsigned char *, uint32_t, uint32_t, uint32_t); // never instantiated here
+#endif
 
 // ---- the kernel ------------------------------------------------------------------------------------------
 // RM: the register machine (ruop.h, kernel_r.cuh) runs the program; its image is packed by pack_r.cpp
@@ -554,9 +582,8 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
 // window and the constant table exist once)
 template <int P, bool K_SMEM, bool RM = false, bool WIDE = false>
 __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
-    static_assert(!WIDE || P <= 2, "the pair stride of the wider layouts is a compile-time constant");
     const uint32_t block_threads = WIDE ? blockDim.x : (uint32_t)BLOCK_THREADS;
-    using RF = Rf<P>;
+    using RF = Rf<P, WIDE && P == 4>;
     const uint32_t smem32 = smem_base32();
     const uint32_t my = RF::mine(smem32);
 
@@ -601,12 +628,12 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
             SAF_FOR_P v.v[p] = 0.0; // missing column reads as 0.0
             if (col != nullptr && len != 0ull) {
                 if constexpr (P == 1) {
-                    const unsigned long long i = point_index<P>(tile_base, 0);
+                    const unsigned long long i = point_index<P, WIDE>(tile_base, 0);
                     if (i < d.n_points) v.v[0] = ld_stream(col + (i < len ? i : len - 1));
                 } else {
 #pragma unroll
                     for (int g = 0; g < P / 2; ++g) {
-                        const unsigned long long i = point_index<P>(tile_base, 2 * g);
+                        const unsigned long long i = point_index<P, WIDE>(tile_base, 2 * g);
                         if (i + 1 < len && i + 1 < d.n_points) {
                             ld_stream2(col + i, v.v[2 * g], v.v[2 * g + 1]);
                         } else {
@@ -627,11 +654,11 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
             for (;;) {
                 unsigned long long st;
                 if constexpr (RM) st = hot_run_r<K_SMEM, SAF_R_THREADED>(smem32, ctx_off, d.image_global, pc, it, iters);
-                else st = hot_run<P, K_SMEM>(smem32, ctx_off, d.image_global, pc, it, iters);
+                else st = hot_run<P, K_SMEM, WIDE && P == 4>(smem32, ctx_off, d.image_global, pc, it, iters);
                 if (st == HOT_DONE) break;
                 pc = (uint32_t)st;
                 it = (uint32_t)(st >> 32);
-                cold_op<P, RM>(d.image_global, d.code_off + pc, d.acc_off, d.x0_off, d.x1_off);
+                cold_op<P, RM, WIDE>(d.image_global, d.code_off + pc, d.acc_off, d.x0_off, d.x1_off);
                 pc += UINSTR_BYTES;
             }
         }
@@ -647,12 +674,12 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
             }
             double *out = d.outs[k];
             if constexpr (P == 1) {
-                const unsigned long long i = point_index<P>(tile_base, 0);
+                const unsigned long long i = point_index<P, WIDE>(tile_base, 0);
                 if (i < d.n_points) st_stream(out + i, v.v[0]);
             } else {
 #pragma unroll
                 for (int g = 0; g < P / 2; ++g) {
-                    const unsigned long long i = point_index<P>(tile_base, 2 * g);
+                    const unsigned long long i = point_index<P, WIDE>(tile_base, 2 * g);
                     if (i + 1 < d.n_points) {
                         st_stream2(out + i, v.v[2 * g], v.v[2 * g + 1]);
                     } else if (i < d.n_points) {
@@ -670,27 +697,33 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
         interp_body<P, SM>(d);                                                                             \
     }
 // *_ksm: constant table staged in shared memory; *_kgm: read from global memory (very large tables)
-SAF_ENTRY(saf_interp_p4_ksm, 4, true, SAF_MINB_P4)
+#ifdef SAF_BUILD_R
 #define SAF_ENTRY_R(NAME, SM, MINB)                                                                        \
     extern "C" __global__ void __launch_bounds__(BLOCK_THREADS, MINB) NAME(const __grid_constant__ LaunchDesc d) { \
         interp_body<R_POINTS, SM, true>(d);                                                                \
     }
 SAF_ENTRY_R(saf_rinterp_ksm, true, SAF_MINB_R)
-#define SAF_ENTRY_W(NAME, SM)                                                                              \
+#else
+SAF_ENTRY(saf_interp_p4_ksm, 4, true, SAF_MINB_P4)
+#define SAF_ENTRY_W(NAME, P, SM)                                                                           \
     extern "C" __global__ void __launch_bounds__(WIDE_MAX_THREADS, 1) NAME(const __grid_constant__ LaunchDesc d) { \
-        interp_body<2, SM, false, true>(d);                                                                \
+        interp_body<P, SM, false, true>(d);                                                                \
     }
 #ifndef SAF_FAST_BUILD
 SAF_ENTRY(saf_interp_p4_kgm, 4, false, SAF_MINB_P4)
 SAF_ENTRY(saf_interp_p2_ksm, 2, true, SAF_MINB_P2)
 SAF_ENTRY(saf_interp_p2_kgm, 2, false, SAF_MINB_P2)
-SAF_ENTRY_W(saf_interp_p2w_ksm, true)
-SAF_ENTRY_W(saf_interp_p2w_kgm, false)
+SAF_ENTRY_W(saf_interp_p2w_ksm, 2, true)
+SAF_ENTRY_W(saf_interp_p2w_kgm, 2, false)
+SAF_ENTRY_W(saf_interp_p4w_ksm, 4, true)
+SAF_ENTRY_W(saf_interp_p4w_kgm, 4, false)
 SAF_ENTRY(saf_interp_p1_ksm, 1, true, SAF_MINB_P1)
 SAF_ENTRY(saf_interp_p1_kgm, 1, false, SAF_MINB_P1)
+#ifdef SAF_WITH_P8 // eight points per thread: a tuning experiment that lost on every workload; not shipped
 SAF_ENTRY(saf_interp_p8_ksm, 8, true, SAF_MINB_P8)
 SAF_ENTRY(saf_interp_p8_kgm, 8, false, SAF_MINB_P8)
 #endif
+#endif // SAF_FAST_BUILD
 
 // ---- FP64 pipe peak probe ---------------------------------------------------------------------------
 // The roofline of this path is the FP64 pipe (BASELINE.json north_star), whose peak is not in
@@ -760,5 +793,6 @@ saf_clifford_probe_kernel(double *xs, double *ys, unsigned long long n, int iter
         }
     }
 }
+#endif // !SAF_BUILD_R
 
 } // namespace saf

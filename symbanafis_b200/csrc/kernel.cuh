@@ -77,7 +77,8 @@ size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_
                               int block_threads = BLOCK_THREADS);
 // Threads of the wide one-block-per-SM layout (two points per thread) for a packed program with n_slots slots, or 0
 // when it would not hold more warps per SM than 128-thread blocks do.
-int wide_block_threads(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points);
+int wide_block_threads(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
+                       int points_per_thread = 2);
 
 // Per-block context behind the register file in shared memory: what hot_run needs besides the image.
 struct alignas(16) BlockCtx { // a multiple of 16 bytes: the constant table and the code window follow it

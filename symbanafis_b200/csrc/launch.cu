@@ -24,6 +24,15 @@ asm(".section .rodata\n"
     ".byte 0\n"
     ".previous\n");
 extern "C" const unsigned char saf_kernel_cubin[];
+// the register machine's image (SAF_MACHINE=r), loaded on first use only
+asm(".section .rodata\n"
+    ".global saf_kernel_r_cubin\n"
+    ".balign 16\n"
+    "saf_kernel_r_cubin:\n"
+    ".incbin \"" SAF_CUBIN_R_PATH "\"\n"
+    ".byte 0\n"
+    ".previous\n");
+extern "C" const unsigned char saf_kernel_r_cubin[];
 
 namespace saf {
 
@@ -40,10 +49,12 @@ struct Driver {
 
 struct DeviceModule {
     CUmodule mod = nullptr;
-    CUfunction interp[11] = {}; // [8] = register machine, [9] [10] = wide blocks (P = 2)
+    CUmodule mod_r = nullptr;   // register machine, loaded on first use
+    CUfunction interp[13] = {}; // [6] [7] = P = 8 (not shipped), [8] = register machine (from mod_r), [9] [10] = wide blocks P = 2, [11] [12] = wide blocks P = 4
     CUfunction peak = nullptr;
     CUfunction clifford_probe = nullptr;
     bool ready = false;
+    int smem_optin = 0;
 };
 DeviceModule g_modules[64];
 std::mutex g_module_mu;
@@ -88,14 +99,21 @@ cudaError_t module_for_current_device(DeviceModule **out) {
         }
         CUresult r = g_drv.module_load_data(&m.mod, saf_kernel_cubin);
         if (r != CUDA_SUCCESS) return as_cuda(r);
-        static const char *names[11] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
+        static const char *names[13] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
                                        "saf_interp_p1_ksm", "saf_interp_p1_kgm", "saf_interp_p8_ksm", "saf_interp_p8_kgm",
-                                       "saf_rinterp_ksm", "saf_interp_p2w_ksm", "saf_interp_p2w_kgm"};
+                                       "saf_rinterp_ksm", "saf_interp_p2w_ksm", "saf_interp_p2w_kgm",
+                                       "saf_interp_p4w_ksm", "saf_interp_p4w_kgm"};
         int optin = 0;
         e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e != cudaSuccess) return e;
-        for (int k = 0; k < 11; ++k) {
+        m.smem_optin = optin;
+        for (int k = 0; k < 13; ++k) {
+            if (k == 8) continue; // register machine: module_r_for()
             r = g_drv.module_get_function(&m.interp[k], m.mod, names[k]);
+            if (r == CUDA_ERROR_NOT_FOUND && (k == 6 || k == 7)) { // built without -DSAF_WITH_P8
+                m.interp[k] = nullptr;
+                continue;
+            }
             if (r != CUDA_SUCCESS) return as_cuda(r);
             // opt in to the full dynamic shared-memory carve-out
             r = g_drv.func_set_attribute(m.interp[k], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, optin);
@@ -111,18 +129,35 @@ cudaError_t module_for_current_device(DeviceModule **out) {
     return cudaSuccess;
 }
 
+// loads the register machine's cubin into the current device's module set (under g_module_mu)
+cudaError_t module_r_for(DeviceModule *m) {
+    std::lock_guard<std::mutex> lk(g_module_mu);
+    if (m->interp[8]) return cudaSuccess;
+    CUresult r = g_drv.module_load_data(&m->mod_r, saf_kernel_r_cubin);
+    if (r != CUDA_SUCCESS) return as_cuda(r);
+    CUfunction f = nullptr;
+    r = g_drv.module_get_function(&f, m->mod_r, "saf_rinterp_ksm");
+    if (r != CUDA_SUCCESS) return as_cuda(r);
+    r = g_drv.func_set_attribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->smem_optin);
+    if (r != CUDA_SUCCESS) return as_cuda(r);
+    m->interp[8] = f;
+    return cudaSuccess;
+}
+
 } // namespace
 
 
 cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape, cudaStream_t stream) {
     const int li = shape.points_per_thread == 4 ? 0 : shape.points_per_thread == 2 ? 1 : shape.points_per_thread == 1 ? 2 : 3;
     const bool wide = shape.block != BLOCK_THREADS;
-    if (wide && (shape.points_per_thread != 2 || shape.rmachine)) return cudaErrorInvalidConfiguration;
-    const int k = shape.rmachine ? 8 : wide ? (shape.k_in_smem ? 9 : 10) : 2 * li + (shape.k_in_smem ? 0 : 1);
+    if (wide && ((shape.points_per_thread != 2 && shape.points_per_thread != 4) || shape.rmachine)) return cudaErrorInvalidConfiguration;
+    const int k = shape.rmachine ? 8 : wide ? (shape.points_per_thread == 4 ? 11 : 9) + (shape.k_in_smem ? 0 : 1) : 2 * li + (shape.k_in_smem ? 0 : 1);
     if (shape.rmachine && !shape.k_in_smem) return cudaErrorInvalidConfiguration;
     DeviceModule *m = nullptr;
     cudaError_t e = module_for_current_device(&m);
     if (e != cudaSuccess) return e;
+    if (shape.rmachine && (e = module_r_for(m)) != cudaSuccess) return e;
+    if (!m->interp[k]) return cudaErrorInvalidConfiguration; // layout not in this build
     void *args[] = {const_cast<LaunchDesc *>(&desc)};
     return as_cuda(g_drv.launch(m->interp[k], (unsigned)shape.grid, 1, 1, (unsigned)shape.block, 1, 1,
                                 (unsigned)shape.smem_bytes, (CUstream)stream, args, nullptr));
@@ -181,31 +216,34 @@ cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long
     if (force_points_per_thread == 1 ||
         (aligned16 && (force_points_per_thread == 2 || force_points_per_thread == 4 || force_points_per_thread == 8)))
         P = force_points_per_thread;
+#ifndef SAF_WITH_P8
+    if (P == 8) P = 4; // the eight-points layout is not in the shipped image
+#endif
     while (P > 1 && !fits(P, 1)) P >>= 1;
     if (!fits(P, 1)) return cudaErrorInvalidConfiguration;
     *points_per_thread = P;
     return cudaSuccess;
 }
 
-int wide_block_threads(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points) {
+int wide_block_threads(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points, int P) {
     int sms = 0, smem_optin = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
     const size_t k_smem = k_bytes <= K_SMEM_MAX ? k_bytes : 0;
     // warps per SM with 128-thread blocks
-    const size_t small = interpreter_smem_bytes(n_slots, 2, k_smem, code_bytes);
+    const size_t small = interpreter_smem_bytes(n_slots, P, k_smem, code_bytes);
     size_t blocks = ((size_t)smem_optin + 1024) / (small + 1024);
-    if (blocks > (size_t)SAF_MINB_P2) blocks = SAF_MINB_P2;
+    if (blocks > (size_t)resident_blocks_for(P)) blocks = resident_blocks_for(P);
     const int warps_small = (int)blocks * (BLOCK_THREADS / 32);
     int threads = 0;
     for (int t = WIDE_MAX_THREADS; t > BLOCK_THREADS; t -= 32)
-        if (interpreter_smem_bytes(n_slots, 2, k_smem, code_bytes, t) <= (size_t)smem_optin) {
+        if (interpreter_smem_bytes(n_slots, P, k_smem, code_bytes, t) <= (size_t)smem_optin) {
             threads = t;
             break;
         }
     if (threads / 32 <= warps_small) return 0;
     // every SM must still get whole tiles to work on
-    if (n_points < (unsigned long long)sms * 2ull * (unsigned long long)threads * 2ull) return 0;
+    if (n_points < (unsigned long long)sms * 2ull * (unsigned long long)threads * (unsigned long long)P) return 0;
     return threads;
 }
 

@@ -31,9 +31,9 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
     out = PackedProgram();
     out.points_per_thread = P;
     out.block_threads = block_threads;
-    out.layout_id = block_threads == BLOCK_THREADS ? P : 2000 + block_threads;
-    if (block_threads != BLOCK_THREADS && (P > 2 || block_threads % 32 != 0 || block_threads > WIDE_MAX_THREADS)) {
-        err = "internal: wide blocks exist for one or two points per thread only";
+    out.layout_id = block_threads == BLOCK_THREADS ? P : 1000 * P + block_threads;
+    if (block_threads != BLOCK_THREADS && ((P != 2 && P != 4) || block_threads % 32 != 0 || block_threads > WIDE_MAX_THREADS)) {
+        err = "internal: wide blocks exist for two or four points per thread only";
         return SAF_ERR_INVALID_ARGUMENT;
     }
     const uint32_t SB = slot_bytes(P, block_threads);

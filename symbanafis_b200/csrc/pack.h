@@ -13,7 +13,7 @@ namespace saf {
 struct PackedProgram {
     int points_per_thread = 0;
     int block_threads = BLOCK_THREADS; // threads per block the slot stride was computed for
-    int layout_id = 0;                 // points_per_thread for the shared-memory machine, 100 + P for the register machine
+    int layout_id = 0;                 // points_per_thread (128-thread blocks), 1000 * P + threads (wide blocks), 100 + P (register machine)
     bool can_iterate = true;           // the image loops in-kernel (saf_iterate_*); register-machine images of programs
                                        // whose results do not pair with their parameters cannot
     // image = constant table (padded to 32 bytes), then the code: n_instr micro-instruction slots cut into
@@ -43,7 +43,7 @@ constexpr uint32_t slot_bytes(int points_per_thread, int block_threads = BLOCK_T
 // Returns 0 or SAF_ERR_UNSUPPORTED (err filled).
 // Register machine (ruop.h, pack_r.cpp): four points per thread, live values in real registers.
 int pack_program_r(const DeviceProgram &dp, PackedProgram &out, std::string &err);
-// block_threads != BLOCK_THREADS: the wide one-block-per-SM layout (points_per_thread <= 2), layout_id = 2000 + threads.
+// block_threads != BLOCK_THREADS: the wide one-block-per-SM layout (two or four points per thread), layout_id = 1000 * P + threads.
 int pack_program(const DeviceProgram &dp, int points_per_thread, PackedProgram &out, std::string &err,
                  int block_threads = BLOCK_THREADS);
 

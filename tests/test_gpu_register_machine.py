@@ -45,11 +45,15 @@ from symbanafis_b200 import workloads
 from symbanafis_b200._lib import DeviceProgramHandle
 w = workloads.get("terrain_gradient"); p = w.program
 h = DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size, p.result_regs)
-n = 600_001  # enough points for the wide one-block-per-SM layout, ragged last tile
+import torch
+n = 700_001  # one launch with enough points for the wide one-block-per-SM layouts (P = 4 and P = 2), ragged last tile
 cols = w.make_inputs(n, 8)
-res = [np.empty(n) for _ in p.result_regs]
-h.eval_host(cols, res, n)
-np.savez(sys.argv[1], **{{f"r{{k}}": r for k, r in enumerate(res)}})
+dev = torch.device("cuda", 0)
+tc = [torch.from_numpy(c).to(dev) for c in cols]
+to = [torch.empty(n, dtype=torch.float64, device=dev) for _ in p.result_regs]
+h.eval_device([t.data_ptr() for t in tc], [n] * len(tc), [t.data_ptr() for t in to], n)
+torch.cuda.synchronize()
+np.savez(sys.argv[1], **{{f"r{{k}}": t.cpu().numpy() for k, t in enumerate(to)}})
 """
 
 
@@ -59,12 +63,13 @@ def test_layout_and_fusion_knobs_do_not_change_results(tmp_path):
     # change HOW the same correctly rounded operations are dispatched
     outs = {}
     for tag, env in (("default", {}), ("narrow", {"SAF_WIDE": "0"}), ("unfused", {"SAF_FUSE": "0"}),
-                     ("p1", {"SAF_POINTS_PER_THREAD": "1"})):
+                     ("p1", {"SAF_POINTS_PER_THREAD": "1"}), ("p2wide", {"SAF_POINTS_PER_THREAD": "2"}),
+                     ("p2narrow", {"SAF_POINTS_PER_THREAD": "2", "SAF_WIDE": "0"}), ("sched_a", {"SAF_SCHED": "n"})):
         path = str(tmp_path / f"{tag}.npz")
         subprocess.run([sys.executable, "-c", _CHILD_WIDE.format(root=ROOT), path], check=True,
                        env=dict(os.environ, **env), timeout=900)
         outs[tag] = np.load(path)
-    for tag in ("narrow", "unfused", "p1"):
+    for tag in ("narrow", "unfused", "p1", "p2wide", "p2narrow", "sched_a"):
         for k in outs["default"].files:
             assert np.array_equal(outs["default"][k].view(np.uint64), outs[tag][k].view(np.uint64)), f"{tag}: {k} differs"
 

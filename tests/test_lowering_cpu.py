@@ -27,7 +27,7 @@ def _check(prog, cols, n, iters=1):
     for k, (r, g) in enumerate(zip(ref, got)):
         assert bits_equal(g, r), f"result {k} differs"
     # the packed micro-instruction image the kernel executes, for every register-file layout
-    for ppt in (1, 2, 4, 8, 2000 + 320):  # 2000 + T: two points per thread, one wide block of T threads per SM
+    for ppt in (1, 2, 4, 8, 2000 + 320, 4000 + 512):  # 1000 * P + T: P points per thread, one wide block of T threads per SM
         got = run_packed_program(h.export_packed(ppt), cols, n, iters)
         for k, (r, g) in enumerate(zip(ref, got)):
             assert bits_equal(g, r), f"packed image (P={ppt}): result {k} differs"

@@ -42,6 +42,29 @@ def main():
     print("exp: max |Q - f| * r^2 =", mp.nstr(err * L * L, 5))
     print("kE = {" + ", ".join("%.17e" % float(x) for x in c) + "}")
 
+    # sincos with one reduction (leanmath.cuh sincos_fast): |r| <= 1.0002 pi/4, degree-5 S and C in z
+    Zq = (mp.pi / 4 * mp.mpf("1.0002")) ** 2
+
+    def fc(z):
+        if z < mp.mpf("1e-20"):
+            return mp.mpf(1) / 24
+        r = mp.sqrt(z)
+        return (mp.cos(r) - 1 + z / 2) / (z * z)
+
+    c = cheb_fit(fs, 0, Zq, 6)
+    err = max(abs(mp.polyval(list(reversed(c)), z) - fs(z)) for z in mp.linspace(0, Zq, 2000))
+    print("sincos S: max |S - f| * z =", mp.nstr(err * Zq, 5))
+    print("kQuad[4..9] = {" + ", ".join("%.17e" % float(x) for x in c) + "}")
+    c = cheb_fit(fc, 0, Zq, 6)
+    err = max(abs(mp.polyval(list(reversed(c)), z) - fc(z)) for z in mp.linspace(0, Zq, 2000))
+    print("sincos C: max |C - f| * z^2 =", mp.nstr(err * Zq * Zq, 5))
+    print("kQuad[10..15] = {" + ", ".join("%.17e" % float(x) for x in c) + "}")
+    h = mp.pi / 2
+    ha = float(h)
+    hb = float(np.nextafter(float(h - mp.mpf(ha)), 0.0))
+    hc = float(h - mp.mpf(ha) - mp.mpf(hb))
+    print("kQuad[0..3] = {%.17e, %.17e, %.17e, %.17e}" % (float(2 / mp.pi), ha, hb, hc))
+
     pa = float(mp.pi)
     pb = float(np.nextafter(float(mp.pi - mp.mpf(pa)), 0.0))
     pc = float(mp.pi - mp.mpf(pa) - mp.mpf(pb))

@@ -70,6 +70,32 @@ static double lean_exp(double x) {
     return from_bits(bits(p) + ((uint64_t)(int64_t)k << 52));
 }
 
+/* sincos with ONE reduction (leanmath.cuh sincos_fast): k = rint(x * 2/pi), r = x - k pi/2, |r| <= pi/4; sin r and cos r
+ * from two degree-5 polynomials in z = r^2; the quadrant swaps / negates them.  20 FP64 operations for both values. */
+static const double TWO_OVER_PI = 6.36619772367581382e-01;
+static const double PIO2_A = 1.57079632679489656e+00, PIO2_B = 6.12323399573676480e-17, PIO2_C = 1.08285667392191403e-32;
+static const double QS[] = {-1.66666666666666657e-01, 8.33333333333094450e-03, -1.98412698367513636e-04,
+                            2.75573160988126868e-06, -2.50511310657360491e-08, 1.59180731629230736e-10};
+static const double QC[] = {4.16666666666666644e-02, -1.38888888888873932e-03, 2.48015872987611761e-05,
+                            -2.75573172693902722e-07, 2.08761457809035442e-09, -1.13825973098618771e-11};
+static void lean_sincos(double x, double *sn, double *cs) {
+    const double t = fma(x, TWO_OVER_PI, MAGIC);
+    const uint32_t q = (uint32_t)bits(t);
+    const double kd = t - MAGIC;
+    double r = fma(kd, -PIO2_A, x);
+    r = fma(kd, -PIO2_B, r);
+    r = fma(kd, -PIO2_C, r);
+    const double z = r * r;
+    double ps = QS[5], pc = QC[5];
+    for (int i = 4; i >= 0; --i) { ps = fma(ps, z, QS[i]); pc = fma(pc, z, QC[i]); }
+    double s = fma(r * z, ps, r);
+    s = from_bits((bits(s) & 0x7fffffffffffffffull) | (bits(r) & 0x8000000000000000ull)); /* sign of r, also for -0 */
+    const double c = fma(z, fma(z, pc, -0.5), 1.0);
+    const double a = (q & 1u) ? c : s, b = (q & 1u) ? s : c; /* odd quadrant: swap */
+    *sn = from_bits(bits(a) ^ ((uint64_t)((q >> 1) & 1u) << 63));
+    *cs = from_bits(bits(b) ^ ((uint64_t)(((q + 1u) >> 1) & 1u) << 63));
+}
+
 static double ulp_of(double ref) {
     int e;
     frexp(ref, &e);
@@ -106,6 +132,45 @@ int main(void) {
         printf("|x| < %-10g  sin: %.3f ulp (true)  %.0f ulp vs glibc   cos: %.3f ulp (true)  %.0f ulp vs glibc\n",
                ranges[ri][1], ws, gs, wc, gc);
         if (ws > 2.5 || wc > 2.5) fail = 1;
+    }
+    for (unsigned ri = 0; ri < sizeof ranges / sizeof ranges[0]; ++ri) {
+        double ws = 0, wc = 0, gs = 0, gc = 0;
+        for (int i = 0; i < 4000000; ++i) {
+            double x = ranges[ri][0] + (ranges[ri][1] - ranges[ri][0]) * rnd(&s);
+            if (i & 1) x = -x;
+            double sn, cs;
+            lean_sincos(x, &sn, &cs);
+            const double e1 = ulp_err(sn, sinl((long double)x)), e2 = ulp_err(cs, cosl((long double)x));
+            const double g1 = fabs(sn - sin(x)) / ulp_of(sin(x)), g2 = fabs(cs - cos(x)) / ulp_of(cos(x));
+            if (e1 > ws) ws = e1;
+            if (e2 > wc) wc = e2;
+            if (g1 > gs) gs = g1;
+            if (g2 > gc) gc = g2;
+        }
+        printf("sincos |x| < %-10g  sin: %.3f ulp (true)  %.0f ulp vs glibc   cos: %.3f ulp (true)  %.0f ulp vs glibc\n",
+               ranges[ri][1], ws, gs, wc, gc);
+        if (ws > 2.5 || wc > 2.5) fail = 1;
+    }
+    {
+        double ws2 = 0, wc2 = 0;
+        for (int k = -700000; k <= 700000; ++k) {
+            const double c = (double)((long double)k * 1.57079632679489661923132169163975144L);
+            for (int d = -2; d <= 2; ++d) {
+                double x = c, sn, cs;
+                for (int j = 0; j < abs(d); ++j) x = nextafter(x, d > 0 ? INFINITY : -INFINITY);
+                lean_sincos(x, &sn, &cs);
+                const double e1 = ulp_err(sn, sinl((long double)x)), e2 = ulp_err(cs, cosl((long double)x));
+                if (e1 > ws2) ws2 = e1;
+                if (e2 > wc2) wc2 = e2;
+            }
+        }
+        printf("sincos next to k*pi/2, |k| <= 7e5: sin %.3f ulp, cos %.3f ulp\n", ws2, wc2);
+        if (ws2 > 2.5 || wc2 > 2.5) fail = 1;
+        double sn, cs;
+        lean_sincos(-0.0, &sn, &cs);
+        if (!signbit(sn) || cs != 1.0) fail = 1;
+        lean_sincos(5e-324, &sn, &cs);
+        if (sn != 5e-324 || cs != 1.0) fail = 1;
     }
     /* points next to multiples of pi/2 (worst cancellation) */
     double ws = 0, wc = 0;
