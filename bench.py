@@ -1,19 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- f64 point-evals/s of the SymbAnaFis batch evaluator on B200 (BASELINE.json metric).
 
-A "step" is one pass of the hot path over one batch of synthetic input.  Default workload =
-BASELINE.json configs[1]: the Clifford attractor map, 1M particles x 1000 iterations per GPU, i.e. one
-step = 1e9 point-evals per GPU (one point-eval = the whole 2-output program on one particle).
+A "step" is one pass of the hot path over one batch of synthetic input.  Headline workload = BASELINE.json
+configs[1]: the Clifford attractor map, 1M particles x 1000 iterations per GPU, i.e. one step = 1e9 point-evals per
+GPU (one point-eval = the whole 2-output program on one particle).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-N > 1 is launched by torchrun (one rank per GPU); points are sharded per rank, there is no collective
-on the data path, the timing is the max over ranks.  Rank 0 prints ONE JSON line.
+The ONE JSON line rank 0 prints carries, besides the headline workload at the top level:
+  "workloads"  : the other four BASELINE.json configs (single_expr, aizawa, double_pendulum, terrain_gradient), each
+                 with ms_per_step, value, roofline{bound, frac, traffic}, e2e, e2e_pageable, cpu_baseline  (N = 1)
+  "c5_sharded" : BASELINE.json configs[4] as north_star states it -- 100 M points of ONE seeded global array cut into N
+                 contiguous shards, one rank per GPU through saf_eval_host, and once from rank 0 alone through
+                 saf_eval_host_multi (one host thread + stream set per device, host gather included)
 
-`value`  : device-timed (CUDA events on the launching stream), columns resident in HBM.
-`e2e`    : the same step through the C-ABI host call (saf_iterate_host / saf_eval_host) with pinned
-           HOST buffers: H2D of the inputs and D2H of the results inside the timed region.
-`--impl reference`: the reference's CPU algorithm (oracle port, all host threads) on a bounded sample.
+N > 1 is launched by torchrun (one rank per GPU); points are sharded per rank, there is no collective on the data path
+(SURVEY.md section 8e), every timing is the max over ranks.
+
+`value`        : device-timed (CUDA events on the launching stream), columns resident in HBM, L2 flushed between steps.
+`e2e`          : the same step through the C-ABI host call (saf_iterate_host / saf_eval_host) with pinned HOST buffers:
+                 H2D of the inputs and D2H of the results inside the timed region.
+`e2e_pageable` : the same with ordinary (pageable) NumPy arrays -- what a caller of the reference holds.
+`--impl reference`: the reference's CPU algorithm (oracle port of the f64x4 + 256-point-chunk path, all host threads)
+                 on a bounded sample of the same workload; same `config` object, byte for byte.
 """
 from __future__ import annotations
 
@@ -33,6 +42,9 @@ import numpy as np  # noqa: E402
 
 METRIC = "f64 point-evals/sec"
 UNIT = "point-evals/s"
+HEADLINE = "clifford"
+OTHER_WORKLOADS = ("single_expr", "aizawa", "double_pendulum", "terrain_gradient")
+C5_TOTAL_POINTS = 100_000_000
 
 
 def parse_args():
@@ -41,10 +53,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="clifford")
+    ap.add_argument("--workload", default=HEADLINE)
     ap.add_argument("--points", type=int, default=0, help="points per GPU (0 = BASELINE.json size)")
     ap.add_argument("--iters", type=int, default=0, help="map iterations per step (0 = BASELINE.json value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="headline workload only (profiling runs)")
+    ap.add_argument("--no-c5-sharded", action="store_true")
+    ap.add_argument("--c5-points", type=int, default=C5_TOTAL_POINTS, help="total points of the sharded C5 run")
     return ap.parse_args()
 
 
@@ -56,7 +71,7 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -116,288 +131,454 @@ def load_peaks():
 
 
 def measured_traffic(workload_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the interpreter launch from the committed ncu capture
-    (profiles/r01_dram_traffic.json), or None when that workload has not been captured."""
-    path = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
-    try:
-        with open(path) as f:
-            t = json.load(f).get(workload_name)
-        return None if t is None else t["dram_bytes_read"] + t["dram_bytes_write"]
-    except (OSError, ValueError, KeyError):
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum of the interpreter launch from the committed ncu captures of the
+    shipped build (profiles/r02_dram_traffic.json), or None when that workload has not been captured."""
+    for name in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f).get(workload_name)
+            if t is not None:
+                return t["dram_bytes_read"] + t["dram_bytes_write"], f"profiles/{name}"
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, None
 
 
-def workload_setup(args):
-    from symbanafis_b200 import workloads
-    w = workloads.get(args.workload)
-    n = args.points or w.n_points
-    iters = args.iters or (w.iterations if w.iterated else 1)
-    return w, n, iters
+def workload_sizes(w, args, headline: bool):
+    n = (args.points if headline and args.points else w.n_points)
+    iters = (args.iters if headline and args.iters else (w.iterations if w.iterated else 1))
+    return n, iters
 
 
-def cpu_baseline(w, n, iters, budget_s=12.0):
-    """The oracle port (256-point chunks over all host cores) on a bounded sample of the same workload."""
+def config_for(w, n, iters, world):
+    """The workload's identity -- the SAME object in the GPU arm and in the reference arm."""
+    return {
+        "workload": f"{w.name}: {w.description}",
+        "points_per_gpu": n, "iterations_per_step": iters, "point_evals_per_step": n * iters * world,
+        "l2": "GPU arm: flushed between timed steps (256 MiB fill)",
+        "sharding": "one rank per GPU, each rank its own shard, no collective",
+    }
+
+
+# ---- the CPU legs (oracle: test infrastructure; timed here as the reported baseline, never the product) -------------
+def cpu_leg(w, n, iters, budget_s, steps=1, warmup=0):
+    """The reference's eval_f64 path restated (f64x4 body, 256-point chunks, one workspace per thread:
+    oracle/saf_oracle_simd.c) on all host threads, on a bounded sample of the workload."""
     import oracle
     from oracle import OracleProgram
     op = OracleProgram.from_program(w.program)
     cores = oracle.online_cores()
     n_s = min(n, 1_000_000)
     cols = w.make_inputs(n_s, 1)
-    # calibrate on a small run, then size the sample for ~budget_s of CPU work
-    t0 = time.perf_counter()
+    t0 = time.perf_counter()  # calibration
     if w.iterated:
-        op.iterate(cols, 2, cores)
+        op.iterate(cols, 2, cores, simd=True)
     else:
-        op.run_chunked(cols, n_s, cores)
-    dt = time.perf_counter() - t0
+        op.run_chunked_simd(cols, n_s, cores)
+    dt = max(time.perf_counter() - t0, 1e-6)
     per_unit = dt / (n_s * (2 if w.iterated else 1))
-    if w.iterated:
-        it_s = int(max(2, min(iters, budget_s / max(per_unit * n_s, 1e-9))))
-        t0 = time.perf_counter()
-        op.iterate(cols, it_s, cores)
-        dt = time.perf_counter() - t0
-        units = n_s * it_s
-        sample = f"{n_s} points x {it_s} iterations of {w.name}"
-    else:
-        reps = int(max(1, min(50, budget_s / max(per_unit * n_s, 1e-9))))
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            op.run_chunked(cols, n_s, cores)
-        dt = time.perf_counter() - t0
-        units = n_s * reps
-        sample = f"{reps} passes over {n_s} points of {w.name}"
-    return {"value": units / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-            "seconds": round(dt, 3)}
+    it_s = int(max(2, min(iters, budget_s / max(per_unit * n_s, 1e-9)))) if w.iterated else 1
+    reps = 1 if w.iterated else int(max(1, min(200, budget_s / max(per_unit * n_s, 1e-9))))
+    state = [c.copy() for c in cols]
+
+    def step():
+        if w.iterated:
+            for s, c in zip(state, cols):
+                s[:] = c
+            op.iterate(state, it_s, cores, simd=True, in_place=True)
+        else:
+            for _ in range(reps):
+                op.run_chunked_simd(cols, n_s, cores)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    units = n_s * (it_s if w.iterated else reps) * steps
+    sample = (f"{n_s} points x {it_s} iterations per step" if w.iterated else f"{reps} passes over {n_s} points per step")
+    kind = "port-f64x4" if oracle.has_simd() else "port"
+    return {"value": units / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + f" of {w.name}",
+            "seconds": round(dt, 3)}, dt / steps
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    w, n, iters = workload_setup(args)
-    import oracle
-    from oracle import OracleProgram
-    op = OracleProgram.from_program(w.program)
-    cores = oracle.online_cores()
-    n_s = min(n, 1_000_000)
-    cols = w.make_inputs(n_s, 1)
-    # size one step for about 2 s of CPU work
-    t0 = time.perf_counter()
-    if w.iterated:
-        op.iterate(cols, 1, cores)
-    else:
-        op.run_chunked(cols, n_s, cores)
-    dt = max(time.perf_counter() - t0, 1e-6)
-    it_s = int(max(1, min(iters, 2.0 / dt))) if w.iterated else 1
-    reps = 1 if w.iterated else int(max(1, min(20, 2.0 / dt)))
-
-    def step():
-        if w.iterated:
-            op.iterate(cols, it_s, cores)
-        else:
-            for _ in range(reps):
-                op.run_chunked(cols, n_s, cores)
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    units = n_s * (it_s if w.iterated else reps)
-    value = units * args.steps / dt
-    sample = (f"{n_s} points x {it_s} iterations per step" if w.iterated else f"{reps} passes over {n_s} points per step")
+    from symbanafis_b200 import workloads
+    w = workloads.get(args.workload)
+    n, iters = workload_sizes(w, args, True)
+    cb, step_s = cpu_leg(w, n, iters, budget_s=2.0, steps=args.steps, warmup=args.warmup)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{w.name}: {w.description}", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of the reference interpreter (oracle/), all host cores; the Rust reference "
-                "cannot be built in this image (no cargo/rustc)",
+        "config": config_for(w, n, iters, max(1, args.gpus)),
+        "sample": cb["sample"],
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference's eval_f64 path (oracle/: f64x4 body + 256-point chunks, all host "
+                "threads); the Rust reference cannot be built in this image (no cargo/rustc)",
     }))
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+# ---- the GPU arm -----------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from symbanafis_b200 import _lib
+        self.torch, self.dist, self._lib, self.args = torch, dist, _lib, args
+        self.rank, self.world, self.local = dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the evaluator has no CPU path")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.cpu_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            # a barrier that keeps the waiting ranks' GPUs idle (an NCCL barrier spins in a kernel): used while rank 0
+            # alone drives all devices through saf_eval_host_multi
+            self.cpu_group = dist.new_group(backend="gloo")
+        self.flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=self.dev)  # 256 MiB > 126 MB L2
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.fp64_peak = _lib.measure_fp64_peak()  # DFMA lane-instr/s, measured live on this GPU
+        self.hbm_gbs, self.peak_src = load_peaks()
 
-    from symbanafis_b200 import _lib
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
 
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the evaluator has no CPU path")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def max_over_ranks(self, vals):
+        from symbanafis_b200.sharding import max_over_ranks
+        return max_over_ranks(vals, device=self.dev)
 
-    w, n, iters = workload_setup(args)
-    p = w.program
-    h = _lib.DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size, p.result_regs)
-    info = h.info()
-    n_state = p.param_count
-    n_out = len(p.result_regs)
+    def handle(self, w):
+        p = w.program
+        return self._lib.DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size,
+                                                    p.result_regs)
 
-    # synthetic inputs: each rank owns its own contiguous shard of the global point set
-    cols_np = w.make_inputs(n, 1 + rank)
-    cols0 = [torch.from_numpy(c).to(dev) for c in cols_np]
-    state = [c.clone() for c in cols0]
-    outs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(n_out)]
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MiB > 126 MB L2
-    stream = torch.cuda.current_stream(dev)
+    # one workload, device-resident columns: K timed steps, CUDA events on the launching stream
+    def device_timed(self, h, w, cols_np, n, iters, steps, warmup):
+        torch = self.torch
+        cols0 = [torch.from_numpy(c).to(self.dev) for c in cols_np]
+        n_out = len(w.program.result_regs)
+        state = [c.clone() for c in cols0] if w.iterated else None
+        outs = None if w.iterated else [torch.empty(n, dtype=torch.float64, device=self.dev) for _ in range(n_out)]
+        s = self.stream.cuda_stream
 
-    def device_step():
-        if w.iterated:
-            for s, c in zip(state, cols0):
-                s.copy_(c)
-            h.iterate_device([s.data_ptr() for s in state], n, iters, stream=stream.cuda_stream)
+        def launch():
+            if w.iterated:
+                h.iterate_device([t.data_ptr() for t in state], n, iters, stream=s)
+            else:
+                h.eval_device([c.data_ptr() for c in cols0], [n] * len(cols0), [o.data_ptr() for o in outs], n, stream=s)
+
+        def reset():
+            if w.iterated:
+                for t, c in zip(state, cols0):
+                    t.copy_(c)
+
+        for _ in range(max(3, warmup)):
+            reset()
+            launch()
+        self.barrier()
+        launches0 = self._lib.kernel_launch_count()
+        ms = []
+        t_wall0 = time.perf_counter()
+        for _ in range(steps):
+            self.flush.fill_(1.0)  # evict L2 between timed steps (not timed)
+            reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            launch()
+            e1.record(self.stream)
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        self.barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = self._lib.kernel_launch_count() - launches0
+        # sustained: back-to-back steps for >= 2 s (no flush, no host sync in between): clocks under a long load
+        sustained = None
+        if w.name == HEADLINE and not self.args.no_workloads:
+            per = max(sum(ms) / len(ms), 1e-3)
+            k = int(min(2000, max(10, 2200.0 / per)))
+            reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            for _ in range(k):
+                launch()
+            e1.record(self.stream)
+            e1.synchronize()
+            t = e0.elapsed_time(e1)
+            sustained = {"steps": k, "seconds": t * 1e-3, "ms_per_step": t / k,
+                         "note": "back-to-back launches, no L2 flush or host sync in between"}
+        return sum(ms) / len(ms), t_wall, launches, sustained
+
+    # the host-buffer C-ABI call: H2D of the inputs and D2H of the results inside the timed region
+    def e2e_timed(self, h, w, cols_np, n, iters, steps, pinned: bool):
+        torch = self.torch
+        n_out = len(w.program.result_regs)
+        if pinned:
+            t_in = [torch.from_numpy(c).pin_memory() for c in cols_np]
+            ins = [t.numpy() for t in t_in]
+            t_state = [torch.empty_like(t).pin_memory() for t in t_in] if w.iterated else None
+            t_out = None if w.iterated else [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(n_out)]
+            state = [t.numpy() for t in t_state] if w.iterated else None
+            outs = None if w.iterated else [t.numpy() for t in t_out]
         else:
-            h.eval_device([c.data_ptr() for c in cols0], [n] * n_state, [o.data_ptr() for o in outs], n,
-                          stream=stream.cuda_stream)
+            ins = [np.array(c, copy=True) for c in cols_np]
+            state = [np.empty_like(c) for c in ins] if w.iterated else None
+            outs = None if w.iterated else [np.empty(n) for _ in range(n_out)]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        def step(timed):
+            if w.iterated:
+                for s_, c in zip(state, ins):
+                    s_[:] = c
+            t0 = time.perf_counter()
+            if w.iterated:
+                h.iterate_host(state, iters)
+            else:
+                h.eval_host(ins, outs, n)
+            return time.perf_counter() - t0
 
-    fp64_peak = _lib.measure_fp64_peak()  # DFMA lane-instr/s, measured live on this GPU
-    ideal = None
-    if rank == 0 and w.name == "clifford":
-        # the same map hard-coded around the same sin/cos kernels, no interpreter: what interpretation costs
-        t_ideal = _lib.measure_clifford_probe(n, iters)
-        ideal = {"kernel": "saf_clifford_probe_kernel (hard-coded map, state in registers, same launch shape)",
-                 "ms_per_step": 1e3 * t_ideal, "value": n * iters / t_ideal, "unit": UNIT}
+        for _ in range(2):
+            step(False)
+        self.barrier()
+        ts = [step(True) for _ in range(steps)]
+        self.barrier()
+        return 1e3 * sum(ts) / len(ts)
 
-    for _ in range(max(3, args.warmup)):
-        device_step()
-    barrier()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = _lib.kernel_launch_count()
-    kernel_ms = []
-    barrier()
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1.0)  # evict L2 between timed steps (not timed)
-        if w.iterated:
-            for s, c in zip(state, cols0):
-                s.copy_(c)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        if w.iterated:
-            h.iterate_device([s.data_ptr() for s in state], n, iters, stream=stream.cuda_stream)
-        else:
-            h.eval_device([c.data_ptr() for c in cols0], [n] * n_state, [o.data_ptr() for o in outs], n,
-                          stream=stream.cuda_stream)
-        e1.record(stream)
-        e1.synchronize()
-        kernel_ms.append(e0.elapsed_time(e1))
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = _lib.kernel_launch_count() - launches0
-    step_ms = sum(kernel_ms) / len(kernel_ms)
-
-    # ---- e2e: the host-buffer C-ABI call, pinned memory, copies inside the timed region ----
-    pinned_in = [torch.from_numpy(c).pin_memory() for c in cols_np]
-    pinned_state = [torch.empty_like(t).pin_memory() for t in pinned_in]
-    pinned_out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(n_out)]
-
-    def host_step():
-        if w.iterated:
-            for s, c in zip(pinned_state, pinned_in):
-                s.copy_(c)
-            h.iterate_host([s.numpy() for s in pinned_state], iters)
-        else:
-            h.eval_host([c.numpy() for c in pinned_in], [o.numpy() for o in pinned_out], n)
-
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        host_step()
-    barrier()
-    e2e_s = []
-    for _ in range(e2e_steps):
-        if w.iterated:
-            for s, c in zip(pinned_state, pinned_in):
-                s.copy_(c)
-        t0 = time.perf_counter()
-        if w.iterated:
-            h.iterate_host([s.numpy() for s in pinned_state], iters)
-        else:
-            h.eval_host([c.numpy() for c in pinned_in], [o.numpy() for o in pinned_out], n)
-        e2e_s.append(time.perf_counter() - t0)
-    barrier()
-    e2e_ms = 1e3 * sum(e2e_s) / len(e2e_s)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- max over ranks ----
-    from symbanafis_b200.sharding import max_over_ranks
-    step_ms, e2e_ms, t_wall = max_over_ranks([step_ms, e2e_ms, t_wall], device=dev)
-
-    units_per_step_gpu = n * iters
-    units_per_step = units_per_step_gpu * world
-    value = units_per_step / (step_ms * 1e-3)
-    e2e_value = units_per_step / (e2e_ms * 1e-3)
-
-    if rank == 0:
-        hbm_gbs, peak_src = load_peaks()
-        bytes_launch = info.bytes_per_point * n                # columns read + written once per launch
-        slots_launch = info.fp64_slots * units_per_step_gpu    # FP64 issue slots per launch
-        t_hbm = bytes_launch / (hbm_gbs * 1e9)
-        t_fp64 = slots_launch / fp64_peak if fp64_peak > 0 else 0.0
+    def roofline(self, info, w, n, iters, step_ms, full_size):
+        bytes_launch = info.bytes_per_point * n               # columns read + written once per launch
+        slots_launch = info.fp64_slots * n * iters            # FP64 issue slots per launch
+        t_hbm = bytes_launch / (self.hbm_gbs * 1e9)
+        t_fp64 = slots_launch / self.fp64_peak if self.fp64_peak > 0 else 0.0
         dur = step_ms * 1e-3
+        traffic, traffic_src = measured_traffic(w.name) if full_size else (None, None)
         if t_fp64 >= t_hbm:
-            achieved = 2.0 * slots_launch / dur / 1e12
-            peak = 2.0 * fp64_peak / 1e12
-            roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak if peak else None,
-                        "traffic": measured_traffic(w.name) if (n == w.n_points) else None,
-                        "traffic_unit": "DRAM bytes per launch (ncu --set full capture, profiles/r01_dram_traffic.json)",
-                        "peak_source": "DFMA-chain probe measured in this run (saf_measure_fp64_peak); "
-                                       "FP64 is not in MEASURED_PEAKS.json",
-                        "algorithmic": f"{info.fp64_slots:g} FP64 issue slots/point-eval (FMA = 2 FLOP) x "
-                                       f"{units_per_step_gpu} point-evals/launch",
-                        "hbm_leg": {"achieved_gbs": bytes_launch / dur / 1e9, "peak_gbs": hbm_gbs,
-                                    "peak_source": peak_src}}
-        else:
-            achieved = bytes_launch / dur / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                        "frac": achieved / hbm_gbs, "traffic": measured_traffic(w.name) if (n == w.n_points) else None,
-                        "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
-                        "algorithmic": f"{info.bytes_per_point:g} B/point x {n} points/launch",
-                        "fp64_leg": {"achieved_tflops": 2.0 * slots_launch / dur / 1e12,
-                                     "peak_tflops": 2.0 * fp64_peak / 1e12}}
-        cb = None
-        if not args.no_cpu_baseline:
-            cb = cpu_baseline(w, n, iters)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"{w.name}: {w.description}",
-                "points_per_gpu": n, "iterations_per_step": iters, "point_evals_per_step": units_per_step,
-                "l2": "flushed between timed steps (256 MiB fill)",
-                "device_program": {"instructions": info.n_dev_instructions, "slots": info.n_slots,
-                                   "constants": info.n_consts, "acc_forwards": info.n_acc_forwards},
-                "sharding": "one rank per GPU, each rank its own shard, no collective",
-            },
-            "roofline": roofline,
-            "ideal_kernel": ideal,
-            "cpu_baseline": cb,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": 8 * n * n_state * world, "d2h_bytes_per_step": 8 * n * n_out * world,
-                    "api": "saf_iterate_host" if w.iterated else "saf_eval_host", "host_memory": "pinned"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "wall_s_timed_region": t_wall,
+            achieved, peak = 2.0 * slots_launch / dur / 1e12, 2.0 * self.fp64_peak / 1e12
+            return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak if peak else None, "traffic": traffic,
+                    "traffic_unit": f"DRAM bytes per launch (ncu --set full capture, {traffic_src})",
+                    "peak_source": "DFMA-chain probe measured in this run (saf_measure_fp64_peak); "
+                                   "FP64 is not in MEASURED_PEAKS.json",
+                    "algorithmic": f"{info.fp64_slots:g} FP64 issue slots/point-eval (FMA = 2 FLOP) x "
+                                   f"{n * iters} point-evals/launch",
+                    "hbm_leg": {"achieved_gbs": bytes_launch / dur / 1e9, "peak_gbs": self.hbm_gbs,
+                                "peak_source": self.peak_src}}
+        achieved = bytes_launch / dur / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": self.hbm_gbs, "unit": "GB/s",
+                "frac": achieved / self.hbm_gbs, "traffic": traffic,
+                "traffic_unit": f"DRAM bytes per launch (ncu --set full capture, {traffic_src})",
+                "peak_source": f"MEASURED_PEAKS.json ({self.peak_src})",
+                "algorithmic": f"{info.bytes_per_point:g} B/point x {n} points/launch",
+                "fp64_leg": {"achieved_tflops": 2.0 * slots_launch / dur / 1e12,
+                             "peak_tflops": 2.0 * self.fp64_peak / 1e12}}
+
+    def measure(self, w, n, iters, steps, warmup, seed, cpu_budget_s, headline):
+        """Everything for one workload; returns the dict rank 0 prints (None on other ranks)."""
+        h = self.handle(w)
+        info = h.info()
+        n_state, n_out = w.program.param_count, len(w.program.result_regs)
+        cols_np = w.make_inputs(n, seed)
+        step_ms, t_wall, launches, sustained = self.device_timed(h, w, cols_np, n, iters, steps, warmup)
+        e2e_steps = max(2, min(steps, 5))
+        e2e_ms = self.e2e_timed(h, w, cols_np, n, iters, e2e_steps, pinned=True)
+        e2e_pg_ms = self.e2e_timed(h, w, cols_np, n, iters, e2e_steps, pinned=False)
+        step_ms, e2e_ms, e2e_pg_ms, t_wall = self.max_over_ranks([step_ms, e2e_ms, e2e_pg_ms, t_wall])
+        if self.rank != 0:
+            return None
+        units = n * iters * self.world
+        api = "saf_iterate_host" if w.iterated else "saf_eval_host"
+        io = {"h2d_bytes_per_step": 8 * n * n_state * self.world, "d2h_bytes_per_step": 8 * n * n_out * self.world, "api": api}
+        out = {
+            "ms_per_step": step_ms, "value": units / (step_ms * 1e-3), "unit": UNIT, "steps": steps,
+            "config": config_for(w, n, iters, self.world),
+            "device_program": {"instructions": info.n_dev_instructions, "slots": info.n_slots,
+                               "constants": info.n_consts, "acc_forwards": info.n_acc_forwards},
+            "roofline": self.roofline(info, w, n, iters, step_ms, n == w.n_points),
+            "e2e": dict(value=units / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, host_memory="pinned", **io),
+            "e2e_pageable": dict(value=units / (e2e_pg_ms * 1e-3), unit=UNIT, ms_per_step=e2e_pg_ms,
+                                 host_memory="pageable (NumPy arrays, staged through the library's pinned ring)", **io),
+            "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
         }
+        if sustained:
+            out["sustained"] = sustained
+        if headline and w.name == "clifford":
+            # the same map hard-coded around the same sin/cos kernels, no interpreter: what interpretation costs
+            t_ideal = self._lib.measure_clifford_probe(n, iters)
+            out["ideal_kernel"] = {"kernel": "saf_clifford_probe_kernel (hard-coded map, state in registers, same launch shape)",
+                                   "ms_per_step": 1e3 * t_ideal, "value": n * iters / t_ideal, "unit": UNIT}
+        out["cpu_baseline"] = None if self.args.no_cpu_baseline else cpu_leg(w, n, iters, cpu_budget_s)[0]
+        return out
+
+    # ---- BASELINE.json configs[4] as north_star states it: 100 M points sharded contiguously over the GPUs ----
+    def c5_sharded(self, total):
+        from symbanafis_b200 import workloads
+        from symbanafis_b200.sharding import shard_bounds
+        torch = self.torch
+        w = workloads.get("terrain_gradient")
+        h = self.handle(w)
+        info = h.info()
+        n_out = len(w.program.result_regs)
+        glob = w.make_inputs(total, 42)                      # ONE seeded global array, the same for every N
+        b, e = shard_bounds(total, self.world, self.rank)    # the split of saf_eval_host_multi and of batch.rs:55-74
+        n = e - b
+        shard = [np.ascontiguousarray(c[b:e]) for c in glob]
+        # device-timed shard
+        cols_d = [torch.from_numpy(c).to(self.dev) for c in shard]
+        outs_d = [torch.empty(n, dtype=torch.float64, device=self.dev) for _ in range(n_out)]
+        s = self.stream.cuda_stream
+        ms = []
+        for i in range(5):
+            self.flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            h.eval_device([c.data_ptr() for c in cols_d], [n] * len(cols_d), [o.data_ptr() for o in outs_d], n, stream=s)
+            e1.record(self.stream)
+            e1.synchronize()
+            if i >= 2:
+                ms.append(e0.elapsed_time(e1))
+        kernel_ms = sum(ms) / len(ms)
+        # every rank its shard through saf_eval_host (pinned and pageable host buffers), all ranks at once
+        pin_in = [torch.from_numpy(c).pin_memory() for c in shard]
+        pin_out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(n_out)]
+        pg_out = [np.empty(n) for _ in range(n_out)]
+
+        def timed(fn, reps=3):
+            fn()
+            ts = []
+            for _ in range(reps):
+                self.barrier()
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return 1e3 * sum(ts) / len(ts)
+
+        pinned_ms = timed(lambda: h.eval_host([t.numpy() for t in pin_in], [t.numpy() for t in pin_out], n))
+        pageable_ms = timed(lambda: h.eval_host(shard, pg_out, n))
+        # what the links alone deliver with every rank copying at once: names the limiter of the end-to-end numbers
+        d_tmp = torch.empty(n, dtype=torch.float64, device=self.dev)
+
+        def copies():
+            for t in pin_in:
+                d_tmp.copy_(t, non_blocking=True)
+            for t in pin_out:
+                t.copy_(d_tmp, non_blocking=True)
+            torch.cuda.synchronize(self.dev)
+
+        copy_ms = timed(copies)
+        same = all(np.array_equal(a.numpy().view(np.uint64), b_.view(np.uint64)) for a, b_ in zip(pin_out, pg_out))
+        kernel_ms, pinned_ms, pageable_ms, copy_ms = self.max_over_ranks([kernel_ms, pinned_ms, pageable_ms, copy_ms])
+        # once more from ONE process: rank 0 drives all N devices through saf_eval_host_multi (host gather included)
+        multi = None
+        self.barrier()
+        del cols_d, outs_d, d_tmp
+        torch.cuda.empty_cache()
+        if self.rank == 0:
+            outs = [np.empty(total) for _ in range(n_out)]
+            devs = list(range(self.world))
+            h.eval_host(glob, outs, total, devices=devs)     # warm-up: contexts, modules, staging rings
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                h.eval_host(glob, outs, total, devices=devs)
+                ts.append(time.perf_counter() - t0)
+            t_multi = sum(ts) / len(ts)
+            ok = all(np.array_equal(o[b:e].view(np.uint64), p_.view(np.uint64)) for o, p_ in zip(outs, pg_out))
+            multi = {"api": "saf_eval_host_multi", "devices": self.world, "host_memory": "pageable",
+                     "ms": 1e3 * t_multi, "value": total / t_multi, "unit": UNIT,
+                     "rank0_shard_bits_equal_per_rank_run": bool(ok)}
+        if self.cpu_group is not None:
+            self.dist.barrier(group=self.cpu_group)  # the other ranks wait here on the CPU, GPUs idle
+        self.barrier()
+        if self.rank != 0:
+            return None
+        bytes_total = 8 * total * (len(glob) + n_out)
+        t_k, t_c = kernel_ms * 1e-3, copy_ms * 1e-3
+        limiter = ("kernel (FP64 interpreter)" if t_k >= t_c else
+                   "host<->device copies (PCIe / host DRAM shared by all ranks), not a collective: there is none")
+        roof = self.roofline(info, w, n, 1, kernel_ms, False)
+        return {
+            "config": f"terrain_gradient: {total} points of one seeded global array, {self.world} contiguous shard(s), "
+                      "program replicated, no collective (host gather only)",
+            "total_points": total, "points_per_gpu": n, "n_gpus": self.world, "scaling": "strong",
+            "kernel": {"ms": kernel_ms, "value": total / t_k, "unit": UNIT, "roofline_frac": roof["frac"], "bound": roof["bound"]},
+            "e2e": {"api": "saf_eval_host per rank", "host_memory": "pinned", "ms": pinned_ms,
+                    "value": total / (pinned_ms * 1e-3), "unit": UNIT},
+            "e2e_pageable": {"api": "saf_eval_host per rank", "host_memory": "pageable", "ms": pageable_ms,
+                             "value": total / (pageable_ms * 1e-3), "unit": UNIT,
+                             "bits_equal_pinned_run": bool(same)},
+            "host_multi": multi,
+            "copies_only": {"ms": copy_ms, "gbs_aggregate": bytes_total / t_c / 1e9,
+                            "note": "the same H2D + D2H bytes with pinned buffers and no kernel, all ranks at once"},
+            "h2d_bytes": 8 * total * len(glob), "d2h_bytes": 8 * total * n_out,
+            "limiter": limiter,
+        }
+
+
+def run_ours(args):
+    from symbanafis_b200 import workloads
+    B = Bench(args)
+    w = workloads.get(args.workload)
+    n, iters = workload_sizes(w, args, True)
+    sampler = ClockSampler(B.local)
+    if B.rank == 0:
+        sampler.start()
+    t_all0 = time.perf_counter()
+    main = B.measure(w, n, iters, args.steps, args.warmup, 1 + B.rank, 12.0, True)
+    others = {}
+    full_run = args.workload == HEADLINE and not args.no_workloads and not args.points and not args.iters
+    if full_run and B.world == 1:
+        for name in OTHER_WORKLOADS:
+            ww = workloads.get(name)
+            nn, ii = workload_sizes(ww, args, False)
+            others[name] = B.measure(ww, nn, ii, max(3, min(args.steps, 10)), 3, 1, 4.0, False)
+    c5 = None
+    if full_run and not args.no_c5_sharded:
+        if B.world == 1 and "terrain_gradient" in others and args.c5_points == C5_TOTAL_POINTS:
+            t = others["terrain_gradient"]  # one GPU: the shard IS the whole array (same seed-42 generator, 100 M points)
+            c5 = {"config": f"terrain_gradient: {C5_TOTAL_POINTS} points, 1 shard (= workloads.terrain_gradient)",
+                  "total_points": C5_TOTAL_POINTS, "points_per_gpu": C5_TOTAL_POINTS, "n_gpus": 1, "scaling": "strong",
+                  "kernel": {"ms": t["ms_per_step"], "value": t["value"], "unit": UNIT,
+                             "roofline_frac": t["roofline"]["frac"], "bound": t["roofline"]["bound"]},
+                  "e2e": {"api": "saf_eval_host", "host_memory": "pinned", "ms": t["e2e"]["ms_per_step"],
+                          "value": t["e2e"]["value"], "unit": UNIT},
+                  "e2e_pageable": {"api": "saf_eval_host", "host_memory": "pageable", "ms": t["e2e_pageable"]["ms_per_step"],
+                                   "value": t["e2e_pageable"]["value"], "unit": UNIT},
+                  "host_multi": None}
+        else:
+            c5 = B.c5_sharded(args.c5_points)
+    t_all = time.perf_counter() - t_all0
+    clocks = sampler.stop() if B.rank == 0 else None
+    if B.rank == 0:
+        line = {
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": B.world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": main["config"],
+            "device_program": main["device_program"],
+            "roofline": main["roofline"],
+            "ideal_kernel": main.get("ideal_kernel"),
+            "sustained": main.get("sustained"),
+            "cpu_baseline": main["cpu_baseline"],
+            "e2e": main["e2e"],
+            "e2e_pageable": main["e2e_pageable"],
+            "gpu_launches": main["gpu_launches"],
+            "clocks": clocks,
+            "wall_s_timed_region": main["wall_s_timed_region"],
+            "wall_s_all_measurements": t_all,
+        }
+        if others:
+            line["workloads"] = others
+        if c5 is not None:
+            line["c5_sharded"] = c5
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if B.world > 1:
+        B.dist.destroy_process_group()
 
 
 def main():

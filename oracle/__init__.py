@@ -41,7 +41,7 @@ class _Prog(C.Structure):
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (``oracle/Makefile``) if the shared object is missing/stale."""
     srcs = [os.path.join(_HERE, f) for f in
-            ("saf_oracle.c", "saf_oracle_math.c", "saf_oracle.h", "saf_oracle_math.h", "Makefile")]
+            ("saf_oracle.c", "saf_oracle_math.c", "saf_oracle_simd.c", "saf_oracle.h", "saf_oracle_math.h", "Makefile")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
@@ -70,6 +70,11 @@ def lib() -> C.CDLL:
         L.saf_oracle_run_chunked.restype = C.c_int
         L.saf_oracle_iterate.argtypes = [C.POINTER(_Prog), PP, C.c_size_t, C.c_size_t, C.c_uint64, C.c_int]
         L.saf_oracle_iterate.restype = C.c_int
+        L.saf_oracle_run_chunked_simd.argtypes = L.saf_oracle_run_chunked.argtypes
+        L.saf_oracle_run_chunked_simd.restype = C.c_int
+        L.saf_oracle_iterate_simd.argtypes = L.saf_oracle_iterate.argtypes
+        L.saf_oracle_iterate_simd.restype = C.c_int
+        L.saf_oracle_has_simd.restype = C.c_int
         for name, n in (("saf_oracle_builtin1", 1), ("saf_oracle_builtin2", 2),
                         ("saf_oracle_builtin3", 3), ("saf_oracle_builtin4", 4)):
             f = getattr(L, name)
@@ -151,10 +156,19 @@ class OracleProgram:
             n_points = len(cols[0]) if len(cols) else 1
         return self._run(lib().saf_oracle_run_chunked, cols, n_points, n_threads)
 
-    def iterate(self, state: Sequence[np.ndarray], iters: int, n_threads: int = 0) -> List[np.ndarray]:
-        st = [np.array(s, dtype=np.float64, copy=True) for s in state]
+    def run_chunked_simd(self, cols: Sequence[np.ndarray], n_points: Optional[int] = None,
+                         n_threads: int = 0) -> List[np.ndarray]:
+        """``run_chunked_evaluator`` with the f64x4 workspace (simd.rs:53-114): what ``eval_f64`` runs."""
+        if n_points is None:
+            n_points = len(cols[0]) if len(cols) else 1
+        return self._run(lib().saf_oracle_run_chunked_simd, cols, n_points, n_threads)
+
+    def iterate(self, state: Sequence[np.ndarray], iters: int, n_threads: int = 0, simd: bool = False,
+                in_place: bool = False) -> List[np.ndarray]:
+        st = list(state) if in_place else [np.array(s, dtype=np.float64, copy=True) for s in state]
         n = st[0].size if st else 0
-        rc = lib().saf_oracle_iterate(C.byref(self._c), _ptr_array(st), len(st), n, iters, n_threads)
+        fn = lib().saf_oracle_iterate_simd if simd else lib().saf_oracle_iterate
+        rc = fn(C.byref(self._c), _ptr_array(st), len(st), n, iters, n_threads)
         if rc != OK:
             raise OracleError(rc)
         return st
@@ -170,3 +184,8 @@ def powi(v: float, n: int) -> float:
 
 def online_cores() -> int:
     return lib().saf_oracle_online_cores()
+
+
+def has_simd() -> bool:
+    """AVX2 + FMA available: the f64x4 body runs as vectors (else it falls back to the scalar path)."""
+    return bool(lib().saf_oracle_has_simd())

@@ -93,6 +93,17 @@ int saf_oracle_run_chunked(const saf_oracle_program *p, const double *const *col
 int saf_oracle_iterate(const saf_oracle_program *p, double *const *state,
                        size_t n_state, size_t n_points, uint64_t iters, int n_threads);
 
+/* The reference's f64x4 path (simd.rs:53-114 + the simd arms of macros.rs / builtins.rs:148-299, saf_oracle_simd.c):
+ * arithmetic as 4-lane vector operations, transcendentals as four scalar calls, scalar tail, 256-point chunks with one
+ * f64x4 workspace per worker.  Same results as the scalar functions above, bit for bit (MulAdd is a true FMA in both).
+ * Falls back to the scalar path when the CPU has no AVX2 + FMA (saf_oracle_has_simd() == 0). */
+int saf_oracle_has_simd(void);
+int saf_oracle_run_chunked_simd(const saf_oracle_program *p, const double *const *cols,
+                                const size_t *col_lens, size_t n_cols,
+                                double *const *outs, size_t n_points, int n_threads);
+int saf_oracle_iterate_simd(const saf_oracle_program *p, double *const *state,
+                            size_t n_state, size_t n_points, uint64_t iters, int n_threads);
+
 /* builtins.rs:38-139 exposed for known-answer tests. */
 double saf_oracle_builtin1(uint32_t fnop, double x);
 double saf_oracle_builtin2(uint32_t fnop, double x1, double x2);

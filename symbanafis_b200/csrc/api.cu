@@ -551,6 +551,89 @@ void release_streams(int dev, const StreamSet &s) {
 
 constexpr size_t kChunkPoints = 1u << 21; // 2 Mi points: 16 MiB per column per chunk
 
+// ---- pageable host buffers --------------------------------------------------------------------------------------
+// Real callers hold pageable memory (a Rust Vec<f64>, a NumPy array: src/bindings/python/parallel.rs:198-223 passes
+// the array's own buffer).  cudaMemcpyAsync on pageable memory is staged by the driver and SYNCHRONOUS with respect to
+// the host, which serialises the three-stream pipeline below.  Pageable columns are therefore staged here, chunk by
+// chunk, through a pooled ring of pinned buffers: the host thread (helped by a few copy threads) moves chunk k + 1 into
+// pinned memory while the GPU copies and evaluates chunk k.
+struct PinnedPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;
+    std::map<void *, size_t> sizes;
+    size_t cached = 0;
+    static constexpr size_t kMaxCached = (size_t)2 << 30;
+    void *acquire(size_t bytes, cudaError_t *err) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = free_blocks.lower_bound(bytes);
+            if (it != free_blocks.end() && it->first <= bytes * 2 + (1 << 20)) {
+                void *p = it->second;
+                cached -= it->first;
+                free_blocks.erase(it);
+                return p;
+            }
+        }
+        void *p = nullptr;
+        *err = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+        if (*err != cudaSuccess) return nullptr;
+        std::lock_guard<std::mutex> lk(mu);
+        sizes[p] = bytes;
+        return p;
+    }
+    void release(void *p) {
+        if (!p) return;
+        std::unique_lock<std::mutex> lk(mu);
+        const size_t b = sizes[p];
+        if (cached + b > kMaxCached) {
+            sizes.erase(p);
+            lk.unlock();
+            cudaFreeHost(p);
+            return;
+        }
+        cached += b;
+        free_blocks.emplace(b, p);
+    }
+};
+PinnedPool g_pinned;
+
+bool is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError(); // older runtimes report unregistered host memory as an error
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+struct CopyJob { void *dst; const void *src; size_t bytes; };
+// host-to-host copies of one chunk, spread over a few threads when they are large (one thread moves ~10 GB/s, the
+// PCIe link 50)
+void parallel_copy(const std::vector<CopyJob> &jobs) {
+    size_t total = 0;
+    for (const auto &j : jobs) total += j.bytes;
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned n_threads = total < ((size_t)4 << 20) ? 1u : std::min(6u, std::max(1u, hw / 2));
+    if (n_threads <= 1) {
+        for (const auto &j : jobs) std::memcpy(j.dst, j.src, j.bytes);
+        return;
+    }
+    // cut every job into n_threads slices (64-byte aligned cuts)
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t <= n_threads; ++t) {
+        auto work = [&jobs, t, n_threads]() {
+            for (const auto &j : jobs) {
+                const size_t per = ((j.bytes + n_threads - 1) / n_threads + 63) & ~(size_t)63;
+                const size_t b = std::min(j.bytes, per * (t - 1)), e = std::min(j.bytes, per * t);
+                if (e > b) std::memcpy((char *)j.dst + b, (const char *)j.src + b, e - b);
+            }
+        };
+        if (t < n_threads) th.emplace_back(work);
+        else work();
+    }
+    for (auto &x : th) x.join();
+}
+
 } // namespace
 
 // Evaluates points [begin, end) of host columns on the current device.
@@ -576,16 +659,30 @@ static int eval_host_range(const saf_program *prog, const double *const *cols, c
     }
     const int n_buf = (int)std::min<size_t>(3, (total + chunk - 1) / chunk);
 
+    // pageable columns / outputs of batches worth staging (small ones: the driver's own path is as good)
+    const bool stage_ok = total * sizeof(double) >= ((size_t)1 << 20);
+    std::vector<uint8_t> in_pageable(n_in, 0), out_pageable(n_out, 0);
+    bool any_pageable = false;
+    if (stage_ok) {
+        for (size_t j = 0; j < n_in; ++j)
+            if (dp.param_slot[j] != NO_SLOT && lens[j] > begin && is_pageable(cols[j])) in_pageable[j] = 1, any_pageable = true;
+        for (size_t r = 0; r < n_out; ++r)
+            if (is_pageable(outs[r])) out_pageable[r] = 1, any_pageable = true;
+    }
+
     StreamSet ss;
     int rc = acquire_streams(dev, &ss);
     if (rc != SAF_OK) return rc;
-    std::vector<void *> scratch;
+    std::vector<void *> scratch, pinned;
     auto cleanup = [&]() {
         for (void *p : scratch) g_pool.release(dev, p);
+        for (void *p : pinned) g_pinned.release(p);
         release_streams(dev, ss);
     };
     std::vector<std::vector<double *>> d_in(n_buf, std::vector<double *>(n_in, nullptr));
     std::vector<std::vector<double *>> d_out(n_buf, std::vector<double *>(n_out, nullptr));
+    std::vector<std::vector<double *>> h_in(n_buf, std::vector<double *>(n_in, nullptr));   // pinned staging
+    std::vector<std::vector<double *>> h_out(n_buf, std::vector<double *>(n_out, nullptr));
     for (int b = 0; b < n_buf; ++b) {
         for (size_t j = 0; j < n_in + n_out; ++j) {
             if (j < n_in && dp.param_slot[j] == NO_SLOT) continue; // column never read: do not copy it
@@ -598,14 +695,48 @@ static int eval_host_range(const saf_program *prog, const double *const *cols, c
             scratch.push_back(p);
             if (j < n_in) d_in[b][j] = (double *)p;
             else d_out[b][j - n_in] = (double *)p;
+            if (j < n_in ? in_pageable[j] : out_pageable[j - n_in]) {
+                void *hp = g_pinned.acquire(chunk * sizeof(double), &e);
+                if (!hp) {
+                    cleanup();
+                    return cuda_fail(e, "cudaHostAlloc(staging)");
+                }
+                pinned.push_back(hp);
+                if (j < n_in) h_in[b][j] = (double *)hp;
+                else h_out[b][j - n_in] = (double *)hp;
+            }
         }
     }
     int status = SAF_OK;
+    // chunk whose results still sit in the pinned output staging of buffer b: {offset, points}
+    std::vector<std::pair<size_t, size_t>> pending(n_buf, {0, 0});
+    std::vector<CopyJob> jobs;
+    auto drain = [&](int b) { // results of the chunk in flight on buffer b -> the caller's (pageable) outputs
+        if (pending[b].second == 0) return;
+        cudaError_t e = cudaStreamSynchronize(ss.s[b]);
+        if (e != cudaSuccess && status == SAF_OK) status = cuda_fail(e, "cudaStreamSynchronize");
+        if (status == SAF_OK) {
+            jobs.clear();
+            for (size_t r = 0; r < n_out; ++r)
+                if (out_pageable[r]) jobs.push_back({outs[r] + pending[b].first, h_out[b][r], pending[b].second * sizeof(double)});
+            parallel_copy(jobs);
+        }
+        pending[b] = {0, 0};
+    };
     size_t k = 0;
     for (size_t off = begin; off < end && status == SAF_OK; off += chunk, ++k) {
         const int b = (int)(k % (size_t)n_buf);
         cudaStream_t st = ss.s[b];
         const size_t n = std::min(chunk, end - off);
+        if (any_pageable) {
+            drain(b); // also makes the staging buffers of b free to be overwritten
+            if (status != SAF_OK) break;
+            jobs.clear();
+            for (size_t j = 0; j < n_in; ++j)
+                if (in_pageable[j] && lens[j] > off)
+                    jobs.push_back({h_in[b][j], cols[j] + off, std::min(n, lens[j] - off) * sizeof(double)});
+            parallel_copy(jobs);
+        }
         std::vector<const double *> c_ptr(n_in, nullptr);
         std::vector<size_t> c_len(n_in, 0);
         for (size_t j = 0; j < n_in; ++j) {
@@ -613,7 +744,8 @@ static int eval_host_range(const saf_program *prog, const double *const *cols, c
             const size_t len = lens[j];
             if (len > off) { // part (or all) of this chunk comes from the column itself
                 const size_t m = std::min(n, len - off);
-                cudaError_t e = cudaMemcpyAsync(d_in[b][j], cols[j] + off, m * sizeof(double), cudaMemcpyHostToDevice, st);
+                const double *src = in_pageable[j] ? h_in[b][j] : cols[j] + off;
+                cudaError_t e = cudaMemcpyAsync(d_in[b][j], src, m * sizeof(double), cudaMemcpyHostToDevice, st);
                 if (e != cudaSuccess) { status = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
                 c_len[j] = m;
             } else { // column exhausted before this chunk: broadcast its last element (scalar.rs:203-207)
@@ -628,10 +760,14 @@ static int eval_host_range(const saf_program *prog, const double *const *cols, c
                                   flags | SAF_EVAL_BROADCAST, st);
         if (status != SAF_OK) break;
         for (size_t r = 0; r < n_out; ++r) {
-            cudaError_t e = cudaMemcpyAsync(outs[r] + off, d_out[b][r], n * sizeof(double), cudaMemcpyDeviceToHost, st);
+            double *dst = out_pageable[r] ? h_out[b][r] : outs[r] + off;
+            cudaError_t e = cudaMemcpyAsync(dst, d_out[b][r], n * sizeof(double), cudaMemcpyDeviceToHost, st);
             if (e != cudaSuccess) { status = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
         }
+        if (any_pageable) pending[b] = {off, n};
     }
+    // oldest chunk first: its copy-out overlaps the GPU work of the younger ones
+    for (size_t i = 0; i < (size_t)n_buf; ++i) drain((int)((k + i) % (size_t)n_buf));
     for (int b = 0; b < n_buf; ++b) {
         cudaError_t e = cudaStreamSynchronize(ss.s[b]);
         if (e != cudaSuccess && status == SAF_OK) status = cuda_fail(e, "cudaStreamSynchronize");

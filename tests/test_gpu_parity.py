@@ -545,7 +545,7 @@ def test_full_size_terrain_gradient_sharding_independence_and_sampled_parity():
     idx = np.random.default_rng(0).choice(n, 3000, replace=False)
     ref = OracleProgram.from_program(w.program).eval_batch([c[idx] for c in cols], idx.size)
     for t, r in zip(whole, ref):
-        assert_close(t.cpu().numpy()[idx], r, 1e-11, 1e-12, what="terrain gradient sample")
+        assert_close(t.cpu().numpy()[idx], r, RTOL, 1e-12, what="terrain gradient sample")
 
 
 def test_one_handle_used_from_many_host_threads():

@@ -26,6 +26,10 @@ def test_compiled_evaluator_metadata():
     for op in ("Square", "Sin", "MulAdd"):
         assert op in text
     assert ev.workspace_size() >= 4
+    # ... and the exact word stream SURVEY.md section 8a derives from the reference's lowering rules
+    # (pow.rs:205-209 Square, func.rs:34-43 Builtin1{ExpNeg}, sum.rs:139-148 MulAdd; temporaries t0..t2 = R1..R3, result R4)
+    assert [int(v) for v in ev.program.flat] == [20, 1, 0, 30, 2, 0, 38, 3, 26, 0, 15, 4, 2, 3, 1, 0]
+    assert list(ev.program.consts) == [] and ev.program.param_count == 1 and list(ev.program.result_regs) == [4]
 
 
 def test_auto_parameter_order_is_alphabetical_and_excludes_known_constants():
