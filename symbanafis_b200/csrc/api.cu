@@ -392,11 +392,17 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
     rc = ensure_device_image(const_cast<saf_program *>(prog), device, *pk, &d.image_global);
     if (rc != SAF_OK) return rc;
     d.code_bytes = pk->code_bytes;
+    // streaming (kernel.cu): a single pass whose columns are all present, full length and 16-byte aligned, whose results
+    // all live in slots, and whose code fits one window
+    bool stream_ok = aligned && d.iters == 1 && !use_r && P >= 2 && d.result_k_mask == 0;
+    for (uint32_t j = 0; j < dp.param_count && stream_ok; ++j)
+        if (dp.param_slot[j] != NO_SLOT && (d.cols[j] == nullptr || d.col_len[j] < n_points)) stream_ok = false;
     LaunchShape shape;
-    e = choose_shape(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points, P, use_r, &shape, block_threads);
+    e = choose_shape(device, pk->n_slots, pk->code_off, pk->code_bytes, n_points, P, use_r, &shape, block_threads, stream_ok);
     if (e == cudaErrorInvalidConfiguration)
         return fail(SAF_ERR_UNSUPPORTED, "program keeps more live values than fit the on-chip register file");
     if (e != cudaSuccess) return cuda_fail(e, "choose_shape");
+    d.n_rf = (uint32_t)shape.n_rf;
     e = launch_interpreter(d, shape, stream);
     if (e != cudaSuccess) return cuda_fail(e, "interpreter launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);

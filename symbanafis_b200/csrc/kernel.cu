@@ -105,6 +105,33 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
 }
 __device__ __forceinline__ uint32_t smem_base32() { return (uint32_t)__cvta_generic_to_shared(saf_smem); }
 
+// ---- bulk asynchronous copies (TMA, 1-D) + mbarrier: the streaming path of interp_body ------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // WIDE (one block of blockDim.x threads per SM): the stride between a thread's pairs is the block's width, a
 // run-time value -- the accesses use [register + uniform register] addressing, no extra instruction.
 template <int P, bool WIDE = false>
@@ -202,10 +229,10 @@ __device__ __noinline__ double cold_powi(double a, int n) { return dm::powi(a, n
 __device__ __noinline__ double cold_recip_expm1(double a) { return __ddiv_rn(1.0, expm1(a)); }
 
 template <int P, bool RM = false, bool WIDE = false>
-__device__ __noinline__ void cold_op(const unsigned char *img, uint32_t cur, int32_t acc_off, int32_t x0_off,
+__device__ __noinline__ void cold_op(uint32_t rf32, const unsigned char *img, uint32_t cur, int32_t acc_off, int32_t x0_off,
                                      int32_t x1_off) {
     using RF = Rf<P, WIDE && P == 4>;
-    const uint32_t my = RF::mine(smem_base32());
+    const uint32_t my = RF::mine(rf32);
     const unsigned long long *w = reinterpret_cast<const unsigned long long *>(img + cur);
     const uint2 q0 = split64(w[0]), q1 = split64(w[1]), q2 = split64(w[2]), q3 = split64(w[3]);
     // word 0 holds the NEXT opcode; register-machine images (ruop.h) carry the cold micro-op above the kinds
@@ -580,15 +607,23 @@ __device__ unsigned long long hot_run_r(uint32_t, uint32_t, const unsigned char 
 // WIDE (P <= 2 only): one block of blockDim.x > BLOCK_THREADS threads per SM -- programs with many live values fit
 // two 128-thread blocks per SM at most, and one wide block holds more warps in the same shared memory (the code
 // window and the constant table exist once)
+// STREAMING (d.n_rf = 2 or 3; the host grants it to single passes over full-length aligned columns whose register
+// file is small -- the HBM-bound programs): shared memory holds n_rf copies of the register file.  A parameter slot's
+// image for one tile is a CONTIGUOUS copy of the column tile (Rf layout, point_index), so one elected thread moves
+// tile t + n_rf - 1 into the parameter slots of another copy with 1-D bulk copies (cp.async.bulk, completion on that
+// copy's mbarrier) while the block evaluates tile t, and result slots go back to the output columns with bulk stores
+// that drain while the next tile runs: column traffic never waits for the interpreter and no register holds column
+// data.  A partial last tile takes the classic path.
 template <int P, bool K_SMEM, bool RM = false, bool WIDE = false>
 __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     const uint32_t block_threads = WIDE ? blockDim.x : (uint32_t)BLOCK_THREADS;
     using RF = Rf<P, WIDE && P == 4>;
     const uint32_t smem32 = smem_base32();
-    const uint32_t my = RF::mine(smem32);
 
-    // ---- behind the register file: block context, constant table (K_SMEM), code window ----
-    const uint32_t ctx_off = d.n_slots * (block_threads * (uint32_t)(P * 8));
+    // ---- behind the register file(s): block context, constant table (K_SMEM), code window ----
+    const uint32_t rf_bytes = d.n_slots * (block_threads * (uint32_t)(P * 8));
+    const uint32_t n_rf = RM ? 1u : d.n_rf;
+    const uint32_t ctx_off = n_rf * rf_bytes;
     const uint32_t k_s = ctx_off + (uint32_t)sizeof(BlockCtx);
     const uint32_t win_s = k_s + (K_SMEM ? d.code_off : 0u);
     {
@@ -599,6 +634,10 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
             ctx->acc_off = d.acc_off;
             ctx->code_off = d.code_off;
             ctx->code_bytes = d.code_bytes;
+            if (n_rf > 1u) {
+                for (uint32_t b = 0; b < n_rf; ++b) mbar_init(smem32 + ctx_off + (uint32_t)offsetof(BlockCtx, mbar) + 8u * b, 1u);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
         }
         if (threadIdx.x < MAX_COLS) ctx->param_off[threadIdx.x] = d.param_off[threadIdx.x];
         if (threadIdx.x < MAX_OUTS) ctx->result_off[threadIdx.x] = d.result_off[threadIdx.x];
@@ -615,9 +654,27 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     const unsigned long long TILE = (unsigned long long)block_threads * P;
     const unsigned long long n_tiles = (d.n_points + TILE - 1) / TILE;
 
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned long long tile_base = tile * TILE;
+    // the program on the register file at shared address rf32: hot_run until it ends, cold micro-ops in between
+    auto run_program = [&](uint32_t rf32, bool restage) {
+        if (restage) stage_window(smem32 + win_s, d.image_global + d.code_off, 0u, d.code_bytes);
+        const uint32_t ctx_rel = smem32 + ctx_off - rf32;
+        uint32_t pc = 0, it = 0;
+        for (;;) {
+            unsigned long long st;
+            if constexpr (RM) st = hot_run_r<K_SMEM, SAF_R_THREADED>(rf32, ctx_rel, d.image_global, pc, it, iters);
+            else st = hot_run<P, K_SMEM, WIDE && P == 4>(rf32, ctx_rel, d.image_global, pc, it, iters);
+            if (st == HOT_DONE) break;
+            pc = (uint32_t)st;
+            it = (uint32_t)(st >> 32);
+            cold_op<P, RM, WIDE>(rf32, d.image_global, d.code_off + pc, d.acc_off, d.x0_off, d.x1_off);
+            pc += UINSTR_BYTES;
+        }
+    };
 
+    // one tile the classic way: loads -> parameter slots, program, result slots -> stores
+    auto classic_tile = [&](unsigned long long tile, bool restage) {
+        const unsigned long long tile_base = tile * TILE;
+        const uint32_t my = RF::mine(smem32);
         // ---- prologue: columns -> parameter slots (scalar.rs:182-207 rules) ----
         for (uint32_t j = 0; j < d.n_params; ++j) {
             const int32_t s = d.param_off[j];
@@ -645,24 +702,7 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
             }
             RF::store(my, (uint32_t)s, v);
         }
-
-        // ---- the program: hot_run until it ends, cold micro-ops in between ----
-        {
-            if (multi_window && tile != blockIdx.x) // the previous tile left the last window staged
-                stage_window(smem32 + win_s, d.image_global + d.code_off, 0u, d.code_bytes);
-            uint32_t pc = 0, it = 0;
-            for (;;) {
-                unsigned long long st;
-                if constexpr (RM) st = hot_run_r<K_SMEM, SAF_R_THREADED>(smem32, ctx_off, d.image_global, pc, it, iters);
-                else st = hot_run<P, K_SMEM, WIDE && P == 4>(smem32, ctx_off, d.image_global, pc, it, iters);
-                if (st == HOT_DONE) break;
-                pc = (uint32_t)st;
-                it = (uint32_t)(st >> 32);
-                cold_op<P, RM, WIDE>(d.image_global, d.code_off + pc, d.acc_off, d.x0_off, d.x1_off);
-                pc += UINSTR_BYTES;
-            }
-        }
-
+        run_program(smem32, restage);
         // ---- epilogue: result slots -> output columns ----
         for (uint32_t k = 0; k < d.n_results; ++k) {
             Pt<P> v;
@@ -688,7 +728,62 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
                 }
             }
         }
+    };
+
+    if constexpr (!RM && P >= 2) {
+        if (n_rf > 1u) {
+            const unsigned long long n_full = d.n_points / TILE; // whole tiles: bulk copies of TILE * 8 bytes
+            const uint32_t tile_bytes = (uint32_t)TILE * 8u;
+            const uint32_t bar0 = smem32 + ctx_off + (uint32_t)offsetof(BlockCtx, mbar);
+            uint32_t n_used = 0;
+            for (uint32_t j = 0; j < d.n_params; ++j) n_used += d.param_off[j] >= 0;
+            auto issue = [&](unsigned long long tile, uint32_t buf) { // elected thread only
+                const uint32_t bar = bar0 + 8u * buf;
+                if (n_used != 0u) mbar_expect_tx(bar, n_used * tile_bytes);
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                for (uint32_t j = 0; j < d.n_params; ++j)
+                    if (d.param_off[j] >= 0)
+                        bulk_load(smem32 + buf * rf_bytes + (uint32_t)d.param_off[j], d.cols[j] + tile * TILE, tile_bytes, bar);
+            };
+            unsigned long long next = blockIdx.x;
+            uint32_t k_issued = 0;
+            if (threadIdx.x == 0)
+                for (; k_issued + 1u < n_rf && next < n_full; ++k_issued, next += gridDim.x) issue(next, k_issued % n_rf);
+            uint32_t it = 0;
+            for (unsigned long long tile = blockIdx.x; tile < n_full; tile += gridDim.x, ++it) {
+                const uint32_t buf = it % n_rf;
+                if (threadIdx.x == 0) {
+                    // the copy that tile it - 1 ran on is free: every thread is past the barrier that ended it, and bulk
+                    // stores only read RESULT slots, bulk loads only write PARAMETER slots
+                    if (next < n_full) {
+                        issue(next, (it + n_rf - 1u) % n_rf);
+                        next += gridDim.x;
+                    }
+                    // the result slots of `buf` were last read by the stores of tile it - n_rf: all but the n_rf - 1
+                    // youngest store groups must have finished reading shared memory
+                    if (n_rf == 2u) bulk_wait_read<1>();
+                    else bulk_wait_read<2>();
+                }
+                __syncthreads();
+                mbar_wait(bar0 + 8u * buf, (it / n_rf) & 1u);
+                run_program(smem32 + buf * rf_bytes, false);
+                fence_async_smem(); // result slots written through the generic proxy -> visible to the bulk stores
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    for (uint32_t k = 0; k < d.n_results; ++k)
+                        bulk_store(d.outs[k] + tile * TILE, smem32 + buf * rf_bytes + (uint32_t)d.result_off[k], tile_bytes);
+                    bulk_commit();
+                }
+            }
+            if (threadIdx.x == 0) bulk_wait_all(); // shared memory must outlive the stores that read it
+            __syncthreads();
+            if (n_full < n_tiles && (n_full % gridDim.x) == blockIdx.x) classic_tile(n_full, false);
+            return;
+        }
     }
+
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        classic_tile(tile, multi_window && tile != blockIdx.x); // the previous tile left the last window staged
 }
 
 // ---- entry points (extern "C": looked up by name in the cubin, launch.cu) ---------------------------------

@@ -40,6 +40,7 @@ struct LaunchDesc {
     uint32_t n_feedback;                 // parameters copied back from results between iterations (0 = double buffered)
     uint32_t n_results;
     uint32_t flags;                      // SAF_EVAL_BROADCAST
+    uint32_t n_rf;                       // register-file copies: 1, or 2 / 3 = STREAMING (bulk-copied column tiles, below)
     uint32_t result_k_mask;              // bit k: result k is a constant (result_off = image offset)
     int32_t acc_off;                     // reserved slot through which ACC is handed to the cold micro-ops
     int32_t x0_off, x1_off;              // staging slots of Builtin3/4 operands
@@ -54,6 +55,7 @@ struct LaunchDesc {
 constexpr size_t K_SMEM_MAX = 24 * 1024;
 
 struct LaunchShape {
+    int n_rf = 1;          // register-file copies in shared memory (> 1: streaming single passes, kernel.cu)
     int points_per_thread; // 1, 2, 4 or 8
     int block;             // threads per block: BLOCK_THREADS, or more for the wide one-block-per-SM layout (P = 2)
     int grid;
@@ -70,11 +72,14 @@ cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape,
 cudaError_t choose_points_per_thread(int device, uint32_t n_slots, unsigned long long n_points, bool aligned16,
                                      int force_points_per_thread, int *points_per_thread);
 // Grid / shared memory / constant-table placement for the packed program.
+// stream_ok: the launch qualifies for streaming (single pass over full-length aligned columns, see kernel.cu); the shape
+// then carries n_rf = 2 or 3 when the extra register-file copies cost no resident block.
 cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
-                         int points_per_thread, bool rmachine, LaunchShape *shape, int block_threads = BLOCK_THREADS);
-// register file + block context + constant table (when staged) + code window
+                         int points_per_thread, bool rmachine, LaunchShape *shape, int block_threads = BLOCK_THREADS,
+                         bool stream_ok = false);
+// n_rf register files + block context + constant table (when staged) + code window
 size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes,
-                              int block_threads = BLOCK_THREADS);
+                              int block_threads = BLOCK_THREADS, int n_rf = 1);
 // Threads of the wide one-block-per-SM layout (two points per thread) for a packed program with n_slots slots, or 0
 // when it would not hold more warps per SM than 128-thread blocks do.
 int wide_block_threads(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
@@ -90,6 +95,7 @@ struct alignas(16) BlockCtx { // a multiple of 16 bytes: the constant table and 
     uint32_t pad_;
     int32_t param_off[MAX_COLS];
     int32_t result_off[MAX_OUTS];
+    unsigned long long mbar[4];          // streaming: one mbarrier per register-file copy ("its column tiles have landed")
 };
 
 static_assert(sizeof(BlockCtx) % 16 == 0, "the code window behind BlockCtx is fetched with 16-byte loads");

@@ -5,6 +5,7 @@
 // whose entry points come from cudaGetDriverEntryPoint, so the library links against the CUDA runtime only
 // and still loads on machines without a driver (program creation / lowering / export work there).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -185,9 +186,9 @@ cudaError_t launch_clifford_probe(double *xs, double *ys, unsigned long long n, 
 
 // register file + block context + constant table (when staged) + code window
 size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_bytes_in_smem, size_t code_bytes,
-                              int block_threads) {
+                              int block_threads, int n_rf) {
     const size_t window = code_bytes < CODE_WINDOW_BYTES ? code_bytes : CODE_WINDOW_BYTES;
-    return (size_t)n_slots * (size_t)block_threads * (size_t)points_per_thread * 8 + sizeof(BlockCtx) +
+    return (size_t)n_rf * (size_t)n_slots * (size_t)block_threads * (size_t)points_per_thread * 8 + sizeof(BlockCtx) +
            ((k_bytes_in_smem + 15) & ~(size_t)15) + ((window + 15) & ~(size_t)15);
 }
 
@@ -248,7 +249,7 @@ int wide_block_threads(int device, uint32_t n_slots, size_t k_bytes, size_t code
 }
 
 cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t code_bytes, unsigned long long n_points,
-                         int P, bool rmachine, LaunchShape *shape, int block_threads) {
+                         int P, bool rmachine, LaunchShape *shape, int block_threads, bool stream_ok) {
     int sms = 0, smem_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -265,11 +266,30 @@ cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t co
     const size_t by_smem = ((size_t)smem_optin + 1024) / (smem + 1024);
     if (by_smem < resident) resident = by_smem;
     if (resident < 1 || block_threads != BLOCK_THREADS) resident = 1;
+    // Streaming: extra register-file copies that column tiles are bulk-copied into while another copy is being
+    // evaluated.  Taken when they cost no resident block (HBM-bound programs are small: few slots).
+    int n_rf = 1;
+    if (stream_ok && !rmachine && P >= 2 && code_bytes <= CODE_WINDOW_BYTES) {
+        static const int want = []() {
+            const char *v = getenv("SAF_STREAM_BUFS"); // tuning knob: 1 disables streaming, 2 (default) / 3 copies
+            const int n = v ? atoi(v) : 2;
+            return n < 1 ? 1 : n > 3 ? 3 : n;
+        }();
+        for (int r = want; r >= 2; --r) {
+            const size_t sm = interpreter_smem_bytes(n_slots, P, k_in_smem ? k_bytes : 0, code_bytes, block_threads, r);
+            if (sm <= (size_t)smem_optin && ((size_t)smem_optin + 1024) / (sm + 1024) >= resident) {
+                n_rf = r;
+                smem = sm;
+                break;
+            }
+        }
+    }
     const unsigned long long tile = (unsigned long long)block_threads * P;
     const unsigned long long n_tiles = (n_points + tile - 1) / tile;
     unsigned long long grid = (unsigned long long)sms * resident;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
+    shape->n_rf = n_rf;
     shape->points_per_thread = P;
     shape->block = block_threads;
     shape->grid = (int)grid;
