@@ -76,30 +76,58 @@ __device__ __forceinline__ void st_stream2(double *p, double a, double b) {
 
 extern __shared__ __align__(16) unsigned char saf_smem[];
 
+// -DSAF_CHECKED (tools/build_variant.sh checked -DSAF_CHECKED): every shared-memory access of the interpreter -- they
+// are raw 32-bit shared addresses in inline PTX, computed from offsets the packer wrote -- is checked against the
+// block's dynamic shared-memory window and its natural alignment, every bulk copy against its column; a violation
+// prints what and where and traps.  compute-sanitizer is closed on the GPU pool this was developed on; this build
+// stands in for its memcheck on the accesses that the compiler cannot see (tools/gpu_checked.sh).
+#ifdef SAF_CHECKED
+__device__ __noinline__ void saf_check_fail(const char *what, uint32_t addr, uint32_t bytes, uint32_t base, uint32_t size) {
+    printf("SAF_CHECKED: %s: shared address 0x%x (+%u bytes) outside [0x%x, 0x%x) or misaligned; block %d thread %d\n", what, addr,
+           bytes, base, base + size, (int)blockIdx.x, (int)threadIdx.x);
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void saf_check(const char *what, uint32_t addr, uint32_t bytes) {
+    uint32_t size;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(size));
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(saf_smem);
+    if (addr < base || addr + bytes > base + size || (addr & (bytes - 1u)) != 0u) saf_check_fail(what, addr, bytes, base, size);
+}
+#define SAF_CHECK(what, addr, bytes) saf_check(what, addr, bytes)
+#else
+#define SAF_CHECK(what, addr, bytes)
+#endif
+
 // Shared-memory register file, addressed by 32-bit shared-space addresses.  For P >= 2 a thread's points are
 // stored as P/2 pairs; pair g of the slot at byte offset `off` lives at  off + g * PAIR_BYTES + tid * 16
 // (`my` = block's shared base + tid * 16).  The base arrives as an opaque function argument / is computed once:
 // when the code mentions the shared-memory symbol itself ptxas re-derives the base (S2UR + UMOV + ULEA) on
 // every access.
 __device__ __forceinline__ void lds64(uint32_t addr, double &x) {
+    SAF_CHECK("lds64", addr, 8u);
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr));
 }
 __device__ __forceinline__ void lds128(uint32_t addr, double &x, double &y) {
+    SAF_CHECK("lds128", addr, 16u);
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
 }
 __device__ __forceinline__ void sts64(uint32_t addr, double x) {
+    SAF_CHECK("sts64", addr, 8u);
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
+    SAF_CHECK("sts128", addr, 16u);
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
+    SAF_CHECK("lds_u32", addr, 4u);
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
     uint4 v;
+    SAF_CHECK("lds_u128", addr, 16u);
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
@@ -120,10 +148,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    SAF_CHECK("bulk_load dst", dst_smem, 16u);
+    SAF_CHECK("bulk_load end", dst_smem + bytes - 16u, 16u);
+    SAF_CHECK("bulk_load mbarrier", bar, 8u);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
                  "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_t bytes) {
+    SAF_CHECK("bulk_store src", src_smem, 16u);
+    SAF_CHECK("bulk_store end", src_smem + bytes - 16u, 16u);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -162,6 +195,15 @@ struct Rf {
 template <int P, bool WIDE = false>
 __device__ __forceinline__ void store_if(uint32_t my, int32_t fd, const Pt<P> &o) {
     const uint32_t p = my + (uint32_t)fd;
+#ifdef SAF_CHECKED
+    if (fd >= 0) {
+        if constexpr (P == 1) { SAF_CHECK("store_if", p, 8u); }
+        else {
+            using RF_ = Rf<P, WIDE>;
+            for (int g = 0; g < P / 2; ++g) SAF_CHECK("store_if", p + g * RF_::pair_bytes(), 16u);
+        }
+    }
+#endif
     if constexpr (WIDE && P == 4) {
         const uint32_t p2 = p + Rf<P, WIDE>::pair_bytes();
         asm volatile("{ .reg .pred q; setp.ge.s32 q, %0, 0; @q st.shared.v2.f64 [%1], {%3, %4}; @q st.shared.v2.f64 [%2], {%5, %6}; }" ::"r"(fd),
@@ -329,6 +371,7 @@ __device__ __forceinline__ void stage_window(uint32_t win_sm, const unsigned cha
     __syncthreads(); // everybody is done with the previous window
     for (uint32_t i = threadIdx.x; i < bytes / 16u; i += blockDim.x) {
         const uint4 v = __ldg(src + i);
+        SAF_CHECK("stage_window", win_sm + 16u * i, 16u);
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(win_sm + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
     __syncthreads();
@@ -607,14 +650,16 @@ __device__ unsigned long long hot_run_r(uint32_t, uint32_t, const unsigned char 
 // WIDE (P <= 2 only): one block of blockDim.x > BLOCK_THREADS threads per SM -- programs with many live values fit
 // two 128-thread blocks per SM at most, and one wide block holds more warps in the same shared memory (the code
 // window and the constant table exist once)
-// STREAMING (d.n_rf = 2 or 3; the host grants it to single passes over full-length aligned columns whose register
+// STREAMING (entry points saf_interp_p{2,4}s_ksm, d.n_rf = 2 or 3; a kernel of its own so that the tile loop below does
+// not weigh on the register allocation of the classic entry points -- ptxas allocates hot_run's registers against
+// its callers' live ranges, and with both loops in one kernel every four-points workload lost 15 %; the host grants it to single passes over full-length aligned columns whose register
 // file is small -- the HBM-bound programs): shared memory holds n_rf copies of the register file.  A parameter slot's
 // image for one tile is a CONTIGUOUS copy of the column tile (Rf layout, point_index), so one elected thread moves
 // tile t + n_rf - 1 into the parameter slots of another copy with 1-D bulk copies (cp.async.bulk, completion on that
 // copy's mbarrier) while the block evaluates tile t, and result slots go back to the output columns with bulk stores
 // that drain while the next tile runs: column traffic never waits for the interpreter and no register holds column
 // data.  A partial last tile takes the classic path.
-template <int P, bool K_SMEM, bool RM = false, bool WIDE = false>
+template <int P, bool K_SMEM, bool RM = false, bool WIDE = false, bool STREAM = false>
 __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
     const uint32_t block_threads = WIDE ? blockDim.x : (uint32_t)BLOCK_THREADS;
     using RF = Rf<P, WIDE && P == 4>;
@@ -622,7 +667,7 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
 
     // ---- behind the register file(s): block context, constant table (K_SMEM), code window ----
     const uint32_t rf_bytes = d.n_slots * (block_threads * (uint32_t)(P * 8));
-    const uint32_t n_rf = RM ? 1u : d.n_rf;
+    const uint32_t n_rf = STREAM ? d.n_rf : 1u;
     const uint32_t ctx_off = n_rf * rf_bytes;
     const uint32_t k_s = ctx_off + (uint32_t)sizeof(BlockCtx);
     const uint32_t win_s = k_s + (K_SMEM ? d.code_off : 0u);
@@ -634,10 +679,6 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
             ctx->acc_off = d.acc_off;
             ctx->code_off = d.code_off;
             ctx->code_bytes = d.code_bytes;
-            if (n_rf > 1u) {
-                for (uint32_t b = 0; b < n_rf; ++b) mbar_init(smem32 + ctx_off + (uint32_t)offsetof(BlockCtx, mbar) + 8u * b, 1u);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
         }
         if (threadIdx.x < MAX_COLS) ctx->param_off[threadIdx.x] = d.param_off[threadIdx.x];
         if (threadIdx.x < MAX_OUTS) ctx->result_off[threadIdx.x] = d.result_off[threadIdx.x];
@@ -730,13 +771,20 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
         }
     };
 
-    if constexpr (!RM && P >= 2) {
+    if constexpr (STREAM) {
+        static_assert(!RM && !WIDE && P >= 2 && K_SMEM, "streaming entry points: 128-thread blocks, P >= 2, constants in shared memory");
         if (n_rf > 1u) {
             const unsigned long long n_full = d.n_points / TILE; // whole tiles: bulk copies of TILE * 8 bytes
             const uint32_t tile_bytes = (uint32_t)TILE * 8u;
-            const uint32_t bar0 = smem32 + ctx_off + (uint32_t)offsetof(BlockCtx, mbar);
+            const uint32_t code_sm = (uint32_t)(d.code_bytes < CODE_WINDOW_BYTES ? d.code_bytes : CODE_WINDOW_BYTES);
+            const uint32_t bar0 = smem32 + win_s + ((code_sm + 15u) & ~15u);
             uint32_t n_used = 0;
             for (uint32_t j = 0; j < d.n_params; ++j) n_used += d.param_off[j] >= 0;
+            if (threadIdx.x == 0) {
+                for (uint32_t b = 0; b < n_rf; ++b) mbar_init(bar0 + 8u * b, 1u);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
             auto issue = [&](unsigned long long tile, uint32_t buf) { // elected thread only
                 const uint32_t bar = bar0 + 8u * buf;
                 if (n_used != 0u) mbar_expect_tx(bar, n_used * tile_bytes);
@@ -746,33 +794,32 @@ __device__ __forceinline__ void interp_body(const LaunchDesc &d) {
                         bulk_load(smem32 + buf * rf_bytes + (uint32_t)d.param_off[j], d.cols[j] + tile * TILE, tile_bytes, bar);
             };
             unsigned long long next = blockIdx.x;
-            uint32_t k_issued = 0;
-            if (threadIdx.x == 0)
-                for (; k_issued + 1u < n_rf && next < n_full; ++k_issued, next += gridDim.x) issue(next, k_issued % n_rf);
+            if (threadIdx.x == 0) { // the tiles of iterations 0 .. n_rf - 1, one per copy
+                uint32_t k = 0;
+                for (; k < n_rf && next < n_full; ++k, next += gridDim.x) issue(next, k);
+            }
             uint32_t it = 0;
             for (unsigned long long tile = blockIdx.x; tile < n_full; tile += gridDim.x, ++it) {
                 const uint32_t buf = it % n_rf;
-                if (threadIdx.x == 0) {
-                    // the copy that tile it - 1 ran on is free: every thread is past the barrier that ended it, and bulk
-                    // stores only read RESULT slots, bulk loads only write PARAMETER slots
-                    if (next < n_full) {
-                        issue(next, (it + n_rf - 1u) % n_rf);
-                        next += gridDim.x;
-                    }
-                    // the result slots of `buf` were last read by the stores of tile it - n_rf: all but the n_rf - 1
-                    // youngest store groups must have finished reading shared memory
-                    if (n_rf == 2u) bulk_wait_read<1>();
-                    else bulk_wait_read<2>();
-                }
-                __syncthreads();
                 mbar_wait(bar0 + 8u * buf, (it / n_rf) & 1u);
                 run_program(smem32 + buf * rf_bytes, false);
                 fence_async_smem(); // result slots written through the generic proxy -> visible to the bulk stores
+                // ONE block barrier per tile.  Before it, the elected thread makes sure that the stores of tile
+                // it - n_rf + 1 have finished reading their result slots (the program of tile it + 1 overwrites them);
+                // behind it every thread is done with this copy's parameter slots and has written its result slots.
+                if (threadIdx.x == 0) {
+                    if (n_rf == 2u) bulk_wait_read<0>();
+                    else bulk_wait_read<1>();
+                }
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     for (uint32_t k = 0; k < d.n_results; ++k)
                         bulk_store(d.outs[k] + tile * TILE, smem32 + buf * rf_bytes + (uint32_t)d.result_off[k], tile_bytes);
                     bulk_commit();
+                    if (next < n_full) { // the tile of iteration it + n_rf lands in the copy this tile has just left
+                        issue(next, buf);
+                        next += gridDim.x;
+                    }
                 }
             }
             if (threadIdx.x == 0) bulk_wait_all(); // shared memory must outlive the stores that read it
@@ -812,6 +859,12 @@ SAF_ENTRY_W(saf_interp_p2w_ksm, 2, true)
 SAF_ENTRY_W(saf_interp_p2w_kgm, 2, false)
 SAF_ENTRY_W(saf_interp_p4w_ksm, 4, true)
 SAF_ENTRY_W(saf_interp_p4w_kgm, 4, false)
+#define SAF_ENTRY_S(NAME, P, MINB)                                                                         \
+    extern "C" __global__ void __launch_bounds__(BLOCK_THREADS, MINB) NAME(const __grid_constant__ LaunchDesc d) { \
+        interp_body<P, true, false, false, true>(d);                                                       \
+    }
+SAF_ENTRY_S(saf_interp_p4s_ksm, 4, SAF_MINB_P4)
+SAF_ENTRY_S(saf_interp_p2s_ksm, 2, SAF_MINB_P2)
 SAF_ENTRY(saf_interp_p1_ksm, 1, true, SAF_MINB_P1)
 SAF_ENTRY(saf_interp_p1_kgm, 1, false, SAF_MINB_P1)
 #ifdef SAF_WITH_P8 // eight points per thread: a tuning experiment that lost on every workload; not shipped

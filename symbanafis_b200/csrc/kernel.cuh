@@ -95,8 +95,11 @@ struct alignas(16) BlockCtx { // a multiple of 16 bytes: the constant table and 
     uint32_t pad_;
     int32_t param_off[MAX_COLS];
     int32_t result_off[MAX_OUTS];
-    unsigned long long mbar[4];          // streaming: one mbarrier per register-file copy ("its column tiles have landed")
 };
+// Streaming launches (n_rf > 1) append one mbarrier per register-file copy behind the code window ("the column tiles
+// of that copy have landed"): STREAM_MBAR_BYTES, counted by interpreter_smem_bytes.
+constexpr uint32_t STREAM_MAX_COPIES = 3;
+constexpr uint32_t STREAM_MBAR_BYTES = 32;
 
 static_assert(sizeof(BlockCtx) % 16 == 0, "the code window behind BlockCtx is fetched with 16-byte loads");
 

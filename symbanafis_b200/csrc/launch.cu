@@ -51,7 +51,7 @@ struct Driver {
 struct DeviceModule {
     CUmodule mod = nullptr;
     CUmodule mod_r = nullptr;   // register machine, loaded on first use
-    CUfunction interp[13] = {}; // [6] [7] = P = 8 (not shipped), [8] = register machine (from mod_r), [9] [10] = wide blocks P = 2, [11] [12] = wide blocks P = 4
+    CUfunction interp[15] = {}; // [13] [14] = streaming entry points P = 4 / 2; // [6] [7] = P = 8 (not shipped), [8] = register machine (from mod_r), [9] [10] = wide blocks P = 2, [11] [12] = wide blocks P = 4
     CUfunction peak = nullptr;
     CUfunction clifford_probe = nullptr;
     bool ready = false;
@@ -100,15 +100,15 @@ cudaError_t module_for_current_device(DeviceModule **out) {
         }
         CUresult r = g_drv.module_load_data(&m.mod, saf_kernel_cubin);
         if (r != CUDA_SUCCESS) return as_cuda(r);
-        static const char *names[13] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
+        static const char *names[15] = {"saf_interp_p4_ksm", "saf_interp_p4_kgm", "saf_interp_p2_ksm", "saf_interp_p2_kgm",
                                        "saf_interp_p1_ksm", "saf_interp_p1_kgm", "saf_interp_p8_ksm", "saf_interp_p8_kgm",
                                        "saf_rinterp_ksm", "saf_interp_p2w_ksm", "saf_interp_p2w_kgm",
-                                       "saf_interp_p4w_ksm", "saf_interp_p4w_kgm"};
+                                       "saf_interp_p4w_ksm", "saf_interp_p4w_kgm", "saf_interp_p4s_ksm", "saf_interp_p2s_ksm"};
         int optin = 0;
         e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e != cudaSuccess) return e;
         m.smem_optin = optin;
-        for (int k = 0; k < 13; ++k) {
+        for (int k = 0; k < 15; ++k) {
             if (k == 8) continue; // register machine: module_r_for()
             r = g_drv.module_get_function(&m.interp[k], m.mod, names[k]);
             if (r == CUDA_ERROR_NOT_FOUND && (k == 6 || k == 7)) { // built without -DSAF_WITH_P8
@@ -152,7 +152,11 @@ cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape,
     const int li = shape.points_per_thread == 4 ? 0 : shape.points_per_thread == 2 ? 1 : shape.points_per_thread == 1 ? 2 : 3;
     const bool wide = shape.block != BLOCK_THREADS;
     if (wide && ((shape.points_per_thread != 2 && shape.points_per_thread != 4) || shape.rmachine)) return cudaErrorInvalidConfiguration;
-    const int k = shape.rmachine ? 8 : wide ? (shape.points_per_thread == 4 ? 11 : 9) + (shape.k_in_smem ? 0 : 1) : 2 * li + (shape.k_in_smem ? 0 : 1);
+    const bool streaming = shape.n_rf > 1;
+    if (streaming && (wide || shape.rmachine || !shape.k_in_smem || (shape.points_per_thread != 4 && shape.points_per_thread != 2)))
+        return cudaErrorInvalidConfiguration;
+    const int k = shape.rmachine ? 8 : streaming ? (shape.points_per_thread == 4 ? 13 : 14)
+                  : wide ? (shape.points_per_thread == 4 ? 11 : 9) + (shape.k_in_smem ? 0 : 1) : 2 * li + (shape.k_in_smem ? 0 : 1);
     if (shape.rmachine && !shape.k_in_smem) return cudaErrorInvalidConfiguration;
     DeviceModule *m = nullptr;
     cudaError_t e = module_for_current_device(&m);
@@ -189,7 +193,7 @@ size_t interpreter_smem_bytes(uint32_t n_slots, int points_per_thread, size_t k_
                               int block_threads, int n_rf) {
     const size_t window = code_bytes < CODE_WINDOW_BYTES ? code_bytes : CODE_WINDOW_BYTES;
     return (size_t)n_rf * (size_t)n_slots * (size_t)block_threads * (size_t)points_per_thread * 8 + sizeof(BlockCtx) +
-           ((k_bytes_in_smem + 15) & ~(size_t)15) + ((window + 15) & ~(size_t)15);
+           ((k_bytes_in_smem + 15) & ~(size_t)15) + ((window + 15) & ~(size_t)15) + (n_rf > 1 ? STREAM_MBAR_BYTES : 0);
 }
 
 static int resident_blocks_for(int P) { return P == 8 ? SAF_MINB_P8 : P == 4 ? SAF_MINB_P4 : P == 2 ? SAF_MINB_P2 : SAF_MINB_P1; }
@@ -269,7 +273,7 @@ cudaError_t choose_shape(int device, uint32_t n_slots, size_t k_bytes, size_t co
     // Streaming: extra register-file copies that column tiles are bulk-copied into while another copy is being
     // evaluated.  Taken when they cost no resident block (HBM-bound programs are small: few slots).
     int n_rf = 1;
-    if (stream_ok && !rmachine && P >= 2 && code_bytes <= CODE_WINDOW_BYTES) {
+    if (stream_ok && !rmachine && (P == 2 || P == 4) && code_bytes <= CODE_WINDOW_BYTES && k_in_smem && block_threads == BLOCK_THREADS) {
         static const int want = []() {
             const char *v = getenv("SAF_STREAM_BUFS"); // tuning knob: 1 disables streaming, 2 (default) / 3 copies
             const int n = v ? atoi(v) : 2;
