@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from .compiler import CompileError, compile_exprs
-from .expr import KNOWN_CONSTANTS, Expr, parse
+from .expr import KNOWN_CONSTANTS, Expr, parse, to_string
 from .isa import Program
 
 ArrayLike = Union[np.ndarray, Sequence[float]]
@@ -290,32 +290,95 @@ def eval_f64(expressions: Sequence, var_names: Sequence[Sequence[str]], data: Se
     return [r.tolist() for r in results]
 
 
-def evaluate_parallel(expressions: Sequence, variables: Sequence[Sequence[str]],
-                      values: Sequence[Sequence[Sequence[float]]]):
-    """Numeric fast path of ``evaluate_parallel`` (parallel.rs:436-487): every value is a number.
+def _format_float(v: float):
+    """EvalResult boxing of the reference's Python binding (bindings/python/parallel.rs:118-141): numeric results -- the
+    Expr::number / format_float string of parallel.rs:475-484, 680-692 -- reach Python as floats."""
+    return float(v)
 
-    ``values[expr][var][point]``; a variable with fewer values than the longest one is broadcast from
-    its last value (parallel.rs:440-465).  Returns ``list[list[float]]``.  ``None`` (``Value::Skip``)
-    and symbolic values belong to the reference's symbolic slow path, which is out of scope here."""
+
+def _slow_point(expr: Expr, names: Sequence[str], point: Sequence[Optional[float]], was_string: bool):
+    """``evaluate_slow_point`` (parallel.rs:630-677) for a point with at least one ``Value::Skip``: numeric variables are
+    substituted, skipped ones stay symbolic; the partially evaluated expression comes back as ``Expr`` (input was an
+    ``Expr``) or as its string (input was a string).  This is the reference's SYMBOLIC path -- there is nothing to
+    evaluate numerically for such a point, on any device.  A maintainer wiring the C ABI into the reference keeps
+    calling the reference's own ``evaluate_slow_point`` here."""
+    partial = expr.substitute({n: v for n, v in zip(names, point) if v is not None})
+    if not partial.variables() and partial.kind == "num":
+        return _format_float(partial.value)
+    return to_string(partial) if was_string else partial
+
+
+def evaluate_parallel(expressions: Sequence, variables: Sequence[Sequence[str]],
+                      values: Sequence[Sequence[Sequence[Optional[float]]]], symbolic_fallback=None):
+    """``evaluate_parallel`` (bindings/python/parallel.rs:34-157 -> drivers/parallel.rs:355-627).
+
+    ``values[expr][var][point]``; a variable with fewer values than the longest one is broadcast from its last value
+    (parallel.rs:440-465); ``None`` is ``Value::Skip``.  Per expression:
+
+    * every value numeric -> the numeric fast path (parallel.rs:436-487): one evaluation on the GPU;
+    * mixed (parallel.rs:489-613): the points whose values are all numeric are gathered and evaluated on the GPU in ONE
+      launch, the others are handed to the symbolic slow path (``symbolic_fallback(expr, names, point_values,
+      was_string)``, default: :func:`_slow_point`) -- the compiled evaluator is never asked to run on the CPU.
+
+    Returns ``list[list]``: floats for numeric results, ``Expr`` / ``str`` for symbolic ones (EvalResult boxing of the
+    binding, parallel.rs:118-141)."""
     if len(expressions) != len(variables) or len(expressions) != len(values):
         raise ValueError("expressions, variables and values must have the same length")
+    slow = symbolic_fallback or _slow_point
     out = []
     for e, names, vals in zip(expressions, variables, values):
+        if not isinstance(e, (str, Expr)):
+            raise TypeError("expressions must be str or Expr")
+        was_string = isinstance(e, str)
+        expr = _as_expr(e)
+        names = [str(n) for n in names]
         if len(names) != len(vals):
-            raise ValueError("EvalColumnMismatch: number of variables and value columns differ")
+            raise ValueError(f"EvalColumnMismatch: expected {len(names)} value columns, got {len(vals)}")
+        cols: List[np.ndarray] = []   # float64, NaN where skipped
+        skips: List[Optional[np.ndarray]] = []
         for col in vals:
-            if any(v is None or isinstance(v, (str, Expr)) for v in col):
-                raise NotImplementedError("symbolic / skipped values are outside the numeric fast path")
-        n_points = max((len(c) for c in vals), default=1)
-        cols = []
-        for c in vals:
-            if len(c) == 0:
-                raise ValueError("empty value column")
-            a = np.asarray(c, dtype=np.float64)
-            if a.size < n_points:
-                a = np.concatenate([a, np.full(n_points - a.size, a[-1])])
-            cols.append(a)
-        ev = _cached_evaluator([_as_expr(e)], list(names))
-        res = ev._run_host(cols, n_points, broadcast=False)[0]
-        out.append(res.tolist())
+            if isinstance(col, np.ndarray):
+                if col.ndim != 1 or col.dtype != np.float64:
+                    raise TypeError("value columns must be 1-D float64 arrays or lists of float / None")
+                cols.append(np.ascontiguousarray(col))
+                skips.append(None)
+                continue
+            if any(isinstance(v, (str, Expr)) for v in col):
+                raise TypeError("value columns hold floats or None (Value::Expr cannot be built from Python)")
+            mask = np.fromiter((v is None for v in col), dtype=bool, count=len(col))
+            cols.append(np.asarray([np.nan if v is None else float(v) for v in col], dtype=np.float64))
+            skips.append(mask if mask.any() else None)
+        n_points = max((c.size for c in cols), default=0)
+        if not names:  # zero-variable expression: one value (parallel.rs:399-409)
+            ev = _cached_evaluator([expr], [])
+            out.append([_format_float(ev._run_host([], 1, broadcast=False)[0][0])])
+            continue
+        if n_points == 0:
+            out.append([])
+            continue
+        if any(c.size == 0 for c in cols):
+            raise ValueError("All evaluation columns must have the same length")  # EvalColumnLengthMismatch (parallel.rs:421-423)
+        full, skip_at = [], np.zeros(n_points, dtype=bool)
+        for c, m in zip(cols, skips):  # broadcast from the last value, skipped or not
+            if c.size < n_points:
+                c = np.concatenate([c, np.full(n_points - c.size, c[-1])])
+                if m is not None:
+                    m = np.concatenate([m, np.full(n_points - m.size, m[-1])])
+            full.append(c)
+            if m is not None:
+                skip_at |= m
+        ev = _cached_evaluator([expr], names)
+        if not skip_at.any():
+            out.append([_format_float(v) for v in ev._run_host(full, n_points, broadcast=False)[0]])
+            continue
+        row: List = [None] * n_points
+        idx = np.flatnonzero(~skip_at)
+        if idx.size:  # the numeric points: gathered, ONE launch, scattered back
+            res = ev._run_host([np.ascontiguousarray(c[idx]) for c in full], int(idx.size), broadcast=False)[0]
+            for i, v in zip(idx, res):
+                row[int(i)] = _format_float(v)
+        for i in np.flatnonzero(skip_at):
+            point = [None if (m is not None and (m[min(i, m.size - 1)])) else float(c[i]) for c, m in zip(full, skips)]
+            row[int(i)] = slow(expr, names, point, was_string)
+        out.append(row)
     return out

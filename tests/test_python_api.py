@@ -56,8 +56,27 @@ def test_argument_validation_happens_before_any_device_work():
     with pytest.raises(ValueError):
         CompiledEvaluator(parse("x"), ["x"]).eval_batch([np.arange(10.0)[::2]])  # not C-contiguous
     assert eval_f64([], [], []) == []                       # test_numpy_returns.py:43-47
-    with pytest.raises(NotImplementedError):
-        evaluate_parallel(["x*y"], [["x", "y"]], [[[2.0, None], [3.0, 5.0]]])  # Value::Skip: symbolic slow path
+    with pytest.raises(TypeError):
+        evaluate_parallel([3.5], [["x"]], [[[1.0]]])           # "expressions must be str or Expr" (parallel.rs:52-55)
+    with pytest.raises(ValueError):
+        evaluate_parallel(["x*y"], [["x", "y"]], [[[1.0, 2.0], []]])  # empty column (parallel.rs:421-423)
+
+
+def test_evaluate_parallel_all_skipped_points_take_the_symbolic_path_only():
+    # tests/python/test_parallel_eval.py:159-187: a point with a None (Value::Skip) stays symbolic -- string in, string
+    # out; Expr in, Expr out (parallel.rs:630-677); no numeric point -> no device work at all
+    r = evaluate_parallel(["x + y"], [["x", "y"]], [[[1.0], [None]]])[0][0]
+    assert isinstance(r, str) and "y" in r and "x" not in r
+    x, y = symb("x"), symb("y")
+    r = evaluate_parallel([x + y], [["x", "y"]], [[[1.0], [None]]])[0][0]
+    from symbanafis_b200.expr import Expr
+    assert isinstance(r, Expr) and r.variables() == ["y"]
+    assert evaluate_parallel(["x"], [["x"]], [[[]]]) == [[]]
+    # a custom hand-off (what a maintainer points at the reference's evaluate_slow_point)
+    seen = []
+    r = evaluate_parallel(["x*y"], [["x", "y"]], [[[None, None], [3.0]]],
+                          symbolic_fallback=lambda e, names, point, was_string: seen.append((names, point)) or "handled")
+    assert r == [["handled", "handled"]] and seen == [(["x", "y"], [None, 3.0])] * 2
 
 
 # ---- the reference's Python tests against the CUDA path --------------------------------------------------------
@@ -86,6 +105,19 @@ def test_evaluate_parallel_numpy_and_expr_inputs():
     assert r == [[1.0, 4.0], [2.0, 3.0]]
     # a shorter value column is broadcast from its last value (parallel.rs:440-465)
     assert evaluate_parallel(["x + y"], [["x", "y"]], [[[1.0, 2.0, 3.0], [10.0]]])[0] == [11.0, 12.0, 13.0]
+
+
+@gpu
+def test_evaluate_parallel_mixed_points_numeric_on_the_gpu_symbolic_handed_off():
+    # tests/python/test_parallel_eval.py:131-144 (parallel.rs:489-613): numeric points through the compiled evaluator,
+    # here gathered into ONE launch; points with a skipped value through the symbolic slow path
+    before = kernel_launch_count()
+    r = evaluate_parallel(["x * y"], [["x", "y"]], [[[2.0, None, 4.0, None, 1.5], [3.0, 5.0]]])
+    assert kernel_launch_count() - before == 1
+    assert r[0][0] == 6.0 and r[0][2] == 20.0 and r[0][4] == 7.5 and all(isinstance(r[0][i], float) for i in (0, 2, 4))
+    assert isinstance(r[0][1], str) and "x" in r[0][1] and "5" in r[0][1] and isinstance(r[0][3], str)
+    # zero-variable expression: one value (parallel.rs:399-409)
+    assert evaluate_parallel(["2 + 3"], [[]], [[]]) == [[5.0]]
 
 
 @gpu
