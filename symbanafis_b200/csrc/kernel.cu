@@ -618,6 +618,13 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
             case U_FS + FS_SQ_ADDS: SAF_ENTER(U_FS + FS_SQ_ADDS) { const uint32_t fs = FI; FSHEAD LS(c, fs) /* after the store: S[imm] may be the kept slot */ SAF_FOR_P acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(a.v[p], a.v[p])); } SAF_NEXT(U_FS + FS_SQ_ADDS)
             case U_FS + FS_MULK2: SAF_ENTER(U_FS + FS_MULK2) { const double k1_ = konst(FC), k2_ = konst(FI); FSHEAD SAF_FOR_P acc.v[p] = __dmul_rn(k2_, __dmul_rn(k1_, a.v[p])); } SAF_NEXT(U_FS + FS_MULK2)
 
+            case U_F5: SAF_ENTER(U_F5) {
+                const double k1_ = konst(fb), k2_ = konst(FC), k3_ = konst(img32(cur + 24));
+                const uint32_t s2_ = FI;
+                LS(a, fa) LS(b, s2_) LS(c, (uint32_t)fd)
+                SAF_FOR_P acc.v[p] = __dadd_rn(c.v[p], __dmul_rn(k3_, __dmul_rn(b.v[p], __dmul_rn(k2_, __dmul_rn(a.v[p], k1_)))));
+            } SAF_NEXT(U_F5)
+
             TCASE(T_FMA, __fma_rn(x, y, z))
             TCASE(T_FMS, __fma_rn(x, y, -z))
             TCASE(T_FNMA, __fma_rn(-x, y, z))

@@ -370,7 +370,27 @@ int pack_program(const DeviceProgram &dp, int P, PackedProgram &out, std::string
             F.push_back(p);
             ++i;
         }
-        U.swap(F);
+        // two fused multiply chains back to back, accumulated into their own destination (uop.h U_F5)
+        std::vector<UI> G;
+        G.reserve(F.size());
+        const uint32_t FM_SK_MULK = U_FM + 3 * BC_SK + F_MULK, FM_SA_MULK_ADDS = U_FM + 3 * BC_SA + F_MULK_ADDS;
+        for (size_t i = 0; i < F.size(); ++i) {
+            const UI &p = F[i];
+            if (p.uop == FM_SK_MULK && p.d == NO_DEST && i + 1 < F.size() && F[i + 1].uop == FM_SA_MULK_ADDS &&
+                F[i + 1].d >= 0 && (uint32_t)F[i + 1].d == F[i + 1].imm) {
+                const UI &q = F[i + 1];
+                UI f = p;           // a = S1, b = K1, c = K2
+                f.uop = U_F5;
+                f.imm = q.a;        // S2
+                f.kinds = q.c;      // K3
+                f.d = q.d;          // S3 = destination
+                G.push_back(f);
+                ++i;
+                continue;
+            }
+            G.push_back(p);
+        }
+        U.swap(G);
     };
 
     std::vector<UI> U;

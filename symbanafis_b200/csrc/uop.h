@@ -86,7 +86,11 @@ constexpr uint32_t FT_ADDS = 0, FT_FMA = 1, FT_COUNT = 8;
 // Fields: a, b = operand and prefix pair of trig1; imm, kinds word = operand and prefix pair of trig2; c = K of the fma.
 constexpr uint32_t U_FD = U_FT + FT_COUNT;                    // + 4 * trig1 + 2 * trig2 + {adds, fma}
 constexpr uint32_t FD_COUNT = 8;
-constexpr uint32_t U_G = U_FD + FD_COUNT;                     // generic micro-ops
+// `S[d] = S[d] + K[kinds] * (S[imm] * (K[c] * (S[a] * K[b])))`: two fused multiply chains back to back -- one term of a
+// gradient sum, `coefficient * (x - c) * exp(..)` accumulated into the running sum that is also its destination (the
+// terrain gradient runs 218 of them per point; 1233 -> 1015 micro-ops)
+constexpr uint32_t U_F5 = U_FD + FD_COUNT;
+constexpr uint32_t U_G = U_F5 + 1;                            // generic micro-ops
 constexpr uint32_t G_POW = 0, G_POWI = 1, G_BUILTIN1 = 2, G_BUILTIN2 = 3, G_BUILTIN3 = 4, G_BUILTIN4 = 5,
                    G_ARG2 = 6, G_FMA = 7, G_FMS = 8, G_FNMA = 9, G_FNMS = 10, G_DIV = 11, G_RECIPEXPM1 = 12, G_COUNT = 13;
 constexpr uint32_t NO_PREFIX = 0xffffffffu; // field b of G_RECIPEXPM1 when there is no affine prefix

@@ -196,7 +196,8 @@ U_FQ = U_FM + 3 * 5  # square {S, A} + {mulK, addS}
 U_FS = U_FQ + 2 * 2  # t = S + K (kept in the slot of the kinds word when >= 0), then t*t [+ S] or K * (K * t)
 U_FT = U_FS + 3  # {sin, cos} x {S[imm] + ACC, fma(S[imm], K[c], ACC)} x {plain, affine prefix}
 U_FD = U_FT + 8  # trig1(S[a] prefix b) combined with trig2(S[imm] prefix kinds-word) by add / fma(., K[c], .)
-U_G = U_FD + 8
+U_F5 = U_FD + 8  # S[d] += K[kinds] * (S[imm] * (K[c] * (S[a] * K[b])))
+U_G = U_F5 + 1
 H1_NAMES = ["sin", "cos", "exp", "ln", "expsqr", "expsqrneg", "expneg", "sincos"]
 BC_NAMES = ["add", "mul", "negmul"]
 BC_KINDS = ["SS", "SK", "SA", "KA", "AA"]
@@ -320,7 +321,11 @@ def run_packed_program(pk: dict, cols: Sequence[np.ndarray], n_points: int, iter
                 kk = T_KINDS[v]
                 r = ref3(_TERNARY_REF[T_NAMES[t]], by_letter(kk[0], fa), by_letter(kk[1], fb), by_letter(kk[2], fc))
             elif uop < U_G:  # fused chains: the same operations, one dispatch (suffix operands: c = constant, imm = slot)
-                if uop >= U_FD:
+                if uop == U_F5:
+                    t_ = ref2("Mul", K(fc), ref2("Mul", S(fa), K(fb)))
+                    r = ref2("Add", S(fd), ref2("Mul", K(kinds), ref2("Mul", S(imm), t_)))
+                    sfx = -1
+                elif uop >= U_FD:
                     t1, rest = divmod(uop - U_FD, 4)
                     t2, tail = divmod(rest, 2)
                     u_ = ref1("Sin" if t1 == 0 else "Cos", ref3("MulAdd", S(fa), K(fb), K(fb + 8)))
