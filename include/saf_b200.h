@@ -98,6 +98,26 @@ SAF_API int saf_program_create(const uint32_t *flat_bytecode, size_t n_words,
  * of the fused program is output 0.. of program j in order. */
 SAF_API int saf_program_fuse(const saf_program *const *programs, size_t n_programs, saf_program **out);
 
+/* Expression strings -> program, without Python or Rust (csrc/compile.cpp): the k
+ * expressions are parsed (the reference's grammar subset: + - * / ^ **, unary minus, calls, implicit multiplication;
+ * src/parser/logic/pratt.rs:87-120), lowered with the reference's instruction-selection rules
+ * (src/evaluator/logic/bytecode/compile/codegen/lower/*.rs: MulAdd / MulSub / NegMulAdd, Square .. InvPow3_2 / Powi,
+ * ExpSqr / ExpSqrNeg / Builtin1{ExpNeg}, RecipExpm1, Sinc, u/c -> u*(1/c), Sin + Cos -> SinCos), value-numbered across
+ * the k outputs, register-allocated (emit/reg_alloc.rs) and encoded (emit/assemble.rs) into ONE multi-output program
+ * over `params` -- what CompiledEvaluator::compile produces, one register file for all outputs.  Compile errors
+ * (UnboundVariable, UnsupportedFunction: api.rs:402-408) -> SAF_ERR_INVALID_PROGRAM, parse errors ->
+ * SAF_ERR_INVALID_ARGUMENT, message in saf_last_error(). */
+SAF_API int saf_compile_exprs(const char *const *exprs, size_t n_exprs, const char *const *params, size_t n_params,
+                              saf_program **out);
+
+/* The reference-format payload (api.rs:125-142 fields) a handle was created from: component `index` of a fused handle,
+ * 0 otherwise.  Any pointer may be NULL; the n_* outputs always receive the full sizes. */
+SAF_API int saf_program_reference_payload(const saf_program *prog, size_t index, uint32_t *flat, size_t cap_words,
+                                          size_t *n_words, double *consts, size_t cap_consts, size_t *n_consts,
+                                          uint32_t *arg_pool, size_t cap_pool, size_t *n_pool, uint32_t *param_count,
+                                          uint32_t *workspace_size, uint32_t *result_regs, size_t cap_results,
+                                          size_t *n_results);
+
 SAF_API void saf_program_destroy(saf_program *prog);
 
 /* Same arguments as saf_program_create, but the handle comes from a per-process cache keyed by the CONTENT of the

@@ -65,7 +65,7 @@ EXPORTED_SYMBOLS = [
     "saf_program_disassemble", "saf_program_export", "saf_program_export_packed", "saf_eval_device", "saf_eval_host",
     "saf_eval_host_multi", "saf_iterate_device", "saf_iterate_host", "saf_last_error",
     "saf_device_count", "saf_kernel_launch_count", "saf_version", "saf_measure_fp64_peak",
-    "saf_measure_clifford_probe",
+    "saf_measure_clifford_probe", "saf_compile_exprs", "saf_program_reference_payload",
 ]
 
 
@@ -88,6 +88,11 @@ def lib() -> C.CDLL:
     L.saf_program_cache_clear.restype = None
     L.saf_program_fuse.argtypes = [PP, sz, PP]
     L.saf_program_fuse.restype = C.c_int
+    L.saf_compile_exprs.argtypes = [C.POINTER(C.c_char_p), sz, C.POINTER(C.c_char_p), sz, PP]
+    L.saf_compile_exprs.restype = C.c_int
+    L.saf_program_reference_payload.argtypes = [vp, sz, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz),
+                                                C.POINTER(u32), C.POINTER(u32), vp, sz, C.POINTER(sz)]
+    L.saf_program_reference_payload.restype = C.c_int
     L.saf_program_destroy.argtypes = [vp]
     L.saf_program_destroy.restype = None
     L.saf_program_get_info.argtypes = [vp, C.POINTER(ProgramInfo)]
@@ -181,6 +186,32 @@ class DeviceProgramHandle:
             arg_pool.ctypes.data if arg_pool.size else None, arg_pool.size,
             int(param_count), int(workspace_size), rr.ctypes.data, rr.size, C.byref(out)))
         return cls(out.value)
+
+    @classmethod
+    def compile(cls, exprs: Sequence[str], params: Sequence[str]) -> "DeviceProgramHandle":
+        """Expression strings -> one multi-output program, compiled by the C++ compiler behind the C ABI
+        (``saf_compile_exprs``, csrc/compile.cpp)."""
+        ea = (C.c_char_p * max(1, len(exprs)))(*[e.encode() for e in exprs])
+        pa = (C.c_char_p * max(1, len(params)))(*[p.encode() for p in params])
+        out = C.c_void_p()
+        check(lib().saf_compile_exprs(ea, len(exprs), pa, len(params), C.byref(out)))
+        return cls(out.value)
+
+    def reference_payload(self, index: int = 0):
+        """(flat uint32[], consts f64[], arg_pool uint32[], param_count, workspace_size, result_regs) of component `index`."""
+        nw, nk, npool, nr = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        pc, ws = C.c_uint32(), C.c_uint32()
+        check(lib().saf_program_reference_payload(self._h, index, None, 0, C.byref(nw), None, 0, C.byref(nk), None, 0,
+                                                  C.byref(npool), C.byref(pc), C.byref(ws), None, 0, C.byref(nr)))
+        flat = np.zeros(max(1, nw.value), dtype=np.uint32)
+        consts = np.zeros(max(1, nk.value), dtype=np.float64)
+        pool = np.zeros(max(1, npool.value), dtype=np.uint32)
+        rr = np.zeros(max(1, nr.value), dtype=np.uint32)
+        check(lib().saf_program_reference_payload(self._h, index, flat.ctypes.data, flat.size, C.byref(nw), consts.ctypes.data,
+                                                  consts.size, C.byref(nk), pool.ctypes.data, pool.size, C.byref(npool),
+                                                  C.byref(pc), C.byref(ws), rr.ctypes.data, rr.size, C.byref(nr)))
+        return (flat[:nw.value], consts[:nk.value], pool[:npool.value], int(pc.value), int(ws.value),
+                [int(r) for r in rr[:nr.value]])
 
     @classmethod
     def fuse(cls, handles: Sequence["DeviceProgramHandle"]) -> "DeviceProgramHandle":

@@ -518,7 +518,7 @@ def compile_exprs(exprs: Sequence[Expr], params: Sequence[str]) -> Program:
             out.append((op, d[0], extra, *s))
         else:
             out.append((op, d[0], *s))
-        for x in set(srcs):  # sources die after the instruction is emitted
+        for x in dict.fromkeys(srcs):  # sources die after the instruction is emitted (in order of first occurrence)
             if x[0] == "t" and last_use.get(x) == idx:
                 free.append(phys[x])
         for x in dests:  # a destination nobody reads (one half of a SinCos)

@@ -118,6 +118,55 @@ extern "C" int saf_program_fuse(const saf_program *const *programs, size_t n_pro
     return build_program(std::move(v), out);
 }
 
+namespace saf { namespace cc {
+int compile(const std::vector<std::string> &exprs, const std::vector<std::string> &params, RefProgram &out, std::string &err);
+} } // namespace saf::cc
+
+extern "C" int saf_compile_exprs(const char *const *exprs, size_t n_exprs, const char *const *params, size_t n_params,
+                                 saf_program **out) {
+    if (!out) return fail(SAF_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!exprs || n_exprs == 0) return fail(SAF_ERR_INVALID_ARGUMENT, "no expression to compile");
+    if (n_params && !params) return fail(SAF_ERR_INVALID_ARGUMENT, "params is NULL");
+    std::vector<std::string> es, ps;
+    for (size_t i = 0; i < n_exprs; ++i) {
+        if (!exprs[i]) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL expression");
+        es.emplace_back(exprs[i]);
+    }
+    for (size_t i = 0; i < n_params; ++i) {
+        if (!params[i]) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL parameter name");
+        ps.emplace_back(params[i]);
+    }
+    RefProgram r;
+    std::string err;
+    const int rc = saf::cc::compile(es, ps, r, err);
+    if (rc != SAF_OK) return fail(rc, err);
+    std::vector<RefProgram> v;
+    v.push_back(std::move(r));
+    return build_program(std::move(v), out);
+}
+
+extern "C" int saf_program_reference_payload(const saf_program *p, size_t index, uint32_t *flat, size_t cap_words,
+                                             size_t *n_words, double *consts, size_t cap_consts, size_t *n_consts,
+                                             uint32_t *arg_pool, size_t cap_pool, size_t *n_pool, uint32_t *param_count,
+                                             uint32_t *workspace_size, uint32_t *result_regs, size_t cap_results,
+                                             size_t *n_results) {
+    if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "program is NULL");
+    if (index >= p->refs.size()) return fail(SAF_ERR_INVALID_ARGUMENT, "component index out of range");
+    const RefProgram &r = p->refs[index];
+    if (n_words) *n_words = r.flat.size();
+    if (n_consts) *n_consts = r.consts.size();
+    if (n_pool) *n_pool = r.pool.size();
+    if (n_results) *n_results = r.result_regs.size();
+    if (param_count) *param_count = r.param_count;
+    if (workspace_size) *workspace_size = r.workspace_size;
+    if (flat) std::memcpy(flat, r.flat.data(), std::min(cap_words, r.flat.size()) * 4);
+    if (consts) std::memcpy(consts, r.consts.data(), std::min(cap_consts, r.consts.size()) * 8);
+    if (arg_pool) std::memcpy(arg_pool, r.pool.data(), std::min(cap_pool, r.pool.size()) * 4);
+    if (result_regs) std::memcpy(result_regs, r.result_regs.data(), std::min(cap_results, r.result_regs.size()) * 4);
+    return SAF_OK;
+}
+
 extern "C" void saf_program_destroy(saf_program *p) {
     if (!p) return;
     for (auto &kv : p->copies) {

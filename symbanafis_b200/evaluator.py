@@ -71,7 +71,23 @@ class CompiledEvaluator:
     def __init__(self, expr, params: Optional[Sequence[str]] = None, context=None):
         if context is not None:
             raise RuntimeError("UnsupportedExpression: user-function contexts are not supported")
-        exprs = [_as_expr(e) for e in expr] if isinstance(expr, (list, tuple)) else [_as_expr(expr)]
+        raw = list(expr) if isinstance(expr, (list, tuple)) else [expr]
+        if params is not None and raw and all(isinstance(e, str) for e in raw):
+            # expression STRINGS with an explicit parameter list compile in C++ behind the C ABI (saf_compile_exprs,
+            # csrc/compile.cpp): no Python on the way from the source text to the device program
+            names = [str(p) for p in params]
+            try:
+                self._h = _lib.DeviceProgramHandle.compile(raw, names)
+            except _lib.SafError as e:
+                if e.code == _lib.SAF_ERR_INVALID_ARGUMENT:
+                    raise ValueError(e.message) from None
+                _raise_from_saf(e)
+            flat, consts, pool, pc, ws, rr = self._h.reference_payload()
+            self.program = Program(flat=flat, consts=consts, arg_pool=pool, param_count=pc, workspace_size=ws,
+                                   result_regs=rr, param_names=names)
+            self.n_results = len(rr)
+            return
+        exprs = [_as_expr(e) for e in raw]
         if params is None:  # compile_auto: alphabetical, known constants excluded (api.rs:461-473)
             names = sorted({v for e in exprs for v in e.variables()} - set(KNOWN_CONSTANTS))
         else:
