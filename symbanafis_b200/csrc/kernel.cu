@@ -415,7 +415,10 @@ __device__ __noinline__ unsigned long long hot_run(uint32_t smem32, uint32_t ctx
     // datapath: fewer issue slots, which pays when the machine is full (P >= 4; Clifford +5 %, Aizawa +15 %
     // against threaded).  The opcode travels one instruction ahead of its operands (uop.h): it is read from the
     // instruction itself only when the loop is entered.
-    constexpr bool THREADED = P <= 2;
+#ifndef SAF_THREADED_MAXP
+#define SAF_THREADED_MAXP 2
+#endif
+    constexpr bool THREADED = P <= SAF_THREADED_MAXP;
     uint32_t uop = lds_u32(pc + 28);
     int32_t fd;
     uint32_t fa, fb, cur, uop_now;

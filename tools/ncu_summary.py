@@ -7,7 +7,7 @@ rep, units = sys.argv[1], float(sys.argv[2])
 hot_n = int(sys.argv[sys.argv.index("--hot") + 1]) if "--hot" in sys.argv else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-h, v = rows[0], rows[2]
+h, units_row, v = rows[0], rows[1], rows[2]
 KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -18,7 +18,18 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
 for k in KEYS:
     if k in h:
-        print(f"{k:82s} {v[h.index(k)]}")
+        print(f"{k:82s} {v[h.index(k)]}" + (f" {units_row[h.index(k)]}" if k.startswith("dram__bytes") else ""))
+
+
+def _bytes(k):
+    if k not in h:
+        return None
+    val, unit = float(v[h.index(k)].replace(",", "")), units_row[h.index(k)].lower()
+    return val * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit, 1.0)
+
+
+print("DRAM_TRAFFIC_JSON " + __import__("json").dumps({"dram_bytes_read": _bytes("dram__bytes_read.sum"),
+                                                        "dram_bytes_write": _bytes("dram__bytes_write.sum")}))
 for i, k in enumerate(h):
     if "issue_stalled" in k and k.endswith("per_issue_active.ratio"):
         try:

@@ -47,6 +47,32 @@ __global__ void k_dfma_tput(double *sink, long long *cyc, int n, int lanes) {
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// DFMA whose addend / multiplier comes from the constant bank (what the lean sin / cos polynomials issue), and DFMA
+// with three distinct register operands: is either slower than the register-register-accumulator form of the probe?
+__device__ __constant__ double k_coef[8] = {1e-9, 2e-9, 3e-9, 4e-9, 5e-9, 6e-9, 7e-9, 8e-9};
+__global__ void k_dfma_const(double *sink, long long *cyc, int n, int mode) {
+    double a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = 1.0 + threadIdx.x * 1e-9 + k; b[k] = 1.0000001 + k * 1e-9; }
+    const double m = 1.0000001;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (mode == 0) a[k] = __fma_rn(a[k], m, k_coef[k]);          // constant-bank addend
+                else if (mode == 1) a[k] = __fma_rn(a[k], k_coef[k], m);      // constant-bank multiplier
+                else a[k] = __fma_rn(a[k], b[k], b[(k + 1) & 7]);             // three distinct registers
+            }
+    }
+    long long t1 = clock64();
+    double s = 0; for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.0) sink[0] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 __global__ void k_lds_lat(long long *cyc, int n) {
     __shared__ unsigned long long chain[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) chain[i] = ((i + 17) & 255) * 8;
@@ -213,6 +239,13 @@ int main() {
         CK(cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost));
         const double instr = (double)warps * n * 32.0; // warp-level DFMAs on the SM
         printf("dfma_tput lanes=%d warps=%d: %.3f SM-cycles per warp-DFMA (%.1f lanes/clk/SM)\n", lanes, warps, h[0] / instr, instr * lanes / h[0]);
+    }
+    for (int mode = 0; mode < 3; ++mode) for (int warps : {8, 16}) {
+        const int n = 2000; k_dfma_const<<<1, warps * 32>>>(sink, cyc, n, mode); CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost));
+        const double instr = (double)warps * n * 32.0;
+        const char *names[] = {"constant-bank addend", "constant-bank multiplier", "three registers"};
+        printf("dfma %s warps=%d: %.3f SM-cycles per warp-DFMA (%.1f lanes/clk/SM)\n", names[mode], warps, h[0] / instr, instr * 32 / h[0]);
     }
     { const int n = 2000; k_lds_lat<<<1, 32>>>(cyc, n); CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost)); printf("lds_lat %.2f cycles per dependent LDS.64\n", (double)h[0] / (n * 16.0)); }
