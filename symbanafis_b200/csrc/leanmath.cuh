@@ -173,7 +173,12 @@ __device__ __forceinline__ void sincos_n(const double (&x)[P], double (&s)[P], d
     bool slow = false;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
+#ifdef SAF_SINCOS_SEPARATE // build knob: the round-1 pair of separate kernels (32 FP64 instructions, bit-identical to Sin / Cos)
+        s[p] = sin_fast(x[p]);
+        c[p] = cos_fast(x[p]);
+#else
         sincos_fast(x[p], s[p], c[p]);
+#endif
         slow |= trig_slow(x[p]);
     }
     if (slow) {

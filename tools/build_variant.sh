@@ -12,4 +12,5 @@ cp $ROOT/symbanafis_b200/csrc/*.cu $ROOT/symbanafis_b200/csrc/*.cuh $ROOT/symban
 cp $ROOT/tools/patch_brx.py $SRC/tools/
 cp $ROOT/include/*.h $SRC/include/
 make -C $SRC/symbanafis_b200/csrc -j4 EXTRA="$*" OUT=$ROOT/build/variants/$NAME.so > $SRC/build.log 2>&1 || { grep -B2 -A6 "error" $SRC/build.log | head -40; exit 1; }
+rm -rf $SRC  # the sources were a copy: the snapshot that travels to the GPU box stays small
 ls -la $ROOT/build/variants/$NAME.so
