@@ -978,4 +978,4 @@ extern "C" int saf_measure_clifford_probe(size_t n_points, int iters, double *se
 
 extern "C" uint64_t saf_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-extern "C" const char *saf_version(void) { return "symbanafis-b200 0.1.0 (sm_100a)"; }
+extern "C" const char *saf_version(void) { return "symbanafis-b200 0.2.0 (sm_100a)"; }
