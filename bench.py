@@ -21,6 +21,11 @@ N > 1 is launched by torchrun (one rank per GPU); points are sharded per rank, t
 `e2e`          : the same step through the C-ABI host call (saf_iterate_host / saf_eval_host) with pinned HOST buffers:
                  H2D of the inputs and D2H of the results inside the timed region.
 `e2e_pageable` : the same with ordinary (pageable) NumPy arrays -- what a caller of the reference holds.
+`machine`      : which of the library's two machines ran the program (--machine): "specialized" (default) = the
+                 program's own straight-line sm_100a kernel, compiled once by saf_program_specialize before the timed
+                 region -- like CompiledEvaluator::compile, outside every timed region; its cost is reported in
+                 machine.compile_ms -- or "interpreter" = the bytecode interpreter kernel, which needs no compilation.
+                 Both return the same bits; "interpreter" beside each workload is the interpreter's device time.
 `--impl reference`: the reference's CPU algorithm (oracle port of the f64x4 + 256-point-chunk path, all host threads)
                  on a bounded sample of the same workload; same `config` object, byte for byte.
 """
@@ -56,6 +61,8 @@ def parse_args():
     ap.add_argument("--workload", default=HEADLINE)
     ap.add_argument("--points", type=int, default=0, help="points per GPU (0 = BASELINE.json size)")
     ap.add_argument("--iters", type=int, default=0, help="map iterations per step (0 = BASELINE.json value)")
+    ap.add_argument("--machine", default="specialized", choices=["specialized", "interpreter"],
+                    help="specialized: saf_program_specialize before the timed region (default); interpreter: never")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="headline workload only (profiling runs)")
     ap.add_argument("--no-c5-sharded", action="store_true")
@@ -130,10 +137,12 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
-def measured_traffic(workload_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the interpreter launch from the committed ncu captures of the
-    shipped build (profiles/r02_dram_traffic.json), or None when that workload has not been captured."""
-    for name in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
+def measured_traffic(workload_name, machine="interpreter"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel launch from the committed ncu captures of the shipped
+    build (profiles/r02_dram_traffic_specialized.json for the specialised kernels, profiles/r02_dram_traffic.json for the
+    interpreter), or None when that workload has not been captured."""
+    names = ("r02_dram_traffic_specialized.json",) if machine == "specialized" else ("r02_dram_traffic.json", "r01_dram_traffic.json")
+    for name in names:
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f).get(workload_name)
@@ -256,13 +265,29 @@ class Bench:
         from symbanafis_b200.sharding import max_over_ranks
         return max_over_ranks(vals, device=self.dev)
 
-    def handle(self, w):
+    def handle(self, w, machine=None):
         p = w.program
-        return self._lib.DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size,
-                                                    p.result_regs)
+        h = self._lib.DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size,
+                                                 p.result_regs)
+        if (machine or self.args.machine) == "specialized":
+            h.specialize()  # NVRTC, once per program, outside every timed region (reported: machine.compile_ms)
+        return h
+
+    def machine_info(self, h):
+        if self.args.machine != "specialized":
+            return {"name": "interpreter", "kernel": "saf_interp_* (bytecode interpreter, shared-memory register file)"}
+        si = h.specialized_info()
+        small = si.small_registers > 0 and si.registers <= 0
+        return {"name": "specialized", "kernel": "saf_spec (the program as straight-line sm_100a code, NVRTC)",
+                "shape": "small-batch" if small else "large-batch",
+                "points_per_thread": si.small_points_per_thread if small else si.points_per_thread,
+                "block_threads": si.small_block_threads if small else si.block_threads,
+                "registers": si.small_registers if small else si.registers,
+                "compile_ms": si.compile_ms + (si.small_compile_ms if si.small_compiled else 0.0),
+                "compile_note": "one-off, before the timed region (saf_program_specialize); the interpreter needs none"}
 
     # one workload, device-resident columns: K timed steps, CUDA events on the launching stream
-    def device_timed(self, h, w, cols_np, n, iters, steps, warmup):
+    def device_timed(self, h, w, cols_np, n, iters, steps, warmup, extras=True):
         torch = self.torch
         cols0 = [torch.from_numpy(c).to(self.dev) for c in cols_np]
         n_out = len(w.program.result_regs)
@@ -305,7 +330,7 @@ class Bench:
         # the 1 M-point single pass).  A 512-point launch of the same program on scratch columns after the flush
         # brings code and image back without touching the timed data; reported beside ms_per_step, never instead.
         warm_ms = None
-        if not w.iterated and steps > 0:
+        if not w.iterated and steps > 0 and extras:
             m_ = 512
             scr_in = [torch.zeros(m_, dtype=torch.float64, device=self.dev) for _ in cols0]
             scr_out = [torch.empty(m_, dtype=torch.float64, device=self.dev) for _ in range(n_out)]
@@ -322,7 +347,7 @@ class Bench:
             warm_ms = sum(wm) / len(wm)
         # sustained: back-to-back steps for >= 2 s (no flush, no host sync in between): clocks under a long load
         sustained = None
-        if w.name == HEADLINE and not self.args.no_workloads:
+        if w.name == HEADLINE and not self.args.no_workloads and extras:
             per = max(sum(ms) / len(ms), 1e-3)
             k = int(min(2000, max(10, 2200.0 / per)))
             reset()
@@ -371,13 +396,13 @@ class Bench:
         self.barrier()
         return 1e3 * sum(ts) / len(ts)
 
-    def roofline(self, info, w, n, iters, step_ms, full_size):
+    def roofline(self, info, w, n, iters, step_ms, full_size, machine=None):
         bytes_launch = info.bytes_per_point * n               # columns read + written once per launch
         slots_launch = info.fp64_slots * n * iters            # FP64 issue slots per launch
         t_hbm = bytes_launch / (self.hbm_gbs * 1e9)
         t_fp64 = slots_launch / self.fp64_peak if self.fp64_peak > 0 else 0.0
         dur = step_ms * 1e-3
-        traffic, traffic_src = measured_traffic(w.name) if full_size else (None, None)
+        traffic, traffic_src = measured_traffic(w.name, machine or self.args.machine) if full_size else (None, None)
         if t_fp64 >= t_hbm:
             achieved, peak = 2.0 * slots_launch / dur / 1e12, 2.0 * self.fp64_peak / 1e12
             return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -408,6 +433,11 @@ class Bench:
         e2e_steps = max(2, min(steps, 5))
         e2e_ms = self.e2e_timed(h, w, cols_np, n, iters, e2e_steps, pinned=True)
         e2e_pg_ms = self.e2e_timed(h, w, cols_np, n, iters, e2e_steps, pinned=False)
+        interp_ms = None
+        if self.args.machine == "specialized":  # the interpreter on the same columns, device-timed, for comparison
+            hi = self.handle(w, "interpreter")
+            interp_ms = self.device_timed(hi, w, cols_np, n, iters, max(2, min(steps, 3)), 3, extras=False)[0]
+            interp_ms = self.max_over_ranks([interp_ms])[0]
         step_ms, e2e_ms, e2e_pg_ms, t_wall = self.max_over_ranks([step_ms, e2e_ms, e2e_pg_ms, t_wall])
         if self.rank != 0:
             return None
@@ -420,11 +450,16 @@ class Bench:
             "device_program": {"instructions": info.n_dev_instructions, "slots": info.n_slots,
                                "constants": info.n_consts, "acc_forwards": info.n_acc_forwards},
             "roofline": self.roofline(info, w, n, iters, step_ms, n == w.n_points),
+            "machine": self.machine_info(h),
             "e2e": dict(value=units / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, host_memory="pinned", **io),
             "e2e_pageable": dict(value=units / (e2e_pg_ms * 1e-3), unit=UNIT, ms_per_step=e2e_pg_ms,
                                  host_memory="pageable (NumPy arrays, staged through the library's pinned ring)", **io),
             "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
         }
+        if interp_ms is not None:
+            out["interpreter"] = {"ms_per_step": interp_ms, "value": units / (interp_ms * 1e-3), "unit": UNIT,
+                                  "roofline_frac": self.roofline(info, w, n, iters, interp_ms, False)["frac"],
+                                  "note": "the same program and columns on the bytecode interpreter kernel (same bits)"}
         if sustained:
             out["sustained"] = sustained
         if warm_ms is not None:
@@ -584,7 +619,7 @@ def run_ours(args):
         hh = B.handle(ww)
         ms_, _, _, _, warm_ = B.device_timed(hh, ww, ww.make_inputs(nn, 1), nn, 1, 5, 3)
         big = {"config": config_for(ww, nn, 1, 1), "ms_per_step": ms_, "value": nn / (ms_ * 1e-3), "unit": UNIT,
-               "roofline": B.roofline(hh.info(), ww, nn, 1, ms_, False),
+               "roofline": B.roofline(hh.info(), ww, nn, 1, ms_, False), "machine": B.machine_info(hh),
                "note": "BASELINE.json configs[0] at 128 Mi points instead of 1 M: the streaming path (bulk-copied column tiles)"}
     c5 = None
     if full_run and not args.no_c5_sharded:
@@ -611,6 +646,8 @@ def run_ours(args):
             "config": main["config"],
             "device_program": main["device_program"],
             "roofline": main["roofline"],
+            "machine": main["machine"],
+            "interpreter": main.get("interpreter"),
             "ideal_kernel": main.get("ideal_kernel"),
             "sustained": main.get("sustained"),
             "cpu_baseline": main["cpu_baseline"],

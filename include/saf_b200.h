@@ -101,7 +101,7 @@ SAF_API int saf_program_fuse(const saf_program *const *programs, size_t n_progra
 /* Expression strings -> program, without Python or Rust (csrc/compile.cpp): the k
  * expressions are parsed (the reference's grammar subset: + - * / ^ **, unary minus, calls, implicit multiplication;
  * src/parser/logic/pratt.rs:87-120), lowered with the reference's instruction-selection rules
- * (src/evaluator/logic/bytecode/compile/codegen/lower/*.rs: MulAdd / MulSub / NegMulAdd, Square .. InvPow3_2 / Powi,
+ * (src/evaluator/logic/bytecode/compile/codegen/lower/ (all files): MulAdd / MulSub / NegMulAdd, Square .. InvPow3_2 / Powi,
  * ExpSqr / ExpSqrNeg / Builtin1{ExpNeg}, RecipExpm1, Sinc, u/c -> u*(1/c), Sin + Cos -> SinCos), value-numbered across
  * the k outputs, register-allocated (emit/reg_alloc.rs) and encoded (emit/assemble.rs) into ONE multi-output program
  * over `params` -- what CompiledEvaluator::compile produces, one register file for all outputs.  Compile errors
@@ -135,6 +135,47 @@ SAF_API int saf_program_intern(const uint32_t *flat_bytecode, size_t n_words,
 SAF_API void saf_program_cache_clear(void);
 
 SAF_API int saf_program_get_info(const saf_program *prog, saf_program_info *info);
+
+/* ---- specialised kernels -------------------------------------------------------------------
+ * The interpreter runs any program the moment it is created.  A caller that will evaluate ONE program over many
+ * points -- the case of CompiledEvaluator (compile once, api.rs:125-142, evaluate many times) -- can additionally have
+ * the program written out as a straight-line sm_100a kernel of its own: every live value a register, every constant an
+ * immediate, no instruction fetch, no dispatch (symbanafis_b200/csrc/spec.cpp generates the text from the same device
+ * program the interpreter runs, NVRTC compiles it; the statements are the interpreter's handlers, so both machines
+ * return the same bits).  After a successful call every saf_eval_* / saf_iterate_* of this program launches the
+ * specialised kernel.  Costs a run-time compilation (tens of milliseconds to seconds, saf_specialized_info.compile_ms);
+ * needs libnvrtc >= 12.8 at run time (SAF_ERR_UNSUPPORTED with the reason otherwise -- the program stays usable).
+ * Programs above 20000 device instructions are not specialised (SAF_ERR_UNSUPPORTED).
+ * Environment: SAF_SPECIALIZE=0 keeps every launch on the interpreter, =1 specialises every program at first launch. */
+SAF_API int saf_program_specialize(saf_program *prog);
+
+typedef struct saf_specialized_info {
+    int compiled;            /* 1 after a successful saf_program_specialize */
+    int can_iterate;         /* saf_iterate_* uses the specialised kernel too (results pair with parameters) */
+    int points_per_thread;   /* 1, 2 or 4 */
+    int block_threads;
+    int min_blocks;          /* __launch_bounds__ resident-block target the register allocation was given */
+    int registers;           /* per thread; -1 until the kernel has been loaded on the current device */
+    int local_bytes;         /* spill / local memory per thread; -1 until loaded */
+    int resident_blocks;     /* per SM on the current device; -1 until loaded */
+    double generate_ms;      /* writing the kernel text */
+    double compile_ms;       /* NVRTC */
+    size_t cubin_bytes;
+    size_t source_bytes;
+    /* the SMALL-BATCH shape: one point per thread in 128-thread blocks, compiled the first time a launch brings fewer
+     * points than 12 warps per SM at the shape above (50 k double pendulums: 2.9 ms against 4.3 ms) */
+    int small_compiled;
+    int small_points_per_thread;
+    int small_block_threads;
+    int small_registers;     /* -1 until loaded on the current device */
+    double small_compile_ms;
+} saf_specialized_info;
+SAF_API int saf_program_specialized_info(const saf_program *prog, saf_specialized_info *info);
+/* The generated CUDA C++ text (for inspection) of the large-batch (small_batch = 0) or the small-batch shape.
+ * Returns the bytes needed (excluding NUL); writes at most cap. */
+SAF_API size_t saf_program_specialized_source(const saf_program *prog, int small_batch, char *buf, size_t cap);
+/* 1 when a usable NVRTC can be loaded in this process, else 0 with the reason in saf_last_error(). */
+SAF_API int saf_specialize_available(void);
 
 /* Human-readable listing of the lowered device program (cf. CompiledEvaluator::disassemble,
  * api.rs:190-267).  Returns the number of bytes needed (excluding NUL); writes at most cap. */

@@ -44,6 +44,16 @@ class ProgramInfo(C.Structure):
     ]
 
 
+class SpecializedInfo(C.Structure):
+    _fields_ = [
+        ("compiled", C.c_int), ("can_iterate", C.c_int), ("points_per_thread", C.c_int), ("block_threads", C.c_int),
+        ("min_blocks", C.c_int), ("registers", C.c_int), ("local_bytes", C.c_int), ("resident_blocks", C.c_int),
+        ("generate_ms", C.c_double), ("compile_ms", C.c_double), ("cubin_bytes", C.c_size_t), ("source_bytes", C.c_size_t),
+        ("small_compiled", C.c_int), ("small_points_per_thread", C.c_int), ("small_block_threads", C.c_int),
+        ("small_registers", C.c_int), ("small_compile_ms", C.c_double),
+    ]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile ``csrc/`` with nvcc (``-gencode arch=compute_100a,code=sm_100a -lineinfo``)."""
     args = ["make", "-C", CSRC]
@@ -66,6 +76,7 @@ EXPORTED_SYMBOLS = [
     "saf_eval_host_multi", "saf_iterate_device", "saf_iterate_host", "saf_last_error",
     "saf_device_count", "saf_kernel_launch_count", "saf_version", "saf_measure_fp64_peak",
     "saf_measure_clifford_probe", "saf_compile_exprs", "saf_program_reference_payload",
+    "saf_program_specialize", "saf_program_specialized_info", "saf_program_specialized_source", "saf_specialize_available",
 ]
 
 
@@ -123,6 +134,14 @@ def lib() -> C.CDLL:
     L.saf_measure_clifford_probe.argtypes = [sz, C.c_int, C.POINTER(C.c_double)]
     L.saf_measure_clifford_probe.restype = C.c_int
     L.saf_version.restype = C.c_char_p
+    L.saf_program_specialize.argtypes = [vp]
+    L.saf_program_specialize.restype = C.c_int
+    L.saf_program_specialized_info.argtypes = [vp, C.POINTER(SpecializedInfo)]
+    L.saf_program_specialized_info.restype = C.c_int
+    L.saf_program_specialized_source.argtypes = [vp, C.c_int, C.c_char_p, sz]
+    L.saf_program_specialized_source.restype = sz
+    L.saf_specialize_available.argtypes = []
+    L.saf_specialize_available.restype = C.c_int
     _lib = L
     return L
 
@@ -141,6 +160,11 @@ def ptr_array(ptrs: Sequence[int]):
 
 def size_array(vals: Sequence[int]):
     return (C.c_size_t * max(1, len(vals)))(*vals)
+
+
+def specialize_available() -> bool:
+    """Can specialised kernels be compiled in this process (NVRTC >= 12.8 loadable)?"""
+    return bool(lib().saf_specialize_available())
 
 
 def device_count() -> int:
@@ -236,6 +260,23 @@ class DeviceProgramHandle:
         info = ProgramInfo()
         check(lib().saf_program_get_info(self._h, C.byref(info)))
         return info
+
+    def specialize(self) -> "SpecializedInfo":
+        """Compiles this program into a straight-line sm_100a kernel of its own (saf_program_specialize): every later
+        eval_* / iterate_* of this handle launches it instead of the interpreter.  Same bits, no dispatch."""
+        check(lib().saf_program_specialize(self._h))
+        return self.specialized_info()
+
+    def specialized_info(self) -> "SpecializedInfo":
+        info = SpecializedInfo()
+        check(lib().saf_program_specialized_info(self._h, C.byref(info)))
+        return info
+
+    def specialized_source(self, small_batch: bool = False) -> str:
+        n = lib().saf_program_specialized_source(self._h, int(small_batch), None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().saf_program_specialized_source(self._h, int(small_batch), buf, n + 1)
+        return buf.value.decode()
 
     def disassemble(self) -> str:
         n = lib().saf_program_disassemble(self._h, None, 0)

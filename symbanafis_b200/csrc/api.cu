@@ -8,6 +8,7 @@
 // one launch for device buffers.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,6 +26,7 @@
 #include "lower.h"
 #include "pack.h"
 #include "ruop.h"
+#include "spec.h"
 
 using namespace saf;
 
@@ -60,6 +62,19 @@ struct saf_program {
     // shared-memory sizes may ask for different widths concurrently, saf_eval_host_multi)
     std::map<int, PackedProgram> packed_wide;
     std::map<std::pair<int, int>, unsigned char *> copies; // (device, P) -> global-memory image for big programs
+    // specialised kernel (spec.h): generated and compiled once by saf_program_specialize, loaded per device on first use
+    // [0]: the shape for batches that fill the machine (compiled by saf_program_specialize); [1]: the small-batch shape,
+    // compiled the first time a launch needs it (spec.h spec_batch_is_small)
+    struct Spec {
+        bool attempted = false;
+        int rc = SAF_OK;
+        std::string err, text;
+        std::vector<char> cubin;
+        SpecShape shape;
+        bool can_iterate = false;
+        double generate_ms = 0.0, compile_ms = 0.0;
+        std::map<int, SpecModule> modules; // by device; entries never move
+    } spec[2];
 };
 
 constexpr int LAYOUT_R = 100 + R_POINTS; // layout id of the register machine
@@ -169,6 +184,14 @@ extern "C" int saf_program_reference_payload(const saf_program *p, size_t index,
 
 extern "C" void saf_program_destroy(saf_program *p) {
     if (!p) return;
+    for (auto &sp : p->spec)
+        for (auto &kv : sp.modules) {
+            int prev = 0;
+            if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(kv.first) == cudaSuccess) {
+                spec_module_unload(&kv.second);
+                cudaSetDevice(prev);
+            }
+        }
     for (auto &kv : p->copies) {
         int prev = 0;
         if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(kv.first.first) == cudaSuccess) {
@@ -293,6 +316,144 @@ extern "C" int saf_program_export(const saf_program *p, uint64_t *code, size_t c
     return SAF_OK;
 }
 
+
+// ---- specialised kernels (spec.h) ------------------------------------------------------------------------------------
+// SAF_SPECIALIZE: 0 = never launch a specialised kernel (the interpreter runs even after saf_program_specialize);
+// 1 = specialise every program at its first launch (how the whole GPU test-suite is run against this machine);
+// unset = specialised kernels run for the programs saf_program_specialize was called on.
+static int specialize_mode() {
+    static const int mode = []() {
+        const char *v = getenv("SAF_SPECIALIZE");
+        return !v || !*v ? -1 : (v[0] == '0' ? 0 : 1);
+    }();
+    return mode;
+}
+
+static int specialize_locked(saf_program *p, int variant = 0) { // p->mu held
+    saf_program::Spec &sp = p->spec[variant];
+    if (sp.attempted) return sp.rc;
+    sp.attempted = true;
+    const auto t0 = std::chrono::steady_clock::now();
+    sp.shape = spec_shape_for(p->dev, variant == 1);
+    sp.rc = spec_generate(p->dev, sp.shape, sp.text, sp.can_iterate, sp.err);
+    const auto t1 = std::chrono::steady_clock::now();
+    sp.generate_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (sp.rc != SAF_OK) return sp.rc;
+    sp.rc = jit_compile(sp.text, sp.cubin, sp.err);
+    sp.compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    return sp.rc;
+}
+
+extern "C" int saf_program_specialize(saf_program *p) {
+    if (!p) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL program");
+    std::lock_guard<std::mutex> lk(p->mu);
+    const int rc = specialize_locked(p);
+    if (rc != SAF_OK) return fail(rc, "specialisation failed: " + p->spec[0].err);
+    return SAF_OK;
+}
+
+extern "C" int saf_program_specialized_info(const saf_program *p, saf_specialized_info *info) {
+    if (!p || !info) return fail(SAF_ERR_INVALID_ARGUMENT, "NULL argument");
+    saf_program *mp = const_cast<saf_program *>(p);
+    std::lock_guard<std::mutex> lk(mp->mu);
+    const saf_program::Spec &sp = p->spec[0];
+    std::memset(info, 0, sizeof *info);
+    info->compiled = sp.attempted && sp.rc == SAF_OK;
+    info->can_iterate = sp.can_iterate;
+    info->points_per_thread = sp.shape.points_per_thread;
+    info->block_threads = sp.shape.block;
+    info->min_blocks = sp.shape.min_blocks;
+    info->generate_ms = sp.generate_ms;
+    info->compile_ms = sp.compile_ms;
+    info->cubin_bytes = sp.cubin.size();
+    info->source_bytes = sp.text.size();
+    info->registers = -1;
+    info->local_bytes = -1;
+    info->resident_blocks = -1;
+    info->small_registers = -1;
+    const saf_program::Spec &sm = p->spec[1];
+    info->small_compiled = sm.attempted && sm.rc == SAF_OK;
+    info->small_points_per_thread = sm.shape.points_per_thread;
+    info->small_block_threads = sm.shape.block;
+    info->small_compile_ms = sm.compile_ms;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        auto it = sp.modules.find(dev);
+        if (it != sp.modules.end()) {
+            info->registers = it->second.registers;
+            info->local_bytes = it->second.local_bytes;
+            info->resident_blocks = it->second.resident_blocks;
+        }
+        it = sm.modules.find(dev);
+        if (it != sm.modules.end()) info->small_registers = it->second.registers;
+    }
+    return SAF_OK;
+}
+
+extern "C" size_t saf_program_specialized_source(const saf_program *p, int small_batch, char *buf, size_t cap) {
+    if (!p) return 0;
+    saf_program *mp = const_cast<saf_program *>(p);
+    std::lock_guard<std::mutex> lk(mp->mu);
+    const std::string &s = p->spec[small_batch ? 1 : 0].text;
+    if (buf && cap) {
+        const size_t n = std::min(cap - 1, s.size());
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size();
+}
+
+extern "C" int saf_specialize_available(void) {
+    std::string why;
+    if (jit_available(why)) return 1;
+    g_last_error = why;
+    return 0;
+}
+
+// The specialised kernel of `prog` for a batch of n_points on the current device, or nullptr when the interpreter
+// should run.
+static int spec_for_launch(const saf_program *prog, uint64_t iters, size_t n_points, const SpecModule **out, SpecShape *shape) {
+    *out = nullptr;
+    const int mode = specialize_mode();
+    if (mode == 0) return SAF_OK;
+    saf_program *mp = const_cast<saf_program *>(prog);
+    std::lock_guard<std::mutex> lk(mp->mu);
+    if (!mp->spec[0].attempted) {
+        if (mode != 1) return SAF_OK;
+        // automatic mode: programs that cannot be specialised (too long, no NVRTC) keep running on the interpreter
+        if (specialize_locked(mp) != SAF_OK) return SAF_OK;
+    }
+    if (mp->spec[0].rc != SAF_OK) return SAF_OK;
+    int dev = 0, sms = 0;
+    SAF_CUDA(cudaGetDevice(&dev));
+    SAF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int variant = spec_batch_is_small(mp->spec[0].shape, n_points, sms) ? 1 : 0;
+    if (const char *v = getenv("SAF_SPEC_VARIANT")) variant = v[0] == 's' ? 1 : v[0] == 'l' ? 0 : variant; // test knob
+    // the small-batch shape is compiled the first time a small batch arrives; if that fails the large shape runs
+    if (variant == 1 && specialize_locked(mp, 1) != SAF_OK) variant = 0;
+    saf_program::Spec &sp = mp->spec[variant];
+    if (iters > 1 && !sp.can_iterate) return SAF_OK;
+    auto it = sp.modules.find(dev);
+    if (it == sp.modules.end()) {
+        SpecModule m;
+        cudaError_t e = spec_module_load(sp.cubin.data(), &m);
+        if (e != cudaSuccess) return cuda_fail(e, "loading the specialised kernel");
+        if (m.max_threads < sp.shape.block) {
+            spec_module_unload(&m);
+            return fail(SAF_ERR_CUDA, "specialised kernel cannot run " + std::to_string(sp.shape.block) + " threads per block");
+        }
+        e = spec_module_occupancy(&m, sp.shape.block);
+        if (e != cudaSuccess) {
+            spec_module_unload(&m);
+            return cuda_fail(e, "occupancy of the specialised kernel");
+        }
+        it = sp.modules.emplace(dev, m).first;
+    }
+    *out = &it->second;
+    *shape = sp.shape;
+    return SAF_OK;
+}
+
 constexpr uint64_t kMaxItersPerLaunch = 1ull << 30;
 
 // ---- launch -------------------------------------------------------------------------------------------
@@ -344,6 +505,33 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
                             cudaStream_t stream) {
     if (n_points == 0) return SAF_OK;
     const DeviceProgram &dp = prog->dev;
+    {
+        const SpecModule *sm = nullptr;
+        SpecShape ss;
+        const int src = spec_for_launch(prog, iters, n_points, &sm, &ss);
+        if (src != SAF_OK) return src;
+        if (sm != nullptr) {
+            SpecDesc sd;
+            std::memset(&sd, 0, sizeof sd);
+            sd.n_points = n_points;
+            sd.iters = iters ? iters : 1;
+            for (uint32_t j = 0; j < dp.param_count; ++j) {
+                if (j < n_cols && cols[j] != nullptr) {
+                    sd.cols[j] = cols[j];
+                    sd.col_len[j] = lens[j];
+                }
+            }
+            for (size_t k = 0; k < dp.result_field.size(); ++k) sd.outs[k] = outs[k];
+            const unsigned long long tile = (unsigned long long)ss.block * (unsigned long long)ss.points_per_thread;
+            const unsigned long long n_tiles = (n_points + tile - 1) / tile;
+            unsigned long long grid = (unsigned long long)sm->sms * (unsigned long long)sm->resident_blocks;
+            if (grid > n_tiles) grid = n_tiles;
+            cudaError_t e = spec_launch(*sm, sd, (int)grid, ss.block, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "specialised kernel launch");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return SAF_OK;
+        }
+    }
     LaunchDesc d;
     std::memset(&d, 0, sizeof d);
     d.n_points = n_points;

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "kernel.cuh"
+#include "spec.h"
 
 // the patched, ptxas-compiled kernel image
 asm(".section .rodata\n"
@@ -45,6 +46,9 @@ struct Driver {
     CUresult (*func_set_attribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*launch)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                        void **, void **) = nullptr;
+    CUresult (*module_unload)(CUmodule) = nullptr;
+    CUresult (*occupancy)(int *, CUfunction, int, size_t) = nullptr;
+    CUresult (*func_get_attribute)(int *, CUfunction_attribute, CUfunction) = nullptr;
     bool ready = false;
 } g_drv;
 
@@ -96,6 +100,9 @@ cudaError_t module_for_current_device(DeviceModule **out) {
             if ((e = entry("cuModuleGetFunction", &g_drv.module_get_function)) != cudaSuccess) return e;
             if ((e = entry("cuFuncSetAttribute", &g_drv.func_set_attribute)) != cudaSuccess) return e;
             if ((e = entry("cuLaunchKernel", &g_drv.launch)) != cudaSuccess) return e;
+            if ((e = entry("cuModuleUnload", &g_drv.module_unload)) != cudaSuccess) return e;
+            if ((e = entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", &g_drv.occupancy)) != cudaSuccess) return e;
+            if ((e = entry("cuFuncGetAttribute", &g_drv.func_get_attribute)) != cudaSuccess) return e;
             g_drv.ready = true;
         }
         CUresult r = g_drv.module_load_data(&m.mod, saf_kernel_cubin);
@@ -166,6 +173,55 @@ cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape,
     void *args[] = {const_cast<LaunchDesc *>(&desc)};
     return as_cuda(g_drv.launch(m->interp[k], (unsigned)shape.grid, 1, 1, (unsigned)shape.block, 1, 1,
                                 (unsigned)shape.smem_bytes, (CUstream)stream, args, nullptr));
+}
+
+// ---- specialised kernels (spec.h): one module per program and device, loaded from the cubin NVRTC produced ----------
+cudaError_t spec_module_load(const void *cubin, SpecModule *out) {
+    DeviceModule *m = nullptr;
+    cudaError_t e = module_for_current_device(&m); // driver entry points + primary context
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    CUmodule mod = nullptr;
+    CUresult r = g_drv.module_load_data(&mod, cubin);
+    if (r != CUDA_SUCCESS) return as_cuda(r);
+    CUfunction f = nullptr;
+    r = g_drv.module_get_function(&f, mod, "saf_spec");
+    int threads = 0, regs = 0, local = 0, resident = 0;
+    if (r == CUDA_SUCCESS) r = g_drv.func_get_attribute(&threads, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, f);
+    if (r == CUDA_SUCCESS) r = g_drv.func_get_attribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, f);
+    if (r == CUDA_SUCCESS) r = g_drv.func_get_attribute(&local, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f);
+    if (r != CUDA_SUCCESS) {
+        g_drv.module_unload(mod);
+        return as_cuda(r);
+    }
+    out->module = mod;
+    out->function = f;
+    out->registers = regs;
+    out->local_bytes = local;
+    out->max_threads = threads;
+    out->sms = sms;
+    out->resident_blocks = resident;
+    return cudaSuccess;
+}
+
+cudaError_t spec_module_occupancy(SpecModule *m, int block) {
+    int resident = 0;
+    CUresult r = g_drv.occupancy(&resident, (CUfunction)m->function, block, 0);
+    if (r != CUDA_SUCCESS) return as_cuda(r);
+    m->resident_blocks = resident < 1 ? 1 : resident;
+    return cudaSuccess;
+}
+
+void spec_module_unload(SpecModule *m) {
+    if (m->module && g_drv.module_unload) g_drv.module_unload((CUmodule)m->module);
+    m->module = m->function = nullptr;
+}
+
+cudaError_t spec_launch(const SpecModule &m, const SpecDesc &desc, int grid, int block, cudaStream_t stream) {
+    void *args[] = {const_cast<SpecDesc *>(&desc)};
+    return as_cuda(g_drv.launch((CUfunction)m.function, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, 0, (CUstream)stream, args, nullptr));
 }
 
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream) {

@@ -140,6 +140,16 @@ class CompiledEvaluator:
     def handle(self) -> _lib.DeviceProgramHandle:
         return self._h
 
+    def specialize(self):
+        """Compiles this evaluator's program into a straight-line sm_100a kernel of its own (saf_program_specialize):
+        every later eval_batch / run_chunked / iterate / *_device call launches it instead of the interpreter and
+        returns the same bits.  Worth its one-off compilation (tenths of a second; seconds for thousands of
+        instructions) when the evaluator is used on many points.  Returns the library's saf_specialized_info."""
+        try:
+            return self._h.specialize()
+        except _lib.SafError as err:
+            _raise_from_saf(err)
+
     # -- evaluation -------------------------------------------------------------------------------
     def evaluate(self, input) -> float:  # noqa: A002 - the reference's name
         """Single point (evaluator.rs:57-61); missing parameters read as 0 (scalar.rs:93-108)."""

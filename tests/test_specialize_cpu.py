@@ -1,0 +1,97 @@
+"""Host half of the specialised kernels (csrc/spec.cpp, jit.cpp), no GPU: the generated text and the NVRTC compilation.
+
+NVRTC is a compiler: it runs without a device, so the whole path up to the cubin is checked here; what the cubin
+computes is checked on the GPU (tests/test_gpu_specialized.py: same bits as the interpreter)."""
+import re
+
+import numpy as np
+import pytest
+
+from symbanafis_b200 import workloads
+from symbanafis_b200._lib import DeviceProgramHandle, SafError, specialize_available
+from symbanafis_b200.compiler import compile_exprs
+from symbanafis_b200.expr import parse
+
+needs_nvrtc = pytest.mark.skipif(not specialize_available(), reason="no libnvrtc >= 12.8 in this container")
+
+
+def _handle(prog):
+    return DeviceProgramHandle.create(prog.flat, prog.consts, prog.arg_pool, prog.param_count, prog.workspace_size,
+                                      prog.result_regs)
+
+
+@needs_nvrtc
+@pytest.mark.parametrize("name", ["single_expr", "clifford", "aizawa", "double_pendulum"])
+def test_named_programs_compile_for_sm_100a(name):
+    w = workloads.get(name)
+    h = _handle(w.program)
+    before = h.specialized_info()
+    assert before.compiled == 0 and before.cubin_bytes == 0
+    info = h.specialize()
+    assert info.compiled == 1 and info.cubin_bytes > 1000 and info.compile_ms > 0
+    assert info.points_per_thread in (1, 2, 4) and info.block_threads % 32 == 0
+    assert info.registers == -1, "no device here: the kernel cannot have been loaded"
+    assert info.can_iterate == (1 if w.iterated else 0) or not w.iterated
+    again = h.specialize()  # idempotent: compiled once
+    assert again.compile_ms == info.compile_ms
+
+
+@needs_nvrtc
+def test_generated_text_is_the_device_program_statement_by_statement():
+    # C1: x^2 + sin(x)*exp(-x)  ->  Square, Sin, ExpNeg, MulAdd; four points per thread
+    w = workloads.get("single_expr")
+    h = _handle(w.program)
+    info = h.specialize()
+    src = h.specialized_source()
+    n_instr = h.info().n_dev_instructions
+    assert len(re.findall(r"// \[\d+\]", src)) == n_instr
+    P = info.points_per_thread
+    assert src.count("__dmul_rn(") >= P  # the square, once per point
+    assert src.count("sp::sin_v(") == 1 and src.count("sp::exp_v(") == 1 and src.count("__fma_rn(") == P
+    assert "lm::" not in src and "for (int p" not in src, "statements are written out per point: no arrays, no loops"
+    # constants travel as bit patterns
+    for k in re.findall(r"const double k\d+ = (\S+);", src):
+        assert k.startswith("__longlong_as_double(0x")
+    assert f"#define SPEC_P {P}" in src and "#include \"spec_prelude.cuh\"" in src
+
+
+@needs_nvrtc
+def test_constant_bits_survive_including_negative_zero_and_nan():
+    prog = compile_exprs([parse("x + 0.1"), parse("x * 3.0")], ["x"])
+    h = _handle(prog)
+    h.specialize()
+    src = h.specialized_source()
+    assert f"0x{np.float64(0.1).view(np.uint64):016x}" in src
+
+
+@needs_nvrtc
+def test_iteration_feedback_is_emitted_only_when_results_pair_with_parameters():
+    it = _handle(workloads.get("clifford").program)
+    assert it.specialize().can_iterate == 1
+    assert re.search(r"if \(\+\+it >= d\.iters\) break;\n\s+s\d+_0 = ", it.specialized_source())
+    one = _handle(compile_exprs([parse("x*y")], ["x", "y"]))  # one result, two parameters
+    assert one.specialize().can_iterate == 0
+    assert not re.search(r"if \(\+\+it >= d\.iters\) break;\n\s+s\d+_0 = ", one.specialized_source())
+
+
+@needs_nvrtc
+def test_many_transcendentals_are_called_not_inlined():
+    few = _handle(workloads.get("clifford").program)
+    few.specialize()
+    assert "#define SPEC_OUTLINE" not in few.specialized_source()
+    terms = " + ".join(f"sin({1 + 0.1 * k}*x)*exp(-{0.2 + 0.01 * k}*x)" for k in range(20))
+    many = _handle(compile_exprs([parse(terms)], ["x"]))
+    many.specialize()
+    assert "#define SPEC_OUTLINE 1" in many.specialized_source()
+
+
+def test_programs_above_the_limit_are_refused_and_stay_usable(monkeypatch):
+    monkeypatch.setenv("SAF_SPEC_MAX_INSTRUCTIONS", "10")  # the shipped limit is 20000 device instructions
+    prog = workloads.get("aizawa").program
+    h = _handle(prog)
+    assert h.info().n_dev_instructions > 10
+    with pytest.raises(SafError) as ei:
+        h.specialize()
+    assert ei.value.code == 6 and "interpreted" in ei.value.message
+    assert h.specialized_info().compiled == 0
+    assert h.info().n_dev_instructions > 10  # the handle is intact
