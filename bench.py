@@ -331,7 +331,9 @@ class Bench:
         # brings code and image back without touching the timed data; reported beside ms_per_step, never instead.
         warm_ms = None
         if not w.iterated and steps > 0 and extras:
-            m_ = 512
+            # (the specialised machine picks its kernel by batch size: the scratch launch must be large enough to run
+            # the SAME kernel as the timed launch -- 256 Ki points, 4 MB of L2)
+            m_ = 512 if self.args.machine == "interpreter" else min(n, 256 * 1024)
             scr_in = [torch.zeros(m_, dtype=torch.float64, device=self.dev) for _ in cols0]
             scr_out = [torch.empty(m_, dtype=torch.float64, device=self.dev) for _ in range(n_out)]
             wm = []

@@ -86,6 +86,13 @@ int env_int(const char *name, int dflt) {
 } // namespace
 
 namespace {
+size_t n_trig_exp(const std::vector<Ins> &ins) {
+    size_t n = 0;
+    for (const Ins &i : ins)
+        n += i.op == D_SIN || i.op == D_COS || i.op == D_EXP || i.op == D_EXPSQR || i.op == D_EXPSQRNEG || i.op == D_EXPNEG ||
+             i.op == D_SINCOS;
+    return n;
+}
 size_t count_instructions(const DeviceProgram &dp, size_t *n_heavy) {
     std::vector<Ins> ins;
     std::string err;
@@ -108,17 +115,27 @@ SpecShape spec_shape_for(const DeviceProgram &dp, bool small_batch) {
     // latency inside one warp, and a column tile is two 16-byte loads per thread); fewer as the live set grows, where
     // the resident warps provide the overlap instead.
     if (long_program) {
-        // 100 KB of straight-line code: ONE block of 512 threads per SM that walks it in step (barriers, below) -- four
-        // points per thread while the slots fit 128 registers (measured on the 110-term gradient, 20 M points:
-        // 128 x 5 blocks, no barriers 23.6 ms; 512 threads, barrier every 400 statements: P = 2 16.6 ms, P = 4 15.9 ms)
-        s.points_per_thread = dp.n_slots <= 12 ? 4 : dp.n_slots <= 28 ? 2 : 1;
+        // 100 KB of straight-line code: ONE block of 512 threads per SM that walks it in step (barriers, below), two
+        // points per thread (measured on the 110-term gradient, 20 M points: 128 threads x 5 blocks, no barriers 23.6 ms;
+        // 512 threads, barrier every 400 statements: P = 2 16.6 ms, 84 registers, 3.7 s of NVRTC; P = 4 15.9 ms, 128
+        // registers and 9.4 s -- not worth the compile time)
+        s.points_per_thread = dp.n_slots <= 28 ? 2 : 1;
         s.block = 512;
         s.min_blocks = 1;
         s.sync_every = 400;
     } else {
         s.points_per_thread = dp.n_slots <= 10 ? 4 : dp.n_slots <= 28 ? 2 : 1;
         s.block = 128;
-        s.min_blocks = s.points_per_thread == 4 ? 3 : 4; // 168 / 128 registers per thread
+        s.min_blocks = s.points_per_thread == 4 ? 5 : 4; // <= 102 / 128 registers per thread
+        // Programs with four or more transcendental leaves bring their own independent dependency chains (speculation,
+        // spec_generate: the leaves of one point interleave): two points per thread and more resident warps then beat
+        // four points per thread (Clifford map, 4 leaves: P = 4 4.95 ms, P = 2 at <= 80 registers 4.81 ms)
+        std::vector<Ins> ins;
+        std::string err;
+        if (s.points_per_thread == 4 && decode(dp, ins, err) && n_trig_exp(ins) >= 4) {
+            s.points_per_thread = 2;
+            s.min_blocks = 6;
+        }
     }
     if (small_batch) {
         // few points: every point its own thread, narrow blocks so that they spread over all SMs, no register cap
@@ -138,6 +155,7 @@ SpecShape spec_shape_for(const DeviceProgram &dp, bool small_batch) {
     // leaves with a body of tens of instructions: beyond a few dozen inlined copies they are called instead (one copy
     // per module; the pendulum's 32 call sites inline: 2.86 ms against 3.70 ms called)
     s.outline = n_heavy * (size_t)s.points_per_thread > (size_t)env_int("SAF_SPEC_INLINE_MAX", 64);
+    s.speculate = env_int("SAF_SPEC_SPECULATE", 1) != 0;
     return s;
 }
 
@@ -226,6 +244,10 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
     // that each warp walks once per tile; left alone the warps drift apart, every warp streams its own copy from L2 and
     // the kernel waits for instructions (ncu: stall_no_instruction 4.3 per issue, profiles/r02_g_*).
     const int sync_every = shape.sync_every;
+    int emit_rc = SAF_OK;
+    // fast: the speculative copy of the body -- transcendental leaves take their fast path unconditionally and only
+    // record whether an argument was outside it (slow_t_ / slow_e_); see `speculate` below
+    auto emit_body = [&](bool fast) {
     for (size_t n = 0; n < ins.size(); ++n) {
         const Ins &i = ins[n];
         if (sync_every > 0 && n > 0 && n % (size_t)sync_every == 0) os << "      __syncthreads();\n";
@@ -245,11 +267,15 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
                 if (!pre.empty()) os << "      a_.v[" << p << "] = " << subst(pre, i, p) << ";\n";
             }
         };
-        auto leaf = [&](const char *fn) {
-            os << "      { const sp::Vec<P> r_ = sp::" << fn << "(a_);";
+        auto leaf = [&](const char *fn_careful) {
+            std::string fn = fn_careful;
+            if (fast) fn = fn.substr(0, fn.size() - 1) + (fn == "exp_v" ? "f(a_, slow_e_)" : "f(a_, slow_t_)");
+            else fn += "(a_)";
+            os << "      { const sp::Vec<P> r_ = sp::" << fn << ";";
             for (int p = 0; p < P; ++p) os << " acc_" << p << " = r_.v[" << p << "];";
             os << " }\n";
         };
+        (void)fast;
         const std::string fn = std::to_string(i.imm) + "u";
         os << "      { // [" << n << "]\n";
         bool writes_acc = true;
@@ -277,7 +303,7 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
         case D_RECIPEXPM1: arg_vec(""); scalar("sp::recip_expm1_($v)"); break;
         case D_SINCOS:
             arg_vec("");
-            os << "      const sp::Vec2<P> r_ = sp::sincos_v(a_);\n";
+            os << "      const sp::Vec2<P> r_ = sp::" << (fast ? "sincos_f(a_, slow_t_)" : "sincos_v(a_)") << ";\n";
             for (int p = 0; p < P; ++p) {
                 os << "      acc_" << p << " = r_.s[" << p << "];";
                 if (field_kind(i.fc) == KIND_S) os << " " << val(i.fc, p) << " = r_.c[" << p << "];";
@@ -308,12 +334,40 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
         case D_FNMS: scalar("__fma_rn(-$a, $b, -$c)"); break;
         default:
             err = "device opcode " + std::to_string(i.op) + " has no specialised form";
-            return SAF_ERR_UNSUPPORTED;
+            emit_rc = SAF_ERR_UNSUPPORTED;
+            return;
         }
         if (writes_acc && field_kind(i.fd) == KIND_S)
             for (int p = 0; p < P; ++p) os << "      " << val(i.fd, p) << " = acc_" << p << ";\n";
         os << "      }\n";
     }
+    };
+
+    // Speculation (programs whose leaves are inlined): every sin / cos / sincos / exp ends in "if the argument was
+    // outside the fast range, call the math library" -- a branch per leaf, i.e. a scheduling barrier per leaf: the
+    // compiler cannot interleave the dependent FMA chains of two independent leaves, and a program with few points has
+    // nothing else to hide their latency with (double pendulum: 24 leaves per RK4 step, 10 warps per SM).  So the body
+    // is written twice.  The first copy takes every fast path unconditionally and only records the largest |argument|
+    // it saw; it is ONE basic block between divisions.  If an argument was outside the fast range -- per thread, rare --
+    // the parameters are restored and the second, careful copy (the leaves with their branches) recomputes the
+    // iteration.  Where the fast path applies the careful leaf returns the fast path's value, so the bits are the same.
+    const bool speculate = !outline && shape.speculate && n_trig_exp(ins) > 0;
+    if (speculate) {
+        for (size_t j = 0; j < n_params; ++j)
+            if (dp.param_slot[j] != NO_SLOT)
+                for (int p = 0; p < P; ++p) os << "      const double save" << j << "_" << p << " = s" << dp.param_slot[j] << "_" << p << ";\n";
+        os << "      unsigned slow_t_ = 0u, slow_e_ = 0u;\n";
+        emit_body(true);
+        os << "      if (slow_t_ >= 0x41300000u || slow_e_ >= 0x4085e000u) {\n";
+        for (size_t j = 0; j < n_params; ++j)
+            if (dp.param_slot[j] != NO_SLOT)
+                for (int p = 0; p < P; ++p) os << "      s" << dp.param_slot[j] << "_" << p << " = save" << j << "_" << p << ";\n";
+        emit_body(false);
+        os << "      }\n";
+    } else {
+        emit_body(false);
+    }
+    if (emit_rc != SAF_OK) return emit_rc;
 
     os << "      if (++it >= d.iters) break;\n";
     if (can_iterate) {

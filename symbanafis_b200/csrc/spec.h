@@ -25,6 +25,7 @@ struct SpecShape {
     int min_blocks = 1;        // __launch_bounds__ second argument: caps the registers per thread
     int sync_every = 0;        // > 0: a block barrier every so many statements (long programs, spec.cpp)
     bool outline = false;      // transcendental leaves are called, not inlined
+    bool speculate = true;     // inlined leaves: fast paths first, careful replay of the iteration when one did not apply
 };
 
 // A loaded specialised kernel on one device (launch.cu).

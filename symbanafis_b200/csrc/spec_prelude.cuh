@@ -122,6 +122,42 @@ SAF_LEAF Vec<SPEC_P> sin_v(Vec<SPEC_P> a) { Vec<SPEC_P> r; lm::sin_n<SPEC_P>(a.v
 SAF_LEAF Vec<SPEC_P> cos_v(Vec<SPEC_P> a) { Vec<SPEC_P> r; lm::cos_n<SPEC_P>(a.v, r.v); return r; }
 SAF_LEAF Vec<SPEC_P> exp_v(Vec<SPEC_P> a) { Vec<SPEC_P> r; lm::exp_n<SPEC_P>(a.v, r.v); return r; }
 SAF_LEAF Vec2<SPEC_P> sincos_v(Vec<SPEC_P> a) { Vec2<SPEC_P> r; lm::sincos_n<SPEC_P>(a.v, r.s, r.c); return r; }
+// speculative leaves (spec.cpp `speculate`): the fast path only; `slow` collects the largest |argument| high word seen,
+// which the generated code compares once per iteration with the fast-range limits of leanmath.cuh (trig_slow, exp_slow)
+__device__ __forceinline__ unsigned hi_abs(double x) { return (unsigned)__double2hiint(x) & 0x7fffffffu; }
+__device__ __forceinline__ Vec<SPEC_P> sin_f(Vec<SPEC_P> a, unsigned &slow) {
+    Vec<SPEC_P> r;
+#pragma unroll
+    for (int p = 0; p < SPEC_P; ++p) { r.v[p] = lm::sin_fast(a.v[p]); slow = max(slow, hi_abs(a.v[p])); }
+    return r;
+}
+__device__ __forceinline__ Vec<SPEC_P> cos_f(Vec<SPEC_P> a, unsigned &slow) {
+    Vec<SPEC_P> r;
+#pragma unroll
+    for (int p = 0; p < SPEC_P; ++p) { r.v[p] = lm::cos_fast(a.v[p]); slow = max(slow, hi_abs(a.v[p])); }
+    return r;
+}
+__device__ __forceinline__ Vec<SPEC_P> exp_f(Vec<SPEC_P> a, unsigned &slow) {
+    Vec<SPEC_P> r;
+#pragma unroll
+    for (int p = 0; p < SPEC_P; ++p) { r.v[p] = lm::exp_fast(a.v[p]); slow = max(slow, hi_abs(a.v[p])); }
+    return r;
+}
+__device__ __forceinline__ Vec2<SPEC_P> sincos_f(Vec<SPEC_P> a, unsigned &slow) {
+    Vec2<SPEC_P> r;
+#pragma unroll
+    for (int p = 0; p < SPEC_P; ++p) {
+#ifdef SAF_SINCOS_SEPARATE
+        r.s[p] = lm::sin_fast(a.v[p]);
+        r.c[p] = lm::cos_fast(a.v[p]);
+#else
+        lm::sincos_fast(a.v[p], r.s[p], r.c[p]);
+#endif
+        slow = max(slow, hi_abs(a.v[p]));
+    }
+    return r;
+}
+static_assert(true, "fast-range limits used by the generated code: trig 0x41300000 (2^20), exp 0x4085e000 (700)");
 SAF_LEAF double log_(double a) { return log(a); }
 SAF_LEAF double div_(double a, double b) { return __ddiv_rn(a, b); }
 

@@ -212,10 +212,11 @@ def test_driver_rules_broadcast_missing_short_unaligned_empty():
     w = workloads.get("single_expr")
     hw = _handle(w.program, True)
     assert hw.specialized_info().points_per_thread == 4
-    m = 70_001
+    m = 700_001  # large-batch shape (>= 12 warps per SM at four points per thread)
     x = w.make_inputs(m + 1, 1)[0]
     out = np.empty(m + 1)
     hw.eval_host([x[1:]], [out[1:]], m)
+    assert hw.specialized_info().registers > 0
     ref = np.empty(m)
     _handle(w.program, False).eval_host([x[1:].copy()], [ref], m)
     assert bits_equal(out[1:], ref)
@@ -315,11 +316,44 @@ def test_one_specialised_handle_from_many_host_threads():
     assert not errs, errs[0]
 
 
+def test_speculative_body_replays_carefully_outside_the_fast_range():
+    # arguments beyond 2^20 (trig) and 700 (exp), Inf and NaN, mixed with ordinary ones in the same thread / warp: the
+    # speculative copy of the body records them and the careful copy recomputes the iteration -- same bits as the
+    # interpreter, whose leaves branch to the math library per call
+    rng = np.random.default_rng(12)
+    n = 20_011
+    x = rng.uniform(-3, 3, n)
+    y = rng.uniform(-3, 3, n)
+    idx = rng.choice(n, 400, replace=False)
+    x[idx[:100]] = rng.uniform(1.1e6, 1e12, 100)
+    y[idx[100:200]] = -rng.uniform(1.1e6, 1e15, 100)
+    x[idx[200:250]] = np.inf
+    y[idx[250:300]] = np.nan
+    x[idx[300:400]] = rng.uniform(700, 800, 100)
+    prog = compile_exprs([parse("sin(1.3*x) + 0.7*cos(0.9*y)"), parse("exp(-x) * sin(y) + cos(x)")], ["x", "y"])
+    for variant in ("large", "small"):
+        import os
+        os.environ["SAF_SPEC_VARIANT"] = variant
+        try:
+            a, b = both(prog, [x, y], n)
+        finally:
+            del os.environ["SAF_SPEC_VARIANT"]
+        assert_same_bits(a, b, f"slow paths ({variant})")
+    w = workloads.get("clifford")  # iterated: the replay restores the state of the iteration it repeats
+    st0 = w.make_inputs(n, 3)
+    st0[0][idx[:50]] = 3e7
+    hi, hs = _handle(w.program, False), _handle(w.program, True)
+    si_, ss_ = [c.copy() for c in st0], [c.copy() for c in st0]
+    hi.iterate_host(si_, 5)
+    hs.iterate_host(ss_, 5)
+    assert_same_bits(si_, ss_, "clifford with out-of-range start")
+
+
 def test_specialised_source_is_inspectable():
     w = workloads.get("clifford")
     h = _handle(w.program, True)
     src = h.specialized_source()
     assert "saf_spec" in src and "lm::" not in src.split("spec_prelude.cuh")[0]
-    assert "sp::sin_v" in src and "__fma_rn" in src
+    assert "sp::sin_v" in src and "sp::sin_f" in src and "__fma_rn" in src
     si = h.specialized_info()
     assert si.compile_ms > 0 and si.source_bytes == len(src)

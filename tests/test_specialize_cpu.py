@@ -44,10 +44,13 @@ def test_generated_text_is_the_device_program_statement_by_statement():
     info = h.specialize()
     src = h.specialized_source()
     n_instr = h.info().n_dev_instructions
-    assert len(re.findall(r"// \[\d+\]", src)) == n_instr
+    # the body is written twice: the speculative copy (fast paths only, sp::*_f) and the careful replay (sp::*_v)
+    assert len(re.findall(r"// \[\d+\]", src)) == 2 * n_instr
     P = info.points_per_thread
-    assert src.count("__dmul_rn(") >= P  # the square, once per point
-    assert src.count("sp::sin_v(") == 1 and src.count("sp::exp_v(") == 1 and src.count("__fma_rn(") == P
+    assert src.count("__dmul_rn(") >= 2 * P  # the square, once per point and copy
+    assert src.count("sp::sin_v(") == 1 and src.count("sp::exp_v(") == 1 and src.count("__fma_rn(") == 2 * P
+    assert src.count("sp::sin_f(") == 1 and src.count("sp::exp_f(") == 1
+    assert "if (slow_t_ >= 0x41300000u || slow_e_ >= 0x4085e000u) {" in src
     assert "lm::" not in src and "for (int p" not in src, "statements are written out per point: no arrays, no loops"
     # constants travel as bit patterns
     for k in re.findall(r"const double k\d+ = (\S+);", src):
@@ -75,6 +78,17 @@ def test_iteration_feedback_is_emitted_only_when_results_pair_with_parameters():
 
 
 @needs_nvrtc
+def test_speculation_only_where_leaves_are_inlined_and_exist(monkeypatch):
+    a = _handle(workloads.get("aizawa").program)  # no transcendental at all: one copy of the body
+    a.specialize()
+    assert "slow_t_" not in a.specialized_source()
+    monkeypatch.setenv("SAF_SPEC_SPECULATE", "0")  # tuning knob
+    c = _handle(workloads.get("clifford").program)
+    c.specialize()
+    assert "slow_t_" not in c.specialized_source() and "sp::sin_v(" in c.specialized_source()
+
+
+@needs_nvrtc
 def test_many_transcendentals_are_called_not_inlined():
     few = _handle(workloads.get("clifford").program)
     few.specialize()
@@ -82,7 +96,7 @@ def test_many_transcendentals_are_called_not_inlined():
     terms = " + ".join(f"sin({1 + 0.1 * k}*x)*exp(-{0.2 + 0.01 * k}*x)" for k in range(20))
     many = _handle(compile_exprs([parse(terms)], ["x"]))
     many.specialize()
-    assert "#define SPEC_OUTLINE 1" in many.specialized_source()
+    assert "#define SPEC_OUTLINE 1" in many.specialized_source() and "slow_t_" not in many.specialized_source()
 
 
 def test_programs_above_the_limit_are_refused_and_stay_usable(monkeypatch):
