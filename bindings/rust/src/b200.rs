@@ -12,6 +12,7 @@ extern "C" {
                           pool: *const u32, n_pool: usize, param_count: u32, workspace_size: u32,
                           result_regs: *const u32, n_results: u32, out: *mut *mut SafProgram) -> c_int;
     fn saf_program_destroy(p: *mut SafProgram);
+    fn saf_program_specialize(p: *mut SafProgram) -> c_int;
     fn saf_program_intern(flat: *const u32, n_words: usize, consts: *const f64, n_consts: usize,
                           pool: *const u32, n_pool: usize, param_count: u32, workspace_size: u32,
                           result_regs: *const u32, n_results: u32, out: *mut *mut SafProgram) -> c_int;
@@ -39,6 +40,16 @@ impl B200Program {
         };
         if rc != 0 { return Err(last_error(rc)); }
         Ok(Self(h))
+    }
+
+    /// Compiles the program into a straight-line sm_100a kernel of its own (NVRTC, once; tenths of a second to a few
+    /// seconds): every later evaluation through this handle launches it instead of the interpreter and returns the
+    /// same bits.  An `Err` (no libnvrtc, program above 20 000 device instructions) leaves the handle on the
+    /// interpreter, fully usable.
+    pub fn specialize(&self) -> Result<(), DiffError> {
+        let rc = unsafe { saf_program_specialize(self.0) };
+        if rc != 0 { return Err(last_error(rc)); }
+        Ok(())
     }
 }
 

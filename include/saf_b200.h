@@ -169,6 +169,10 @@ typedef struct saf_specialized_info {
     int small_block_threads;
     int small_registers;     /* -1 until loaded on the current device */
     double small_compile_ms;
+    /* short programs that read few columns carry a second entry point (saf_spec_pf) that single passes (saf_eval_*)
+     * launch: it loads the columns of a block's next tile before it evaluates the current one */
+    int has_prefetch_entry;
+    int prefetch_registers;  /* -1 until loaded / when absent */
 } saf_specialized_info;
 SAF_API int saf_program_specialized_info(const saf_program *prog, saf_specialized_info *info);
 /* The generated CUDA C++ text (for inspection) of the large-batch (small_batch = 0) or the small-batch shape.

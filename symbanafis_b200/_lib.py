@@ -51,6 +51,7 @@ class SpecializedInfo(C.Structure):
         ("generate_ms", C.c_double), ("compile_ms", C.c_double), ("cubin_bytes", C.c_size_t), ("source_bytes", C.c_size_t),
         ("small_compiled", C.c_int), ("small_points_per_thread", C.c_int), ("small_block_threads", C.c_int),
         ("small_registers", C.c_int), ("small_compile_ms", C.c_double),
+        ("has_prefetch_entry", C.c_int), ("prefetch_registers", C.c_int),
     ]
 
 

@@ -71,7 +71,7 @@ struct saf_program {
         std::string err, text;
         std::vector<char> cubin;
         SpecShape shape;
-        bool can_iterate = false;
+        bool can_iterate = false, has_prefetch_entry = false;
         double generate_ms = 0.0, compile_ms = 0.0;
         std::map<int, SpecModule> modules; // by device; entries never move
     } spec[2];
@@ -335,7 +335,7 @@ static int specialize_locked(saf_program *p, int variant = 0) { // p->mu held
     sp.attempted = true;
     const auto t0 = std::chrono::steady_clock::now();
     sp.shape = spec_shape_for(p->dev, variant == 1);
-    sp.rc = spec_generate(p->dev, sp.shape, sp.text, sp.can_iterate, sp.err);
+    sp.rc = spec_generate(p->dev, sp.shape, sp.text, sp.can_iterate, sp.has_prefetch_entry, sp.err);
     const auto t1 = std::chrono::steady_clock::now();
     sp.generate_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     if (sp.rc != SAF_OK) return sp.rc;
@@ -371,6 +371,8 @@ extern "C" int saf_program_specialized_info(const saf_program *p, saf_specialize
     info->local_bytes = -1;
     info->resident_blocks = -1;
     info->small_registers = -1;
+    info->prefetch_registers = -1;
+    info->has_prefetch_entry = sp.has_prefetch_entry;
     const saf_program::Spec &sm = p->spec[1];
     info->small_compiled = sm.attempted && sm.rc == SAF_OK;
     info->small_points_per_thread = sm.shape.points_per_thread;
@@ -383,6 +385,7 @@ extern "C" int saf_program_specialized_info(const saf_program *p, saf_specialize
             info->registers = it->second.registers;
             info->local_bytes = it->second.local_bytes;
             info->resident_blocks = it->second.resident_blocks;
+            info->prefetch_registers = it->second.function_pf ? it->second.registers_pf : -1;
         }
         it = sm.modules.find(dev);
         if (it != sm.modules.end()) info->small_registers = it->second.registers;
@@ -436,7 +439,7 @@ static int spec_for_launch(const saf_program *prog, uint64_t iters, size_t n_poi
     auto it = sp.modules.find(dev);
     if (it == sp.modules.end()) {
         SpecModule m;
-        cudaError_t e = spec_module_load(sp.cubin.data(), &m);
+        cudaError_t e = spec_module_load(sp.cubin.data(), sp.has_prefetch_entry, &m);
         if (e != cudaSuccess) return cuda_fail(e, "loading the specialised kernel");
         if (m.max_threads < sp.shape.block) {
             spec_module_unload(&m);
@@ -524,9 +527,10 @@ static int launch_on_device(const saf_program *prog, const double *const *cols, 
             for (size_t k = 0; k < dp.result_field.size(); ++k) sd.outs[k] = outs[k];
             const unsigned long long tile = (unsigned long long)ss.block * (unsigned long long)ss.points_per_thread;
             const unsigned long long n_tiles = (n_points + tile - 1) / tile;
-            unsigned long long grid = (unsigned long long)sm->sms * (unsigned long long)sm->resident_blocks;
+            const bool pf = sd.iters == 1 && sm->function_pf != nullptr; // single pass: the entry point with next-tile prefetch
+            unsigned long long grid = (unsigned long long)sm->sms * (unsigned long long)(pf ? sm->resident_blocks_pf : sm->resident_blocks);
             if (grid > n_tiles) grid = n_tiles;
-            cudaError_t e = spec_launch(*sm, sd, (int)grid, ss.block, stream);
+            cudaError_t e = spec_launch(*sm, pf, sd, (int)grid, ss.block, stream);
             if (e != cudaSuccess) return cuda_fail(e, "specialised kernel launch");
             g_launches.fetch_add(1, std::memory_order_relaxed);
             return SAF_OK;

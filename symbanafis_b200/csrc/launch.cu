@@ -176,7 +176,7 @@ cudaError_t launch_interpreter(const LaunchDesc &desc, const LaunchShape &shape,
 }
 
 // ---- specialised kernels (spec.h): one module per program and device, loaded from the cubin NVRTC produced ----------
-cudaError_t spec_module_load(const void *cubin, SpecModule *out) {
+cudaError_t spec_module_load(const void *cubin, bool with_prefetch_entry, SpecModule *out) {
     DeviceModule *m = nullptr;
     cudaError_t e = module_for_current_device(&m); // driver entry points + primary context
     if (e != cudaSuccess) return e;
@@ -192,12 +192,21 @@ cudaError_t spec_module_load(const void *cubin, SpecModule *out) {
     if (r == CUDA_SUCCESS) r = g_drv.func_get_attribute(&threads, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, f);
     if (r == CUDA_SUCCESS) r = g_drv.func_get_attribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, f);
     if (r == CUDA_SUCCESS) r = g_drv.func_get_attribute(&local, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f);
+    CUfunction fp = nullptr;
+    int regs_pf = 0;
+    if (r == CUDA_SUCCESS && with_prefetch_entry) {
+        r = g_drv.module_get_function(&fp, mod, "saf_spec_pf");
+        if (r == CUDA_SUCCESS) r = g_drv.func_get_attribute(&regs_pf, CU_FUNC_ATTRIBUTE_NUM_REGS, fp);
+    }
     if (r != CUDA_SUCCESS) {
         g_drv.module_unload(mod);
         return as_cuda(r);
     }
     out->module = mod;
     out->function = f;
+    out->function_pf = fp;
+    out->registers_pf = regs_pf;
+    out->resident_blocks_pf = 0;
     out->registers = regs;
     out->local_bytes = local;
     out->max_threads = threads;
@@ -211,17 +220,22 @@ cudaError_t spec_module_occupancy(SpecModule *m, int block) {
     CUresult r = g_drv.occupancy(&resident, (CUfunction)m->function, block, 0);
     if (r != CUDA_SUCCESS) return as_cuda(r);
     m->resident_blocks = resident < 1 ? 1 : resident;
+    if (m->function_pf) {
+        r = g_drv.occupancy(&resident, (CUfunction)m->function_pf, block, 0);
+        if (r != CUDA_SUCCESS) return as_cuda(r);
+        m->resident_blocks_pf = resident < 1 ? 1 : resident;
+    }
     return cudaSuccess;
 }
 
 void spec_module_unload(SpecModule *m) {
     if (m->module && g_drv.module_unload) g_drv.module_unload((CUmodule)m->module);
-    m->module = m->function = nullptr;
+    m->module = m->function = m->function_pf = nullptr;
 }
 
-cudaError_t spec_launch(const SpecModule &m, const SpecDesc &desc, int grid, int block, cudaStream_t stream) {
+cudaError_t spec_launch(const SpecModule &m, bool prefetch_entry, const SpecDesc &desc, int grid, int block, cudaStream_t stream) {
     void *args[] = {const_cast<SpecDesc *>(&desc)};
-    return as_cuda(g_drv.launch((CUfunction)m.function, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, 0, (CUstream)stream, args, nullptr));
+    return as_cuda(g_drv.launch((CUfunction)(prefetch_entry ? m.function_pf : m.function), (unsigned)grid, 1, 1, (unsigned)block, 1, 1, 0, (CUstream)stream, args, nullptr));
 }
 
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream) {

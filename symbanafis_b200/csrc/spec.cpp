@@ -156,6 +156,7 @@ SpecShape spec_shape_for(const DeviceProgram &dp, bool small_batch) {
     // per module; the pendulum's 32 call sites inline: 2.86 ms against 3.70 ms called)
     s.outline = n_heavy * (size_t)s.points_per_thread > (size_t)env_int("SAF_SPEC_INLINE_MAX", 64);
     s.speculate = env_int("SAF_SPEC_SPECULATE", 1) != 0;
+    s.prefetch = env_int("SAF_SPEC_PREFETCH", 1) != 0;
     return s;
 }
 
@@ -165,7 +166,9 @@ bool spec_batch_is_small(const SpecShape &large, unsigned long long n_points, in
     return n_points < 12ull * 32ull * (unsigned long long)large.points_per_thread * (unsigned long long)(sms > 0 ? sms : 1);
 }
 
-int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &text, bool &can_iterate, std::string &err) {
+int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &text, bool &can_iterate, bool &has_prefetch_entry,
+                  std::string &err) {
+    has_prefetch_entry = false;
     std::vector<Ins> ins;
     if (!decode(dp, ins, err)) return SAF_ERR_INVALID_PROGRAM;
     const size_t max_instr = (size_t)env_int("SAF_SPEC_MAX_INSTRUCTIONS", (int)SPEC_MAX_INSTRUCTIONS); // tuning / test knob
@@ -199,10 +202,44 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
     if (outline) os << "#define SPEC_OUTLINE 1\n";
     os << "#include \"spec_prelude.cuh\"\n";
     os << "using namespace saf;\n";
-    os << "extern \"C\" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MINB) saf_spec(const __grid_constant__ sp::SpecDesc d) {\n";
+    size_t n_used = 0;
+    for (size_t j = 0; j < n_params; ++j) n_used += dp.param_slot[j] != NO_SLOT;
+    // A second entry point with next-tile prefetch for single passes (below) when the program is short and reads few
+    // columns; in-kernel iteration keeps the plain one (the prefetched columns are registers that an iterated map holds
+    // for nothing: Aizawa 68 -> 86 registers, 0.466 -> 0.530 ms).
+    // Only where a single pass has HBM time worth hiding: >= 0.2 bytes of column traffic per FP64 slot (single expression
+    // 0.44, Clifford step 0.46, Aizawa step 1.8; the pendulum's RK4 step, 0.10, is FP64 time only).
+    const double bytes_per_slot = 8.0 * (double)(n_used + n_results) / (dp.fp64_slots > 1.0 ? dp.fp64_slots : 1.0);
+    has_prefetch_entry = shape.prefetch && n_used > 0 && n_used * (size_t)P <= 16 && ins.size() <= 512 && bytes_per_slot >= 0.2;
+    int emit_rc = SAF_OK;
+    auto emit_kernel = [&](const char *kernel_name, bool prefetch) {
+    os << "extern \"C\" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MINB) " << kernel_name
+       << "(const __grid_constant__ sp::SpecDesc d) {\n";
     os << "  constexpr int P = SPEC_P;\n";
     for (size_t k = 0; k < dp.consts.size(); ++k) os << "  const double k" << k << " = " << konst_literal(dp.consts[k]) << ";\n";
     os << "  const unsigned long long TILE = (unsigned long long)SPEC_BLOCK * P, n_tiles = (d.n_points + TILE - 1) / TILE;\n";
+    // Prefetch (short programs with few columns): the columns of a block's NEXT tile are loaded into registers before the
+    // current tile is evaluated, so that the loads are in flight during the arithmetic -- a single pass such as
+    // x^2 + sin(x) exp(-x) has as much FP64 time as HBM time per tile, and without the overlap pays their sum.
+    auto emit_loads = [&](const char *base, const char *full, const char *prefix, const char *indent) {
+        for (size_t j = 0; j < n_params; ++j) {
+            if (dp.param_slot[j] == NO_SLOT) continue;
+            os << indent << "{ double t_[P]; sp::load_col<P, SPEC_BLOCK>(d, " << j << ", " << base << ", " << full << ", t_);";
+            for (int p = 0; p < P; ++p) os << " " << prefix << dp.param_slot[j] << "_" << p << " = t_[" << p << "];";
+            os << " }\n";
+        }
+    };
+    if (prefetch) {
+        for (size_t j = 0; j < n_params; ++j) {
+            if (dp.param_slot[j] == NO_SLOT) continue;
+            os << "  double";
+            for (int p = 0; p < P; ++p) os << (p ? ", " : " ") << "n" << dp.param_slot[j] << "_" << p << " = 0.0";
+            os << ";\n";
+        }
+        os << "  if (blockIdx.x < n_tiles) {\n    const unsigned long long b0_ = blockIdx.x * TILE;\n    const bool f0_ = b0_ + TILE <= d.n_points;\n";
+        emit_loads("b0_", "f0_", "n", "    ");
+        os << "  }\n";
+    }
     os << "  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n";
     os << "    const unsigned long long tile_base = tile * TILE;\n";
     os << "    const bool full = tile_base + TILE <= d.n_points;\n";
@@ -213,11 +250,19 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
         for (int p = 0; p < P; ++p) os << (p ? ", " : " ") << "s" << s << "_" << p << " = 0.0";
         os << ";\n";
     }
-    for (size_t j = 0; j < n_params; ++j) {
-        if (dp.param_slot[j] == NO_SLOT) continue;
-        os << "    { double t_[P]; sp::load_col<P, SPEC_BLOCK>(d, " << j << ", tile_base, full, t_);";
-        for (int p = 0; p < P; ++p) os << " s" << dp.param_slot[j] << "_" << p << " = t_[" << p << "];";
-        os << " }\n";
+    if (prefetch) {
+        for (size_t j = 0; j < n_params; ++j) {
+            if (dp.param_slot[j] == NO_SLOT) continue;
+            os << "   ";
+            for (int p = 0; p < P; ++p) os << " s" << dp.param_slot[j] << "_" << p << " = n" << dp.param_slot[j] << "_" << p << ";";
+            os << "\n";
+        }
+        os << "    if (tile + gridDim.x < n_tiles) {\n      const unsigned long long b1_ = (tile + gridDim.x) * TILE;\n"
+              "      const bool f1_ = b1_ + TILE <= d.n_points;\n";
+        emit_loads("b1_", "f1_", "n", "      ");
+        os << "    }\n";
+    } else {
+        emit_loads("tile_base", "full", "s", "    ");
     }
     os << "    for (unsigned long long it = 0;;) {\n";
 
@@ -244,7 +289,6 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
     // that each warp walks once per tile; left alone the warps drift apart, every warp streams its own copy from L2 and
     // the kernel waits for instructions (ncu: stall_no_instruction 4.3 per issue, profiles/r02_g_*).
     const int sync_every = shape.sync_every;
-    int emit_rc = SAF_OK;
     // fast: the speculative copy of the body -- transcendental leaves take their fast path unconditionally and only
     // record whether an argument was outside it (slow_t_ / slow_e_); see `speculate` below
     auto emit_body = [&](bool fast) {
@@ -367,7 +411,7 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
     } else {
         emit_body(false);
     }
-    if (emit_rc != SAF_OK) return emit_rc;
+    if (emit_rc != SAF_OK) return;
 
     os << "      if (++it >= d.iters) break;\n";
     if (can_iterate) {
@@ -385,6 +429,10 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
         os << " sp::store_out<P, SPEC_BLOCK>(d, " << k << ", tile_base, full, r_); }\n";
     }
     os << "  }\n}\n";
+    };
+    emit_kernel("saf_spec", false);
+    if (emit_rc == SAF_OK && has_prefetch_entry) emit_kernel("saf_spec_pf", true);
+    if (emit_rc != SAF_OK) return emit_rc;
     text = os.str();
     return SAF_OK;
 }

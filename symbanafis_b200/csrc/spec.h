@@ -25,6 +25,7 @@ struct SpecShape {
     int min_blocks = 1;        // __launch_bounds__ second argument: caps the registers per thread
     int sync_every = 0;        // > 0: a block barrier every so many statements (long programs, spec.cpp)
     bool outline = false;      // transcendental leaves are called, not inlined
+    bool prefetch = true;      // short programs: the next tile's columns are loaded before the current tile is evaluated
     bool speculate = true;     // inlined leaves: fast paths first, careful replay of the iteration when one did not apply
 };
 
@@ -32,8 +33,9 @@ struct SpecShape {
 struct SpecModule {
     void *module = nullptr;   // CUmodule
     void *function = nullptr; // CUfunction `saf_spec`
-    int registers = 0, local_bytes = 0, max_threads = 0;
-    int sms = 0, resident_blocks = 0;
+    void *function_pf = nullptr; // CUfunction `saf_spec_pf` (single passes with next-tile prefetch) or null
+    int registers = 0, local_bytes = 0, max_threads = 0, registers_pf = 0;
+    int sms = 0, resident_blocks = 0, resident_blocks_pf = 0;
 };
 
 // Largest device program (instructions) that is specialised: beyond it compile time is better spent interpreting.
@@ -49,7 +51,10 @@ bool spec_batch_is_small(const SpecShape &large, unsigned long long n_points, in
 
 // Writes the CUDA C++ text of the kernel `saf_spec` for `dp`.  can_iterate: the text contains the in-kernel feedback
 // of results into parameters (needs as many results as parameters).  Returns 0 or SAF_ERR_UNSUPPORTED.
-int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &text, bool &can_iterate, std::string &err);
+// has_prefetch_entry: the text holds a second kernel, `saf_spec_pf`, for single passes (iters == 1): it loads the columns
+// of a block's next tile before it evaluates the current one.
+int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &text, bool &can_iterate, bool &has_prefetch_entry,
+                  std::string &err);
 
 // NVRTC (jit.cpp).  Compiles `text` (which includes spec_prelude.cuh and through it the device math headers; all of
 // them are embedded in this library) for sm_100a.  Returns 0, SAF_ERR_UNSUPPORTED when libnvrtc cannot be loaded, or
@@ -63,10 +68,10 @@ bool jit_available(std::string &why_not);
 } // namespace saf
 #include <cuda_runtime.h>
 namespace saf {
-cudaError_t spec_module_load(const void *cubin, SpecModule *out);   // current device
-cudaError_t spec_module_occupancy(SpecModule *m, int block);        // fills resident_blocks
+cudaError_t spec_module_load(const void *cubin, bool with_prefetch_entry, SpecModule *out); // current device
+cudaError_t spec_module_occupancy(SpecModule *m, int block);                                // fills resident_blocks*
 void spec_module_unload(SpecModule *m);
-cudaError_t spec_launch(const SpecModule &m, const SpecDesc &desc, int grid, int block, cudaStream_t stream);
+cudaError_t spec_launch(const SpecModule &m, bool prefetch_entry, const SpecDesc &desc, int grid, int block, cudaStream_t stream);
 #endif
 
 } // namespace saf

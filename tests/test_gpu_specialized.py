@@ -276,6 +276,26 @@ def test_device_resident_in_place_iteration_same_bits():
     assert_same_bits(res[0], res[1], "device-resident clifford x25")
 
 
+def test_single_passes_launch_the_prefetch_entry_also_in_place():
+    torch = pytest.importorskip("torch")
+    w = workloads.get("clifford")
+    n = 1_000_003  # several tiles per block: every block prefetches its next tile while it evaluates the current one
+    cols = w.make_inputs(n, 4)
+    h = _handle(w.program, True)
+    s = torch.cuda.current_stream().cuda_stream
+    xs = [torch.from_numpy(c.copy()).cuda() for c in cols]
+    outs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in cols]
+    h.eval_device([t.data_ptr() for t in xs], [n, n], [o.data_ptr() for o in outs], n, stream=s)
+    si = h.specialized_info()
+    assert si.has_prefetch_entry == 1 and si.prefetch_registers > 0
+    # in place: outputs alias the columns (what one step of saf_iterate_device does); tiles never overlap
+    h.eval_device([t.data_ptr() for t in xs], [n, n], [t.data_ptr() for t in xs], n, stream=s)
+    torch.cuda.synchronize()
+    ref = _eval(_handle(w.program, False), w.program, cols, n)
+    assert_same_bits(ref, [o.cpu().numpy() for o in outs], "clifford single pass, prefetch entry")
+    assert_same_bits(ref, [t.cpu().numpy() for t in xs], "clifford single pass in place, prefetch entry")
+
+
 def test_program_too_long_to_specialise_keeps_running_on_the_interpreter(monkeypatch):
     monkeypatch.setenv("SAF_SPEC_MAX_INSTRUCTIONS", "10")  # the shipped limit is 20000 device instructions
     w = workloads.get("aizawa")

@@ -42,7 +42,11 @@ def test_generated_text_is_the_device_program_statement_by_statement():
     w = workloads.get("single_expr")
     h = _handle(w.program)
     info = h.specialize()
-    src = h.specialized_source()
+    full_src = h.specialized_source()
+    # two entry points: saf_spec, and saf_spec_pf (single passes: next-tile prefetch) with the same statements
+    assert info.has_prefetch_entry == 1 and full_src.count("__global__") == 2
+    src = full_src[:full_src.index("saf_spec_pf")]
+    assert "n0_0" in full_src[full_src.index("saf_spec_pf"):] and "n0_0" not in src
     n_instr = h.info().n_dev_instructions
     # the body is written twice: the speculative copy (fast paths only, sp::*_f) and the careful replay (sp::*_v)
     assert len(re.findall(r"// \[\d+\]", src)) == 2 * n_instr
@@ -56,6 +60,8 @@ def test_generated_text_is_the_device_program_statement_by_statement():
     for k in re.findall(r"const double k\d+ = (\S+);", src):
         assert k.startswith("__longlong_as_double(0x")
     assert f"#define SPEC_P {P}" in src and "#include \"spec_prelude.cuh\"" in src
+    pend = _handle(workloads.get("double_pendulum").program)  # FP64 time only: no prefetch entry
+    assert pend.specialize().has_prefetch_entry == 0
 
 
 @needs_nvrtc

@@ -8,7 +8,11 @@ import csv, json, os, shutil, sys
 tag, prefix = sys.argv[1], sys.argv[2]
 src, dst = os.path.join("gpurun_out", tag), "profiles"
 traffic = {}
-tpath = os.path.join(dst, "r02_dram_traffic.json")
+# captures of the interpreter (tools/gpu_prof.sh with MACHINE=interpreter) carry the suffix _interp in their names
+tpath_spec = os.path.join(dst, "r02_dram_traffic_specialized.json")
+tpath_interp = os.path.join(dst, "r02_dram_traffic.json")
+traffic_spec = json.load(open(tpath_spec)) if os.path.exists(tpath_spec) else {}
+tpath = tpath_interp
 if os.path.exists(tpath):
     traffic = json.load(open(tpath))
 for f in sorted(os.listdir(src)):
@@ -25,17 +29,21 @@ for f in sorted(os.listdir(src)):
             line = (f"Plain run of the same command (exit 0, before the capture): {d['ms_per_step']:.4f} ms/step, "
                     f"{d['value']:.3e} point-evals/s, roofline {d['roofline']['bound']} {d['roofline']['frac']:.3f}.\n\n")
     with open(os.path.join(dst, f"{prefix}_{name}.md"), "w") as o:
-        o.write(f"# Round 2, shipped build: {name} -- ncu --set full --clock-control none --import-source on, one launch "
+        o.write(f"# Round 2, shipped build: {name} ({'interpreter kernel' if name.endswith('_interp') or '_interp_' in name else 'specialised kernel saf_spec'}) -- ncu --set full --clock-control none --import-source on, one launch "
                 f"(tools/gpu_prof.sh, gpurun tag {tag})\n\n{line}```\n{text}```\n")
     for l in text.splitlines():
         if l.startswith("DRAM_TRAFFIC_JSON "):
             t = json.loads(l[len("DRAM_TRAFFIC_JSON "):])
             key = name if "_" not in name or not name.split("_")[-1].isdigit() else None
+            tgt = traffic if key and key.endswith("_interp") else traffic_spec
+            if key and key.endswith("_interp"):
+                key = key[:-len("_interp")]
             if key:
-                traffic[key] = dict(t, source=f"profiles/{prefix}_{name}.md (gpurun tag {tag})",
+                tgt[key] = dict(t, source=f"profiles/{prefix}_{name}.md (gpurun tag {tag})",
                                     note="one ncu --set full capture, per launch; output columns of a small launch are still in the "
                                          "126 MB L2 when the kernel ends, so their DRAM writes show up after it")
 json.dump(traffic, open(tpath, "w"), indent=1)
+json.dump(traffic_spec, open(tpath_spec, "w"), indent=1)
 bl = os.path.join(src, "bench_full.log")
 if os.path.exists(bl):
     js = [l for l in open(bl) if l.startswith("{")]
@@ -45,12 +53,13 @@ if os.path.exists(bl):
                 f"```json\n{js[-1] if js else 'no JSON line'}```\n## python bench.py --impl reference --steps 3 --warmup 1\n```json\n{ref[-1] if ref else 'no JSON line'}```\n")
         if js:
             d = json.loads(js[-1])
-            o.write("\n| workload | ms/step | point-evals/s | roofline | e2e pinned | e2e pageable | CPU f64x4 arm |\n|---|---|---|---|---|---|---|\n")
+            o.write("\n| workload | machine | ms/step | point-evals/s | roofline | interpreter ms/step | e2e pinned | e2e pageable | CPU f64x4 arm |\n|---|---|---|---|---|---|---|---|---|\n")
             rows = [("clifford (headline)", d)] + list(d.get("workloads", {}).items())
             for k, v in rows:
                 cb = v.get("cpu_baseline") or {}
-                o.write(f"| {k} | {v['ms_per_step']:.4f} | {v['value']:.3e} | {v['roofline']['bound']} {v['roofline']['frac']:.3f} | "
-                        f"{v['e2e']['value']:.3e} | {v['e2e_pageable']['value']:.3e} | {cb.get('value', 0):.3e} x{cb.get('cores', '?')} |\n")
+                mi, it = v.get("machine") or {}, v.get("interpreter") or {}
+                o.write(f"| {k} | {mi.get('name', 'interpreter')} P={mi.get('points_per_thread', '-')} x{mi.get('block_threads', '-')} | {v['ms_per_step']:.4f} | {v['value']:.3e} | {v['roofline']['bound']} {v['roofline']['frac']:.3f} | "
+                        f"{it.get('ms_per_step', float('nan')):.4f} | {v['e2e']['value']:.3e} | {v['e2e_pageable']['value']:.3e} | {cb.get('value', 0):.3e} x{cb.get('cores', '?')} |\n")
 lc = os.path.join(src, "launches.csv")
 if os.path.exists(lc):
     shutil.copy(lc, os.path.join(dst, f"{prefix}_launches_clifford.csv"))
@@ -64,7 +73,7 @@ if os.path.exists(lc):
         o.write("| kernel | launches | total ms | mean ms |\n|---|---|---|---|\n")
         for k, (n, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             o.write(f"| {k} | {n} | {ns / 1e6:.3f} | {ns / 1e6 / n:.3f} |\n")
-        o.write("\nThe interpreter (`saf_interp_p4_ksm`) is the only kernel of the library inside a timed step (one launch per step = 1000 map "
+        o.write("\nThe library's kernel (`saf_spec`, the specialised Clifford program; `saf_interp_p4_ksm` in the interpreter comparison) is the only kernel of the library inside a timed step (one launch per step = 1000 map "
                 "iterations over 1 M particles); the rest are torch's L2-flush fill and state copies, the FP64-peak probe, the ideal-kernel probe and "
                 "the host-path launches of the e2e legs, all outside the CUDA events of the device-timed steps.\n")
 print("collected", tag, "->", prefix)

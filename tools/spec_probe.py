@@ -80,5 +80,5 @@ for name in names:
                       "spec_min_ms": round(t_s[0], 4), "speedup": round(t_i[1] / t_s[1], 2), "bits_equal": bool(same), "nan_pattern_equal": bool(nan_same),
                       "interp_frac_fp64": round(flops / (t_i[1] * 1e-3) / peak, 3), "spec_frac_fp64": round(flops / (t_s[1] * 1e-3) / peak, 3),
                       "hbm_GBs_spec": round(info.bytes_per_point * n / (t_s[1] * 1e-3) / 1e9, 1),
-                      "P": si.points_per_thread, "block": si.block_threads, "regs": si.registers, "small": [si.small_compiled, si.small_points_per_thread, si.small_registers], "local": si.local_bytes, "resident": si.resident_blocks,
+                      "P": si.points_per_thread, "block": si.block_threads, "regs": si.registers, "pf_regs": si.prefetch_registers, "small": [si.small_compiled, si.small_points_per_thread, si.small_registers], "local": si.local_bytes, "resident": si.resident_blocks,
                       "compile_ms": round(si.compile_ms, 1), "env": {k: v for k, v in os.environ.items() if k.startswith("SAF_SPEC")}}), flush=True)
