@@ -251,6 +251,11 @@ class Bench:
             # a barrier that keeps the waiting ranks' GPUs idle (an NCCL barrier spins in a kernel): used while rank 0
             # alone drives all devices through saf_eval_host_multi
             self.cpu_group = dist.new_group(backend="gloo")
+        self.machine_note = None
+        if args.machine == "specialized" and not _lib.specialize_available():
+            # no usable libnvrtc on this box: the interpreter runs everything (it always can); say so in the line
+            self.machine_note = "specialised kernels unavailable (" + _lib.lib().saf_last_error().decode() + "): interpreter"
+            args.machine = "interpreter"
         self.flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=self.dev)  # 256 MiB > 126 MB L2
         self.stream = torch.cuda.current_stream(self.dev)
         self.fp64_peak = _lib.measure_fp64_peak()  # DFMA lane-instr/s, measured live on this GPU
@@ -275,7 +280,10 @@ class Bench:
 
     def machine_info(self, h):
         if self.args.machine != "specialized":
-            return {"name": "interpreter", "kernel": "saf_interp_* (bytecode interpreter, shared-memory register file)"}
+            out = {"name": "interpreter", "kernel": "saf_interp_* (bytecode interpreter, shared-memory register file)"}
+            if self.machine_note:
+                out["note"] = self.machine_note
+            return out
         si = h.specialized_info()
         small = si.small_registers > 0 and si.registers <= 0
         return {"name": "specialized", "kernel": "saf_spec (the program as straight-line sm_100a code, NVRTC)",
@@ -575,7 +583,7 @@ class Bench:
             return None
         bytes_total = 8 * total * (len(glob) + n_out)
         t_k, t_c = kernel_ms * 1e-3, copy_ms * 1e-3
-        limiter = ("kernel (FP64 interpreter)" if t_k >= t_c else
+        limiter = (f"kernel (FP64-bound, {self.args.machine} machine)" if t_k >= t_c else
                    "host<->device copies (PCIe / host DRAM shared by all ranks), not a collective: there is none")
         roof = self.roofline(info, w, n, 1, kernel_ms, False)
         return {
@@ -589,6 +597,7 @@ class Bench:
                              "value": total / (pageable_ms * 1e-3), "unit": UNIT,
                              "bits_equal_pinned_run": bool(same)},
             "host_multi": multi,
+            "machine": self.machine_info(h),
             "copies_only": {"ms": copy_ms, "gbs_aggregate": bytes_total / t_c / 1e9,
                             "note": "the same H2D + D2H bytes with pinned buffers and no kernel, all ranks at once"},
             "h2d_bytes": 8 * total * len(glob), "d2h_bytes": 8 * total * n_out,

@@ -138,11 +138,13 @@ SpecShape spec_shape_for(const DeviceProgram &dp, bool small_batch) {
         }
     }
     if (small_batch) {
-        // few points: every point its own thread, narrow blocks so that they spread over all SMs, no register cap
-        // (double pendulum, 50 k points: P = 1 2.86 ms, P = 2 4.3 ms, P = 4 6.4 ms)
+        // few points: every point its own thread and a loose register cap (168): the warps that exist are all that
+        // hides latency, every one of them should be resident in the first round (double pendulum, 50 k points:
+        // P = 1 2.86 ms, P = 2 4.3 ms, P = 4 6.4 ms before speculation; after it 2.39 ms uncapped at 170 registers =
+        // two rounds of two blocks per SM, 2.19 ms at <= 168 = three blocks per SM)
         s.points_per_thread = 1;
         s.block = 128;
-        s.min_blocks = 1;
+        s.min_blocks = 3;
         if (long_program) s.sync_every = 400;
     }
     const int p = env_int("SAF_SPEC_P", 0);

@@ -8,7 +8,7 @@
 TAG=$1; shift
 O=gpurun_out/$TAG; mkdir -p $O
 MACHINE=${MACHINE:-specialized}
-KERNEL=saf_spec; [ "$MACHINE" = "interpreter" ] && KERNEL='regex:saf_r?interp'
+KERNEL='regex:saf_spec'; [ "$MACHINE" = "interpreter" ] && KERNEL='regex:saf_r?interp'
 SUF=""; [ "$MACHINE" = "interpreter" ] && SUF="_interp"
 for spec in "$@"; do
   w=${spec%%:*}; pts=0; [ "$spec" != "$w" ] && pts=${spec##*:}

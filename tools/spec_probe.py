@@ -13,7 +13,7 @@ from symbanafis_b200 import _lib, workloads  # noqa: E402
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 names = [a for a in sys.argv[1:] if not a.startswith("-")] or ["single_expr", "clifford", "aizawa", "double_pendulum", "terrain_gradient"]
-SIZES = {"single_expr": (int(os.environ.get("SINGLE_N", 1_000_000)), 1), "clifford": (1_000_000, 1000), "aizawa": (500_000, 600), "double_pendulum": (50_000, 600),
+SIZES = {"single_expr": (int(os.environ.get("SINGLE_N", 1_000_000)), 1), "clifford": (1_000_000, 1000), "aizawa": (500_000, 600), "double_pendulum": (int(os.environ.get("PEND_N", 50_000)), 600),
          "terrain_gradient": (int(os.environ.get("TERRAIN_N", 20_000_000)), 1)}
 peak = _lib.measure_fp64_peak()
 
