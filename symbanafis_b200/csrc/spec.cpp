@@ -213,6 +213,10 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
     // 0.44, Clifford step 0.46, Aizawa step 1.8; the pendulum's RK4 step, 0.10, is FP64 time only).
     const double bytes_per_slot = 8.0 * (double)(n_used + n_results) / (dp.fp64_slots > 1.0 ? dp.fp64_slots : 1.0);
     has_prefetch_entry = shape.prefetch && n_used > 0 && n_used * (size_t)P <= 16 && ins.size() <= 512 && bytes_per_slot >= 0.2;
+    // Constants are immediates everywhere.  (Tried for long programs: a __constant__ table read through `const double
+    // k17 = saf_kt[17]` -- two UMOVs per constant saved, but the compiler hoists the loads: 84 -> 128 registers, terrain
+    // gradient 16.6 -> 18.8 ms.  Dropped.)
+    const bool pair_leaves = env_int("SAF_SPEC_PAIR", 1) != 0;
     int emit_rc = SAF_OK;
     auto emit_kernel = [&](const char *kernel_name, bool prefetch) {
     os << "extern \"C\" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MINB) " << kernel_name
@@ -348,6 +352,35 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
         case D_EXPNEG: arg_vec("-$v"); leaf("exp_v"); break;
         case D_RECIPEXPM1: arg_vec(""); scalar("sp::recip_expm1_($v)"); break;
         case D_SINCOS:
+            // Called leaves: two adjacent, independent SinCos -- sincos(f x + p), sincos(g y + q) of one term -- share ONE
+            // call over 2 P values: half the call / return / constant-load overhead, twice the chains inside the leaf.
+            if (outline && !fast && pair_leaves && n + 1 < ins.size() && ins[n + 1].op == D_SINCOS && field_kind(ins[n + 1].fa) == KIND_S &&
+                !(field_kind(i.fd) == KIND_S && field_index(i.fd) == field_index(ins[n + 1].fa)) &&
+                !(field_kind(i.fc) == KIND_S && field_index(i.fc) == field_index(ins[n + 1].fa))) {
+                const Ins &j = ins[n + 1];
+                auto arg_of = [&](const Ins &q, int p) {
+                    if (q.prefix == PREFIX_MUL) return "__dmul_rn(" + val(q.fa, p) + ", " + konst(field_index(q.fb)) + ")";
+                    if (q.prefix == PREFIX_FMA)
+                        return "__fma_rn(" + val(q.fa, p) + ", " + konst(field_index(q.fb)) + ", " + konst(field_index(q.fb) + 1) + ")";
+                    return val(q.fa, p);
+                };
+                os << "      sp::Vec<2 * P> a_;\n";
+                for (int p = 0; p < P; ++p) os << "      a_.v[" << p << "] = " << arg_of(i, p) << ";\n";
+                for (int p = 0; p < P; ++p) os << "      a_.v[" << P + p << "] = " << arg_of(j, p) << ";\n";
+                os << "      const sp::Vec2<2 * P> r_ = sp::sincos_v2(a_);\n";
+                for (int half = 0; half < 2; ++half) {
+                    const Ins &q = half ? j : i;
+                    for (int p = 0; p < P; ++p) {
+                        os << "      acc_" << p << " = r_.s[" << half * P + p << "];";
+                        if (field_kind(q.fc) == KIND_S) os << " " << val(q.fc, p) << " = r_.c[" << half * P + p << "];";
+                        if (field_kind(q.fd) == KIND_S) os << " " << val(q.fd, p) << " = acc_" << p << ";";
+                        os << "\n";
+                    }
+                }
+                os << "      } // [" << n + 1 << "] rode along\n";
+                ++n;
+                continue;
+            }
             arg_vec("");
             os << "      const sp::Vec2<P> r_ = sp::" << (fast ? "sincos_f(a_, slow_t_)" : "sincos_v(a_)") << ";\n";
             for (int p = 0; p < P; ++p) {

@@ -158,6 +158,9 @@ __device__ __forceinline__ Vec2<SPEC_P> sincos_f(Vec<SPEC_P> a, unsigned &slow) 
     return r;
 }
 static_assert(true, "fast-range limits used by the generated code: trig 0x41300000 (2^20), exp 0x4085e000 (700)");
+#ifdef SPEC_OUTLINE
+SAF_LEAF Vec2<2 * SPEC_P> sincos_v2(Vec<2 * SPEC_P> a) { Vec2<2 * SPEC_P> r; lm::sincos_n<2 * SPEC_P>(a.v, r.s, r.c); return r; }
+#endif
 SAF_LEAF double log_(double a) { return log(a); }
 SAF_LEAF double div_(double a, double b) { return __ddiv_rn(a, b); }
 
