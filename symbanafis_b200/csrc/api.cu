@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +23,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include "../../include/saf_b200.h"
 #include "kernel.cuh"
@@ -854,31 +858,99 @@ bool is_pageable(const void *p) {
 }
 
 struct CopyJob { void *dst; const void *src; size_t bytes; };
+// Persistent copy workers: a chunk is staged by two parallel_copy calls (in, out), a 100 M-point batch by a hundred;
+// spawning and joining five threads per call cost 0.1-0.3 ms each time -- as much as the copy of a 16 MB chunk itself.
+class CopyPool {
+  public:
+    void run(std::vector<std::function<void()>> &tasks) { // runs all tasks, the last one on the calling thread
+        if (tasks.empty()) return;
+        struct Done {
+            std::mutex mu;
+            std::condition_variable cv;
+            size_t left;
+        } done;
+        done.left = tasks.size() - 1;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (pid_ != getpid()) { // forked child: the parent's workers do not exist here
+                pid_ = getpid();
+                n_workers_ = 0;
+                queue_.clear();
+            }
+            while (n_workers_ + 1 < tasks.size() && n_workers_ < kMaxWorkers) {
+                std::thread([this]() { work(); }).detach();
+                ++n_workers_;
+            }
+            for (size_t i = 0; i + 1 < tasks.size(); ++i) {
+                std::function<void()> *t = &tasks[i];
+                queue_.push_back([t, &done]() {
+                    (*t)();
+                    std::lock_guard<std::mutex> lk(done.mu);
+                    if (--done.left == 0) done.cv.notify_one();
+                });
+            }
+        }
+        cv_.notify_all();
+        tasks.back()();
+        std::unique_lock<std::mutex> lk(done.mu);
+        done.cv.wait(lk, [&]() { return done.left == 0; });
+    }
+
+  private:
+    static constexpr size_t kMaxWorkers = 16;
+    void work() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&]() { return !queue_.empty(); });
+                f = std::move(queue_.front());
+                queue_.pop_front();
+            }
+            f();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> queue_;
+    size_t n_workers_ = 0;
+    pid_t pid_ = getpid();
+};
+// never destroyed: its detached workers wait on its condition variable until the process ends
+CopyPool &g_copy_pool = *new CopyPool();
+
 // host-to-host copies of one chunk, spread over a few threads when they are large (one thread moves ~10 GB/s, the
 // PCIe link 50)
 void parallel_copy(const std::vector<CopyJob> &jobs) {
     size_t total = 0;
     for (const auto &j : jobs) total += j.bytes;
     static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned n_threads = total < ((size_t)4 << 20) ? 1u : std::min(6u, std::max(1u, hw / 2));
+    static const unsigned cap = []() {
+        const char *v = getenv("SAF_COPY_THREADS"); // tuning knob
+        // eight copy threads keep a 100 M-point pageable batch behind its kernel on a 16-thread host (terrain gradient:
+        // 115 ms with six, 82.6 ms with eight against an 80.3 ms pinned run); six when several ranks share the host
+        // (torchrun exports LOCAL_WORLD_SIZE), the configuration measured on the 8-GPU box
+        const char *lw = getenv("LOCAL_WORLD_SIZE");
+        const int n = v ? atoi(v) : (lw && atoi(lw) > 1 ? 6 : 8);
+        return (unsigned)(n < 1 ? 1 : n > 16 ? 16 : n);
+    }();
+    const unsigned n_threads = total < ((size_t)2 << 20) ? 1u : std::min(cap, std::max(1u, hw / 2));
     if (n_threads <= 1) {
         for (const auto &j : jobs) std::memcpy(j.dst, j.src, j.bytes);
         return;
     }
     // cut every job into n_threads slices (64-byte aligned cuts)
-    std::vector<std::thread> th;
+    std::vector<std::function<void()>> tasks;
     for (unsigned t = 1; t <= n_threads; ++t) {
-        auto work = [&jobs, t, n_threads]() {
+        tasks.emplace_back([&jobs, t, n_threads]() {
             for (const auto &j : jobs) {
                 const size_t per = ((j.bytes + n_threads - 1) / n_threads + 63) & ~(size_t)63;
                 const size_t b = std::min(j.bytes, per * (t - 1)), e = std::min(j.bytes, per * t);
                 if (e > b) std::memcpy((char *)j.dst + b, (const char *)j.src + b, e - b);
             }
-        };
-        if (t < n_threads) th.emplace_back(work);
-        else work();
+        });
     }
-    for (auto &x : th) x.join();
+    g_copy_pool.run(tasks);
 }
 
 } // namespace
