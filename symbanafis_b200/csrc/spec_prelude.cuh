@@ -36,6 +36,12 @@ struct SpecDesc {
 #define SAF_P _Pragma("unroll") for (int p = 0; p < SPEC_P; ++p)
 
 // Plain (coherent) loads: saf_iterate_device and in-place evaluation pass the same buffers as columns and outputs.
+#ifdef SAF_HOST_SHIM // tests/spec_host: the generated text compiled by g++ for the CPU test-suite (never in the product)
+inline double ld1(const double *p) { return *p; }
+inline void ld2(const double *p, double &a, double &b) { a = p[0]; b = p[1]; }
+inline void st1(double *p, double v) { *p = v; }
+inline void st2(double *p, double a, double b) { p[0] = a; p[1] = b; }
+#else
 __device__ __forceinline__ double ld1(const double *p) {
     double r;
     asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
@@ -48,6 +54,7 @@ __device__ __forceinline__ void st1(double *p, double v) { asm volatile("st.glob
 __device__ __forceinline__ void st2(double *p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
+#endif
 
 template <int P, int BLOCK>
 __device__ __forceinline__ unsigned long long point_index(unsigned long long tile_base, int p) {

@@ -377,3 +377,26 @@ def test_specialised_source_is_inspectable():
     assert "sp::sin_v" in src and "sp::sin_f" in src and "__fma_rn" in src
     si = h.specialized_info()
     assert si.compile_ms > 0 and si.source_bytes == len(src)
+
+
+def test_gpu_execution_equals_cpu_execution_of_the_same_generated_text():
+    # tests/spec_host compiles the generated text with g++ (CUDA vocabulary shimmed onto IEEE operations and libm's fma):
+    # inside the fast range of the lean sin / cos / exp kernels every statement is an exactly rounded operation, so the
+    # B200 and the CPU must produce the same bits from the same text
+    from spec_host import host_kernel
+    for name, iters in (("clifford", 3), ("aizawa", 5), ("single_expr", 1)):
+        w = workloads.get(name)
+        n = 4099
+        cols = w.make_inputs(n, 8)
+        h = _handle(w.program, True)
+        k = host_kernel(h.specialized_source())
+        n_out = len(w.program.result_regs)
+        if iters == 1:
+            gpu = _eval(h, w.program, cols, n)
+            cpu = k.run(cols, n, n_out, grid=2)
+        else:
+            gpu = [c.copy() for c in cols]
+            h.iterate_host(gpu, iters)
+            cpu = [c.copy() for c in cols]
+            k.run(cpu, n, n_out, iters=iters, grid=2, outs=cpu)
+        assert_same_bits(gpu, cpu, f"{name}: GPU vs CPU execution of the generated kernel")

@@ -115,3 +115,116 @@ def test_programs_above_the_limit_are_refused_and_stay_usable(monkeypatch):
     assert ei.value.code == 6 and "interpreted" in ei.value.message
     assert h.specialized_info().compiled == 0
     assert h.info().n_dev_instructions > 10  # the handle is intact
+
+
+# ---- the generated text, EXECUTED on the CPU (tests/spec_host: g++ + a CUDA-vocabulary shim; test infrastructure) ----------
+from oracle import OracleProgram  # noqa: E402
+from spec_host import host_kernel  # noqa: E402
+from util import assert_close, bits_equal, random_program  # noqa: E402
+
+
+def _host(prog, monkeypatch=None, **env):
+    if monkeypatch is not None:
+        for k, v in env.items():
+            monkeypatch.setenv(k, str(v))
+    h = _handle(prog)
+    h.specialize()
+    return host_kernel(h.specialized_source())
+
+
+@needs_nvrtc
+@pytest.mark.parametrize("entry", [0, 1])
+@pytest.mark.parametrize("n", [1, 511, 512, 1537, 5000])
+def test_generated_aizawa_kernel_is_bit_exact_against_the_oracle_on_the_cpu(n, entry):
+    # arithmetic only: every statement is an IEEE operation -> the same bits as the reference interpreter restated
+    w = workloads.get("aizawa")
+    k = _host(w.program)
+    assert k.points_per_thread == 4 and k.has_prefetch_entry
+    cols = w.make_inputs(n, 9)
+    ref = OracleProgram.from_program(w.program).eval_batch(cols, n)
+    got = k.run(cols, n, 3, grid=3, entry=entry)  # three blocks: several tiles per block, a ragged last tile
+    for g, r in zip(got, ref):
+        assert bits_equal(g, r)
+
+
+@needs_nvrtc
+def test_generated_kernel_iterates_in_place_like_the_oracle():
+    w = workloads.get("aizawa")
+    k = _host(w.program)
+    n = 3000
+    cols = w.make_inputs(n, 2)
+    ref = OracleProgram.from_program(w.program).iterate(cols, 7)
+    st = [c.copy() for c in cols]
+    k.run(st, n, 3, iters=7, grid=2, outs=st)  # outputs alias the columns: saf_iterate_device's call
+    for g, r in zip(st, ref):
+        assert bits_equal(g, r)
+
+
+@needs_nvrtc
+@pytest.mark.parametrize("name,p", [("single_expr", 4), ("clifford", 2), ("double_pendulum", 2), ("double_pendulum", 1)])
+def test_generated_kernels_with_transcendentals_match_the_oracle(name, p, monkeypatch):
+    w = workloads.get(name)
+    k = _host(w.program, monkeypatch, SAF_SPEC_P=p)
+    assert k.points_per_thread == p
+    n = 2049
+    cols = w.make_inputs(n, 4)
+    n_out = len(w.program.result_regs)
+    ref = OracleProgram.from_program(w.program).eval_batch(cols, n)
+    for entry in ([0, 1] if k.has_prefetch_entry else [0]):
+        got = k.run(cols, n, n_out, grid=2, entry=entry)
+        for j, (g, r) in enumerate(zip(got, ref)):
+            assert_close(g, r, 1e-12, 1e-13, what=f"{name} output {j} entry {entry}")
+
+
+@needs_nvrtc
+def test_speculative_body_replays_the_iteration_on_the_cpu():
+    # arguments outside the fast range of the lean kernels: the fast copy of the body flags them, the careful copy
+    # recomputes the whole iteration from the saved parameters (spec.cpp `speculate`)
+    w = workloads.get("clifford")
+    k = _host(w.program)
+    n = 1024
+    cols = w.make_inputs(n, 5)
+    cols[0][::7] = 3.0e7
+    cols[1][3::11] = -8.0e9
+    cols[0][5] = np.inf
+    cols[1][6] = np.nan
+    o = OracleProgram.from_program(w.program)
+    ref = o.eval_batch(cols, n)
+    got = k.run(cols, n, 2, grid=1)
+    for g, r in zip(got, ref):
+        assert_close(g, r, 1e-12, 1e-13, what="clifford with slow-path arguments")
+    ref3 = o.iterate(cols, 3)
+    st = [c.copy() for c in cols]
+    k.run(st, n, 2, iters=3, grid=1, outs=st)
+    for g, r in zip(st, ref3):
+        assert_close(g, r, 1e-11, 1e-13, what="clifford x3 with slow-path start")
+
+
+@needs_nvrtc
+def test_generated_kernel_column_rules_missing_short_unaligned():
+    prog = compile_exprs([parse("a*b + c")], ["a", "b", "c"])
+    k = _host(prog)
+    rng = np.random.default_rng(3)
+    n = 1300
+    a, b, c = rng.normal(size=n), rng.normal(size=700), rng.normal(size=1)
+    o = OracleProgram.from_program(prog)
+    assert bits_equal(k.run([a, b, c], n, 1)[0], o.eval_batch([a, b, c], n)[0])          # short columns repeat their last value
+    assert bits_equal(k.run([a, a, None], n, 1)[0], o.eval_batch([a, a], n)[0])          # missing column reads 0.0
+    buf = np.empty(n + 1)
+    buf[1:] = a
+    out = np.empty(n + 1)
+    got = k.run([buf[1:], b, c], n, 1, outs=[out[1:]])[0]                                  # 8-byte aligned only: scalar accesses
+    assert bits_equal(got, o.eval_batch([a, b, c], n)[0])
+
+
+@needs_nvrtc
+@pytest.mark.parametrize("seed", range(8))
+def test_generated_kernels_of_random_programs_match_the_oracle(seed):
+    rng = np.random.default_rng(7000 + seed)
+    prog = random_program(rng, n_params=int(rng.integers(1, 5)), n_instr=int(rng.integers(1, 40)), n_results=int(rng.integers(1, 4)))
+    n = 300
+    cols = [rng.uniform(-3, 3, n) for _ in range(prog.param_count)]
+    ref = OracleProgram.from_program(prog).eval_batch(cols, n)
+    got = _host(prog).run(cols, n, len(prog.result_regs), grid=2)
+    for g, r in zip(got, ref):
+        assert_close(g, r, rtol=1e-6, atol=1e-10, what=f"seed {seed}")  # the reference's own fuzz comparator
