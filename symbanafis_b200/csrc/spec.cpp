@@ -126,7 +126,8 @@ SpecShape spec_shape_for(const DeviceProgram &dp, bool small_batch) {
     } else {
         s.points_per_thread = dp.n_slots <= 10 ? 4 : dp.n_slots <= 28 ? 2 : 1;
         s.block = 128;
-        s.min_blocks = s.points_per_thread == 4 ? 5 : 4; // <= 102 / 128 registers per thread
+        s.min_blocks = s.points_per_thread == 4 ? 6 : 4; // <= 80 / 128 registers per thread (single expression at 128 Mi
+                                                         // points: 0.440 ms at 88 registers, 0.425 ms at 80)
         // Programs with four or more transcendental leaves bring their own independent dependency chains (speculation,
         // spec_generate: the leaves of one point interleave): two points per thread and more resident warps then beat
         // four points per thread (Clifford map, 4 leaves: P = 4 4.95 ms, P = 2 at <= 80 registers 4.81 ms)
@@ -235,16 +236,27 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
             os << " }\n";
         }
     };
+    // Two tiles ahead while that costs at most 16 registers (a 1 us memory latency at 6.5 TB/s is 44 KB in flight per
+    // SM; one 16-byte load per thread and tile ahead is half of that)
+    const bool prefetch2 = prefetch && n_used * (size_t)P <= 4 && env_int("SAF_SPEC_PREFETCH", 1) >= 2;
     if (prefetch) {
         for (size_t j = 0; j < n_params; ++j) {
             if (dp.param_slot[j] == NO_SLOT) continue;
             os << "  double";
             for (int p = 0; p < P; ++p) os << (p ? ", " : " ") << "n" << dp.param_slot[j] << "_" << p << " = 0.0";
+            if (prefetch2)
+                for (int p = 0; p < P; ++p) os << ", m" << dp.param_slot[j] << "_" << p << " = 0.0";
             os << ";\n";
         }
         os << "  if (blockIdx.x < n_tiles) {\n    const unsigned long long b0_ = blockIdx.x * TILE;\n    const bool f0_ = b0_ + TILE <= d.n_points;\n";
         emit_loads("b0_", "f0_", "n", "    ");
         os << "  }\n";
+        if (prefetch2) {
+            os << "  if (blockIdx.x + gridDim.x < n_tiles) {\n    const unsigned long long b0_ = (blockIdx.x + gridDim.x) * TILE;\n"
+                  "    const bool f0_ = b0_ + TILE <= d.n_points;\n";
+            emit_loads("b0_", "f0_", "m", "    ");
+            os << "  }\n";
+        }
     }
     os << "  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n";
     os << "    const unsigned long long tile_base = tile * TILE;\n";
@@ -261,11 +273,14 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
             if (dp.param_slot[j] == NO_SLOT) continue;
             os << "   ";
             for (int p = 0; p < P; ++p) os << " s" << dp.param_slot[j] << "_" << p << " = n" << dp.param_slot[j] << "_" << p << ";";
+            if (prefetch2)
+                for (int p = 0; p < P; ++p) os << " n" << dp.param_slot[j] << "_" << p << " = m" << dp.param_slot[j] << "_" << p << ";";
             os << "\n";
         }
-        os << "    if (tile + gridDim.x < n_tiles) {\n      const unsigned long long b1_ = (tile + gridDim.x) * TILE;\n"
+        const char *ahead = prefetch2 ? "2ull * gridDim.x" : "gridDim.x";
+        os << "    if (tile + " << ahead << " < n_tiles) {\n      const unsigned long long b1_ = (tile + " << ahead << ") * TILE;\n"
               "      const bool f1_ = b1_ + TILE <= d.n_points;\n";
-        emit_loads("b1_", "f1_", "n", "      ");
+        emit_loads("b1_", "f1_", prefetch2 ? "m" : "n", "      ");
         os << "    }\n";
     } else {
         emit_loads("tile_base", "full", "s", "    ");
