@@ -79,6 +79,7 @@ struct saf_program {
         double generate_ms = 0.0, compile_ms = 0.0;
         std::map<int, SpecModule> modules; // by device; entries never move
     } spec[2];
+    double interpreted_work = 0.0; // SAF_SPECIALIZE=auto: instruction-points run on the interpreter so far
 };
 
 constexpr int LAYOUT_R = 100 + R_POINTS; // layout id of the register machine
@@ -324,14 +325,18 @@ extern "C" int saf_program_export(const saf_program *p, uint64_t *code, size_t c
 // ---- specialised kernels (spec.h) ------------------------------------------------------------------------------------
 // SAF_SPECIALIZE: 0 = never launch a specialised kernel (the interpreter runs even after saf_program_specialize);
 // 1 = specialise every program at its first launch (how the whole GPU test-suite is run against this machine);
+// auto = specialise a program once the work it has done on the interpreter says it is here to stay (below);
 // unset = specialised kernels run for the programs saf_program_specialize was called on.
 static int specialize_mode() {
     static const int mode = []() {
         const char *v = getenv("SAF_SPECIALIZE");
-        return !v || !*v ? -1 : (v[0] == '0' ? 0 : 1);
+        return !v || !*v ? -1 : v[0] == '0' ? 0 : v[0] == 'a' ? 2 : 1;
     }();
     return mode;
 }
+// auto mode: instruction-points (device instructions x points x iterations) a handle must have run on the interpreter
+// before it is specialised at its next launch: 2e10 is 50-100 ms of interpreter time, the order of one compilation
+constexpr double kAutoSpecializeWork = 2e10;
 
 static int specialize_locked(saf_program *p, int variant = 0) { // p->mu held
     saf_program::Spec &sp = p->spec[variant];
@@ -426,8 +431,15 @@ static int spec_for_launch(const saf_program *prog, uint64_t iters, size_t n_poi
     saf_program *mp = const_cast<saf_program *>(prog);
     std::lock_guard<std::mutex> lk(mp->mu);
     if (!mp->spec[0].attempted) {
-        if (mode != 1) return SAF_OK;
-        // automatic mode: programs that cannot be specialised (too long, no NVRTC) keep running on the interpreter
+        if (mode == 2) {
+            if (mp->interpreted_work < kAutoSpecializeWork) { // this launch still goes to the interpreter, and counts
+                mp->interpreted_work += (double)mp->dev.n_dev_instructions * (double)n_points * (double)(iters ? iters : 1);
+                return SAF_OK;
+            }
+        } else if (mode != 1) {
+            return SAF_OK;
+        }
+        // programs that cannot be specialised (too long, no NVRTC) keep running on the interpreter
         if (specialize_locked(mp) != SAF_OK) return SAF_OK;
     }
     if (mp->spec[0].rc != SAF_OK) return SAF_OK;

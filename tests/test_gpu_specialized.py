@@ -400,3 +400,28 @@ def test_gpu_execution_equals_cpu_execution_of_the_same_generated_text():
             cpu = [c.copy() for c in cols]
             k.run(cpu, n, n_out, iters=iters, grid=2, outs=cpu)
         assert_same_bits(gpu, cpu, f"{name}: GPU vs CPU execution of the generated kernel")
+
+
+def test_auto_mode_specialises_a_program_once_it_has_worked_enough():
+    # SAF_SPECIALIZE is read once per process: a child process runs with auto
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np\n"
+        "from symbanafis_b200 import workloads\n"
+        "from symbanafis_b200._lib import DeviceProgramHandle\n"
+        "w = workloads.get('aizawa'); p = w.program\n"
+        "h = DeviceProgramHandle.create(p.flat, p.consts, p.arg_pool, p.param_count, p.workspace_size, p.result_regs)\n"
+        "n = 400_000; st = w.make_inputs(n, 1)\n"
+        "h.iterate_host([c.copy() for c in st], 100)\n"        # 25 instr x 4e5 x 100 = 1e9 < 2e10: interpreter
+        "assert h.specialized_info().compiled == 0\n"
+        "a = [c.copy() for c in st]; h.iterate_host(a, 3000)\n"  # 3e10: still the interpreter for THIS call, counted
+        "b = [c.copy() for c in st]; h.iterate_host(b, 3000)\n"  # specialised at this launch
+        "si = h.specialized_info(); assert si.compiled == 1 and max(si.registers, si.small_registers) > 0, (si.compiled, si.registers)\n"
+        "assert all(np.array_equal(x.view(np.uint64), y.view(np.uint64)) for x, y in zip(a, b))\n"
+        "print('auto ok')\n")
+    env = dict(os.environ, SAF_SPECIALIZE="auto")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "auto ok" in r.stdout, r.stdout + r.stderr
