@@ -228,3 +228,26 @@ def test_generated_kernels_of_random_programs_match_the_oracle(seed):
     got = _host(prog).run(cols, n, len(prog.result_regs), grid=2)
     for g, r in zip(got, ref):
         assert_close(g, r, rtol=1e-6, atol=1e-10, what=f"seed {seed}")  # the reference's own fuzz comparator
+
+
+@needs_nvrtc
+@pytest.mark.parametrize("small", [False, True])
+def test_generated_long_program_kernel_matches_the_oracle_on_the_cpu(small, monkeypatch):
+    # the terrain gradient takes the long-program path of the generator: leaves called (SPEC_OUTLINE), the two SinCos of a
+    # term in one call (sincos_v2), block barriers between stretches of statements (no-ops here: threads run in turn)
+    if small:
+        monkeypatch.setenv("SAF_SPEC_P", "1")
+        monkeypatch.setenv("SAF_SPEC_BLOCK", "128")
+    w = workloads.get("terrain_gradient")
+    h = _handle(w.program)
+    info = h.specialize()
+    src = h.specialized_source()
+    assert "#define SPEC_OUTLINE 1" in src and src.count("sp::sincos_v2(") == 112 and "__syncthreads();" in src
+    assert info.points_per_thread == (1 if small else 2) and info.has_prefetch_entry == 0
+    k = host_kernel(src)
+    n = 1500
+    cols = w.make_inputs(n, 3)
+    ref = OracleProgram.from_program(w.program).eval_batch(cols, n)
+    got = k.run(cols, n, 2, grid=2)
+    for j, (g, r) in enumerate(zip(got, ref)):
+        assert_close(g, r, 1e-12, 1e-13, what=f"terrain gradient output {j}")
