@@ -425,3 +425,30 @@ def test_auto_mode_specialises_a_program_once_it_has_worked_enough():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "auto ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", list(workloads.WORKLOADS))
+@pytest.mark.parametrize("n", [1, 777, 100_003])
+def test_no_write_outside_the_outputs_and_no_write_to_the_columns(name, n):
+    # compute-sanitizer is closed on the GPU pool; the specialised kernels address global memory only through
+    # load_col / store_out (spec_prelude.cuh), whose bounds this checks from outside: 64-element guard bands around every
+    # output stay untouched, the columns come back unchanged, ragged and 8-byte-aligned placements included
+    torch = pytest.importorskip("torch")
+    w = workloads.get(name)
+    cols = w.make_inputs(n, 13)
+    n_out = len(w.program.result_regs)
+    G = 64
+    s = torch.cuda.current_stream().cuda_stream
+    for machine in ("specialized", "interpreter"):
+        h = _handle(w.program, machine == "specialized")
+        for shift in (0, 1):  # shift 1: 8-byte aligned, not 16 -> the scalar access paths
+            d_cols = [torch.from_numpy(c.copy()).cuda() for c in cols]
+            arena = [torch.full((n + 2 * G + 1,), -12345.678, dtype=torch.float64, device="cuda") for _ in range(n_out)]
+            outs = [a[G + shift:G + shift + n] for a in arena]
+            h.eval_device([t.data_ptr() for t in d_cols], [n] * len(d_cols), [o.data_ptr() for o in outs], n, stream=s)
+            torch.cuda.synchronize()
+            for a in arena:
+                assert bool((a[:G + shift] == -12345.678).all()) and bool((a[G + shift + n:] == -12345.678).all()), \
+                    f"{name} {machine}: write outside the output column (n={n}, shift={shift})"
+            for t, c in zip(d_cols, cols):
+                assert np.array_equal(t.cpu().numpy().view(np.uint64), c.view(np.uint64)), f"{name} {machine}: a column was modified"
