@@ -10,6 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <functional>
+#include <map>
 #include <set>
 #include <sstream>
 
@@ -86,6 +89,8 @@ int env_int(const char *name, int dflt) {
 } // namespace
 
 namespace {
+#include "reroll.inc"
+
 size_t n_trig_exp(const std::vector<Ins> &ins) {
     size_t n = 0;
     for (const Ins &i : ins)
@@ -169,9 +174,10 @@ bool spec_batch_is_small(const SpecShape &large, unsigned long long n_points, in
     return n_points < 12ull * 32ull * (unsigned long long)large.points_per_thread * (unsigned long long)(sms > 0 ? sms : 1);
 }
 
-int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &text, bool &can_iterate, bool &has_prefetch_entry,
+int spec_generate(const DeviceProgram &dp, SpecShape &shape, std::string &text, bool &can_iterate, bool &has_prefetch_entry,
                   std::string &err) {
     has_prefetch_entry = false;
+    shape.rolled = false;
     std::vector<Ins> ins;
     if (!decode(dp, ins, err)) return SAF_ERR_INVALID_PROGRAM;
     const size_t max_instr = (size_t)env_int("SAF_SPEC_MAX_INSTRUCTIONS", (int)SPEC_MAX_INSTRUCTIONS); // tuning / test knob
@@ -182,6 +188,37 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
     }
     const size_t n_params = dp.param_count, n_results = dp.result_field.size();
     can_iterate = n_results >= n_params && n_params > 0;
+
+    // Long sums of similar terms as a loop (reroll.inc): the kernel is then a short program again -- leaves inline, no
+    // barriers, 128-thread blocks, a quarter of the NVRTC time.  OPT-IN (SAF_SPEC_REROLL=1): same bits (CPU-tested), but
+    // measured SLOWER than the straight-line kernel on the terrain gradient (0.53 against 0.67 of the FP64 roofline,
+    // profiles/r02_j_rolled_terrain_gradient.md): one term per loop trip leaves a warp nothing to overlap its own
+    // dependency chain with (stall_wait 3.5 per issue), and selecting the running sum a contribution goes to at run time
+    // costs a register move per sum and case.  `shape.reroll_note` says what was rolled, or why not.
+    Rolled rolled;
+    std::string rolled_tables, rolled_body;
+    if (ins.size() > 512 && env_int("SAF_SPEC_REROLL", 0) != 0) {
+        std::string why;
+        if (reroll_analyse(dp, ins, rolled, why)) {
+            shape.rolled = true;
+            shape.points_per_thread = env_int("SAF_SPEC_P", 2) == 4 ? 4 : env_int("SAF_SPEC_P", 2) == 1 ? 1 : 2;
+            shape.block = 128;
+            const int b = env_int("SAF_SPEC_BLOCK", 0);
+            if (b >= 32 && b <= 1024 && b % 32 == 0) shape.block = b;
+            shape.min_blocks = env_int("SAF_SPEC_MINB", 4);
+            shape.sync_every = 0;
+            shape.outline = false;
+            std::ostringstream t, b_;
+            reroll_emit(dp, rolled, shape.points_per_thread, t, b_);
+            rolled_tables = t.str();
+            rolled_body = b_.str();
+            shape.reroll_note = std::to_string(rolled.groups.size()) + " terms of " + std::to_string(rolled.classes.size()) +
+                                " shapes into " + std::to_string(rolled.chains.size()) + " sums";
+        } else {
+            shape.reroll_note = "not rolled: " + why;
+        }
+        if (std::getenv("SAF_SPEC_DEBUG")) std::fprintf(stderr, "saf spec: %s\n", shape.reroll_note.c_str());
+    }
 
     std::set<uint32_t> slots;
     auto note = [&](uint32_t f) {
@@ -218,6 +255,7 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
     // k17 = saf_kt[17]` -- two UMOVs per constant saved, but the compiler hoists the loads: 84 -> 128 registers, terrain
     // gradient 16.6 -> 18.8 ms.  Dropped.)
     const bool pair_leaves = env_int("SAF_SPEC_PAIR", 1) != 0;
+    os << rolled_tables;
     int emit_rc = SAF_OK;
     auto emit_kernel = [&](const char *kernel_name, bool prefetch) {
     os << "extern \"C\" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MINB) " << kernel_name
@@ -445,8 +483,10 @@ int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &
     // it saw; it is ONE basic block between divisions.  If an argument was outside the fast range -- per thread, rare --
     // the parameters are restored and the second, careful copy (the leaves with their branches) recomputes the
     // iteration.  Where the fast path applies the careful leaf returns the fast path's value, so the bits are the same.
-    const bool speculate = !outline && shape.speculate && n_trig_exp(ins) > 0;
-    if (speculate) {
+    const bool speculate = !outline && shape.speculate && n_trig_exp(ins) > 0 && !shape.rolled;
+    if (shape.rolled) {
+        os << rolled_body;
+    } else if (speculate) {
         for (size_t j = 0; j < n_params; ++j)
             if (dp.param_slot[j] != NO_SLOT)
                 for (int p = 0; p < P; ++p) os << "      const double save" << j << "_" << p << " = s" << dp.param_slot[j] << "_" << p << ";\n";

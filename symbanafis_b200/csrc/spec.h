@@ -26,7 +26,9 @@ struct SpecShape {
     int sync_every = 0;        // > 0: a block barrier every so many statements (long programs, spec.cpp)
     bool outline = false;      // transcendental leaves are called, not inlined
     bool prefetch = true;      // short programs: the next tile's columns are loaded before the current tile is evaluated
-    bool speculate = true;     // inlined leaves: fast paths first, careful replay of the iteration when one did not apply
+    bool speculate = true;
+    bool rolled = false;       // the body is a loop over similar terms (reroll.inc); set by spec_generate
+    std::string reroll_note;   // what was rolled, or why not     // inlined leaves: fast paths first, careful replay of the iteration when one did not apply
 };
 
 // A loaded specialised kernel on one device (launch.cu).
@@ -53,7 +55,7 @@ bool spec_batch_is_small(const SpecShape &large, unsigned long long n_points, in
 // of results into parameters (needs as many results as parameters).  Returns 0 or SAF_ERR_UNSUPPORTED.
 // has_prefetch_entry: the text holds a second kernel, `saf_spec_pf`, for single passes (iters == 1): it loads the columns
 // of a block's next tile before it evaluates the current one.
-int spec_generate(const DeviceProgram &dp, const SpecShape &shape, std::string &text, bool &can_iterate, bool &has_prefetch_entry,
+int spec_generate(const DeviceProgram &dp, SpecShape &shape, std::string &text, bool &can_iterate, bool &has_prefetch_entry,
                   std::string &err);
 
 // NVRTC (jit.cpp).  Compiles `text` (which includes spec_prelude.cuh and through it the device math headers; all of

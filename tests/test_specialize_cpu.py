@@ -251,3 +251,27 @@ def test_generated_long_program_kernel_matches_the_oracle_on_the_cpu(small, monk
     got = k.run(cols, n, 2, grid=2)
     for j, (g, r) in enumerate(zip(got, ref)):
         assert_close(g, r, 1e-12, 1e-13, what=f"terrain gradient output {j}")
+
+
+@needs_nvrtc
+def test_rolled_kernel_of_a_long_sum_returns_the_bits_of_the_straight_line_kernel(monkeypatch):
+    # csrc/reroll.inc (opt-in, SAF_SPEC_REROLL=1): the 110-term gradient as a loop over its terms, constants in a table
+    w = workloads.get("terrain_gradient")
+    straight = _handle(w.program)
+    straight.specialize()
+    monkeypatch.setenv("SAF_SPEC_REROLL", "1")
+    rolled = _handle(w.program)
+    info = rolled.specialize()
+    src = rolled.specialized_source()
+    assert "saf_rr_kt" in src and "for (int g_ = 0; g_ < 222; ++g_)" in src and "#define SPEC_OUTLINE" not in src
+    assert info.block_threads == 128 and len(src) < len(straight.specialized_source()) // 2
+    n = 1500
+    cols = w.make_inputs(n, 3)
+    a = host_kernel(straight.specialized_source()).run(cols, n, 2, grid=2)
+    b = host_kernel(src).run(cols, n, 2, grid=2)
+    for x, y in zip(a, b):
+        assert bits_equal(x, y)
+    # a program without long running sums is left alone
+    c = _handle(workloads.get("double_pendulum").program)
+    c.specialize()
+    assert "saf_rr_kt" not in c.specialized_source()
