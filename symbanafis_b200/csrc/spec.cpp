@@ -348,12 +348,14 @@ int spec_generate(const DeviceProgram &dp, SpecShape &shape, std::string &text, 
     // that each warp walks once per tile; left alone the warps drift apart, every warp streams its own copy from L2 and
     // the kernel waits for instructions (ncu: stall_no_instruction 4.3 per issue, profiles/r02_g_*).
     const int sync_every = shape.sync_every;
+    const bool speculating = shape.speculate && n_trig_exp(ins) > 0 && !shape.rolled &&
+                             (!shape.outline || env_int("SAF_SPEC_SPECULATE_LONG", 0) != 0);
     // fast: the speculative copy of the body -- transcendental leaves take their fast path unconditionally and only
     // record whether an argument was outside it (slow_t_ / slow_e_); see `speculate` below
     auto emit_body = [&](bool fast) {
     for (size_t n = 0; n < ins.size(); ++n) {
         const Ins &i = ins[n];
-        if (sync_every > 0 && n > 0 && n % (size_t)sync_every == 0) os << "      __syncthreads();\n";
+        if (sync_every > 0 && n > 0 && n % (size_t)sync_every == 0 && (fast || !speculating)) os << "      __syncthreads();\n";
         auto scalar = [&](const std::string &tmpl) {
             for (int p = 0; p < P; ++p) os << "      acc_" << p << " = " << subst(tmpl, i, p) << ";\n";
         };
@@ -483,7 +485,12 @@ int spec_generate(const DeviceProgram &dp, SpecShape &shape, std::string &text, 
     // it saw; it is ONE basic block between divisions.  If an argument was outside the fast range -- per thread, rare --
     // the parameters are restored and the second, careful copy (the leaves with their branches) recomputes the
     // iteration.  Where the fast path applies the careful leaf returns the fast path's value, so the bits are the same.
-    const bool speculate = !outline && shape.speculate && n_trig_exp(ins) > 0 && !shape.rolled;
+    // Long programs can speculate too (SAF_SPEC_SPECULATE_LONG=1, OFF): the fast copy has its leaves' fast paths INLINE --
+    // no calls, no argument moves, no per-leaf branches -- and keeps the barriers; the careful copy keeps the called
+    // leaves and has NO barriers (it runs under a per-thread condition).  Same bits (CPU-tested), but 17 s of NVRTC and,
+    // at the 128 registers a 512-thread block leaves, 45.7 ms per 20 M points of the terrain gradient against 15.9.
+    const bool speculate = shape.speculate && n_trig_exp(ins) > 0 && !shape.rolled &&
+                           (!outline || env_int("SAF_SPEC_SPECULATE_LONG", 0) != 0);
     if (shape.rolled) {
         os << rolled_body;
     } else if (speculate) {
