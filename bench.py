@@ -440,6 +440,11 @@ class Bench:
         n_state, n_out = w.program.param_count, len(w.program.result_regs)
         cols_np = w.make_inputs(n, seed)
         step_ms, t_wall, launches, sustained, warm_ms = self.device_timed(h, w, cols_np, n, iters, steps, warmup)
+        if step_ms < 0.1 and steps < 50:
+            # a launch of a few microseconds: one hiccup of the box (seen once: 0.18 ms among 0.010 ms steps) would
+            # decide the mean of a handful of steps -- time 50 of them instead (still the mean, still every step flushed)
+            steps = 50
+            step_ms, t_wall, launches, sustained, warm_ms = self.device_timed(h, w, cols_np, n, iters, steps, warmup)
         e2e_steps = max(2, min(steps, 5))
         e2e_ms = self.e2e_timed(h, w, cols_np, n, iters, e2e_steps, pinned=True)
         e2e_pg_ms = self.e2e_timed(h, w, cols_np, n, iters, e2e_steps, pinned=False)
@@ -651,7 +656,7 @@ def run_ours(args):
     clocks = sampler.stop() if B.rank == 0 else None
     if B.rank == 0:
         line = {
-            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": B.world, "steps": args.steps,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": B.world, "steps": main["steps"],
             "warmup": max(3, args.warmup), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": main["config"],
