@@ -452,3 +452,18 @@ def test_no_write_outside_the_outputs_and_no_write_to_the_columns(name, n):
                     f"{name} {machine}: write outside the output column (n={n}, shift={shift})"
             for t, c in zip(d_cols, cols):
                 assert np.array_equal(t.cpu().numpy().view(np.uint64), c.view(np.uint64)), f"{name} {machine}: a column was modified"
+
+
+def test_rolled_long_sum_same_bits_on_the_gpu(monkeypatch):
+    # csrc/reroll.inc (opt-in): the 110-term gradient as a loop over its terms -- slower than the straight-line kernel
+    #  but the same arithmetic: the same bits
+    w = workloads.get("terrain_gradient")
+    n = 150_001
+    cols = w.make_inputs(n, 21)
+    ref = _eval(_handle(w.program, False), w.program, cols, n)
+    monkeypatch.setenv("SAF_SPEC_REROLL", "1")
+    h = _handle(w.program, True)
+    assert "saf_rr_kt" in h.specialized_source()
+    got = _eval(h, w.program, cols, n)
+    assert max(h.specialized_info().registers, h.specialized_info().small_registers) > 0
+    assert_same_bits(ref, got, "rolled terrain gradient")
