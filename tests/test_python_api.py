@@ -166,3 +166,16 @@ def test_compiled_evaluator_batch_and_scalar_conventions():
     assert len(big) == 10000 and abs(big[0] - 1.0) < 1e-10
     assert CompiledEvaluator(parse("42"), []).evaluate([]) == 42.0
     assert abs(CompiledEvaluator(parse("sin(pi/2)"), []).evaluate([]) - 1.0) < 1e-10
+
+
+def test_package_exports_the_reference_names_lazily():
+    import importlib
+    import symbanafis_b200
+    importlib.reload(symbanafis_b200)
+    assert {"CompiledEvaluator", "eval_f64", "evaluate_parallel"} <= set(dir(symbanafis_b200))
+    from symbanafis_b200 import CompiledEvaluator as A
+    from symbanafis_b200.evaluator import CompiledEvaluator as B
+    assert A is B
+    import pytest as _pytest
+    with _pytest.raises(AttributeError):
+        symbanafis_b200.no_such_name
