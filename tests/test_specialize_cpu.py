@@ -275,3 +275,39 @@ def test_rolled_kernel_of_a_long_sum_returns_the_bits_of_the_straight_line_kerne
     c = _handle(workloads.get("double_pendulum").program)
     c.specialize()
     assert "saf_rr_kt" not in c.specialized_source()
+
+
+def _random_expression(rng, depth=0):
+    leaves = ["x", "y", "z", "0.5", "1.25", "-2.0", "3.0"]
+    if depth >= 4 or rng.random() < 0.2:
+        return leaves[int(rng.integers(len(leaves)))]
+    kind = rng.random()
+    a = _random_expression(rng, depth + 1)
+    if kind < 0.45:
+        b = _random_expression(rng, depth + 1)
+        return f"({a} {'+-*/'[int(rng.integers(4))]} {b})"
+    if kind < 0.85:
+        fn = ["sin", "cos", "exp", "tanh", "sinh", "atan", "erf", "sqrt(abs", "log1p(abs", "cosh"][int(rng.integers(10))]
+        return f"{fn}({a}))" if "(" in fn else f"{fn}({a})"
+    return f"({a})^{int(rng.integers(2, 5))}"
+
+
+@needs_nvrtc
+@pytest.mark.parametrize("seed", range(12))
+def test_generated_kernels_of_random_expressions_match_the_oracle(seed):
+    # expression strings -> C++ compiler (csrc/compile.cpp) -> lowering -> generated kernel, executed on the CPU, against
+    # the oracle running the same reference bytecode
+    rng = np.random.default_rng(9000 + seed)
+    exprs = [_random_expression(rng) for _ in range(int(rng.integers(1, 4)))]
+    h = DeviceProgramHandle.compile(exprs, ["x", "y", "z"])
+    flat, consts, pool, param_count, workspace, regs = h.reference_payload(0)
+    from symbanafis_b200.isa import Program
+    prog = Program(flat=list(flat), consts=list(consts), arg_pool=list(pool), param_count=param_count, workspace_size=workspace,
+                   result_regs=list(regs))
+    h.specialize()
+    n = 257
+    cols = [rng.uniform(-1.5, 1.5, n) for _ in range(3)]
+    ref = OracleProgram.from_program(prog).eval_batch(cols, n)
+    got = host_kernel(h.specialized_source()).run(cols, n, len(exprs), grid=2)
+    for e, g, r in zip(exprs, got, ref):
+        assert_close(g, r, rtol=1e-9, atol=1e-12, what=e)
