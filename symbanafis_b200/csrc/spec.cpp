@@ -191,10 +191,9 @@ int spec_generate(const DeviceProgram &dp, SpecShape &shape, std::string &text, 
 
     // Long sums of similar terms as a loop (reroll.inc): the kernel is then a short program again -- leaves inline, no
     // barriers, 128-thread blocks, a quarter of the NVRTC time.  OPT-IN (SAF_SPEC_REROLL=1): same bits (CPU-tested), but
-    // measured SLOWER than the straight-line kernel on the terrain gradient (0.53 against 0.67 of the FP64 roofline,
+    // measured SLOWER than the straight-line kernel on the terrain gradient (0.565 against 0.668 of the FP64 roofline,
     // profiles/r02_j_rolled_terrain_gradient.md): one term per loop trip leaves a warp nothing to overlap its own
-    // dependency chain with (stall_wait 3.5 per issue), and selecting the running sum a contribution goes to at run time
-    // costs a register move per sum and case.  `shape.reroll_note` says what was rolled, or why not.
+    // dependency chain with (stall_wait 3.5 per issue).  `shape.reroll_note` says what was rolled, or why not.
     Rolled rolled;
     std::string rolled_tables, rolled_body;
     if (ins.size() > 512 && env_int("SAF_SPEC_REROLL", 0) != 0) {
@@ -205,11 +204,11 @@ int spec_generate(const DeviceProgram &dp, SpecShape &shape, std::string &text, 
             shape.block = 128;
             const int b = env_int("SAF_SPEC_BLOCK", 0);
             if (b >= 32 && b <= 1024 && b % 32 == 0) shape.block = b;
-            shape.min_blocks = env_int("SAF_SPEC_MINB", 4);
+            shape.min_blocks = env_int("SAF_SPEC_MINB", 5);
             shape.sync_every = 0;
             shape.outline = false;
             std::ostringstream t, b_;
-            reroll_emit(dp, rolled, shape.points_per_thread, t, b_);
+            reroll_emit_iteration(dp, rolled, shape.points_per_thread, shape.speculate, t, b_);
             rolled_tables = t.str();
             rolled_body = b_.str();
             shape.reroll_note = std::to_string(rolled.groups.size()) + " terms of " + std::to_string(rolled.classes.size()) +
