@@ -148,7 +148,8 @@ SAF_API int saf_program_get_info(const saf_program *prog, saf_program_info *info
  * Programs above 20000 device instructions are not specialised (SAF_ERR_UNSUPPORTED).
  * Environment: SAF_SPECIALIZE=0 keeps every launch on the interpreter, =1 specialises every program at first launch,
  * =auto specialises a program at the first launch after it has run 2e10 instruction-points on the interpreter (50-100 ms
- * of work: the order of one compilation) -- for callers that cannot say in advance which programs will be reused. */
+ * of work: the order of one compilation) -- for callers that cannot say in advance which programs will be reused.
+ * SAF_SPEC_CACHE_DIR=<directory> keeps compiled kernels on disk (keyed by content): the next process skips NVRTC. */
 SAF_API int saf_program_specialize(saf_program *prog);
 
 typedef struct saf_specialized_info {

@@ -11,6 +11,10 @@
 #include "spec.h"
 
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
 
 #include <cstdlib>
 #include <cstring>
@@ -110,6 +114,56 @@ bool jit_available(std::string &why_not) {
     return ok;
 }
 
+namespace {
+// Optional disk cache of compiled kernels (SAF_SPEC_CACHE_DIR=<directory>, off when unset): a process that creates the
+// same programs again -- a restarted service, a test-suite -- skips NVRTC.  The key covers everything that decides
+// the cubin: the generated text, the embedded headers it includes, the NVRTC version, the target.
+uint64_t fnv1a(const char *p, size_t n, uint64_t h) {
+    for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)p[i]) * 0x100000001b3ull;
+    return h;
+}
+std::string cache_path(const std::string &text, int major, int minor) {
+    const char *dir = std::getenv("SAF_SPEC_CACHE_DIR");
+    if (dir == nullptr || *dir == 0) return std::string();
+    uint64_t h1 = 0xcbf29ce484222325ull, h2 = 0x84222325cbf29ce4ull;
+    const char *parts[] = {text.c_str(), saf_text_spec_prelude, saf_text_devmath, saf_text_leanmath, saf_text_saf_isa};
+    for (const char *p : parts) {
+        const size_t n = std::strlen(p);
+        h1 = fnv1a(p, n, h1);
+        h2 = fnv1a(p, n, h2 ^ n);
+    }
+    char name[160];
+    std::snprintf(name, sizeof name, "/saf_spec_sm100a_nvrtc%d.%d_%016llx%016llx.cubin", major, minor, (unsigned long long)h1,
+                  (unsigned long long)h2);
+    return std::string(dir) + name;
+}
+bool cache_read(const std::string &path, std::vector<char> &cubin) {
+    if (path.empty()) return false;
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    bool ok = n > 64;
+    if (ok) {
+        cubin.resize((size_t)n);
+        ok = std::fread(cubin.data(), 1, (size_t)n, f) == (size_t)n && std::memcmp(cubin.data(), "\177ELF", 4) == 0;
+    }
+    std::fclose(f);
+    if (!ok) cubin.clear();
+    return ok;
+}
+void cache_write(const std::string &path, const std::vector<char> &cubin) {
+    if (path.empty()) return;
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    FILE *f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return; // an unwritable cache directory is not an error
+    const bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    std::fclose(f);
+    if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+}
+} // namespace
+
 int jit_compile(const std::string &text, std::vector<char> &cubin, std::string &err) {
     {
         std::lock_guard<std::mutex> lk(g_rtc_mu);
@@ -119,6 +173,10 @@ int jit_compile(const std::string &text, std::vector<char> &cubin, std::string &
         }
     }
     const Nvrtc &r = g_rtc; // read-only from here on; NVRTC itself may be called from several threads
+    int v_major = 0, v_minor = 0;
+    r.Version(&v_major, &v_minor);
+    const std::string cached = cache_path(text, v_major, v_minor);
+    if (cache_read(cached, cubin)) return SAF_OK;
     const char *headers[] = {saf_text_spec_prelude, saf_text_devmath, saf_text_leanmath, saf_text_saf_isa, kCstdint, kCstdint, kCfloat};
     const char *names[] = {"spec_prelude.cuh", "devmath.cuh", "leanmath.cuh", "saf_isa.h", "cstdint", "stdint.h", "cfloat"};
     nvrtcProgram prog = nullptr;
@@ -152,6 +210,7 @@ int jit_compile(const std::string &text, std::vector<char> &cubin, std::string &
         err = std::string("nvrtcGetCUBIN: ") + (rc ? r.GetErrorString(rc) : "empty image");
         return SAF_ERR_CUDA;
     }
+    cache_write(cached, cubin);
     return SAF_OK;
 }
 

@@ -311,3 +311,29 @@ def test_generated_kernels_of_random_expressions_match_the_oracle(seed):
     got = host_kernel(h.specialized_source()).run(cols, n, len(exprs), grid=2)
     for e, g, r in zip(exprs, got, ref):
         assert_close(g, r, rtol=1e-9, atol=1e-12, what=e)
+
+
+@needs_nvrtc
+def test_disk_cache_of_compiled_kernels_is_opt_in_and_keyed_by_content(tmp_path, monkeypatch):
+    import os
+    w = workloads.get("aizawa")
+    a = _handle(w.program)
+    a.specialize()
+    assert not list(tmp_path.iterdir())                      # no cache directory configured: nothing is written
+    monkeypatch.setenv("SAF_SPEC_CACHE_DIR", str(tmp_path))
+    b = _handle(w.program)
+    ib = b.specialize()
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 1 and files[0].startswith("saf_spec_sm100a_nvrtc") and files[0].endswith(".cubin")
+    c = _handle(w.program)
+    ic = c.specialize()                                      # served from the file: no NVRTC
+    assert ic.cubin_bytes == ib.cubin_bytes and ic.compile_ms < ib.compile_ms / 3
+    d = _handle(workloads.get("clifford").program)           # another program: another entry
+    d.specialize()
+    assert len(os.listdir(tmp_path)) == 2
+    # a damaged entry is ignored and replaced
+    with open(tmp_path / files[0], "wb") as f:
+        f.write(b"garbage")
+    e = _handle(w.program)
+    assert e.specialize().cubin_bytes == ib.cubin_bytes
+    assert os.path.getsize(tmp_path / files[0]) == ib.cubin_bytes
