@@ -337,3 +337,32 @@ def test_disk_cache_of_compiled_kernels_is_opt_in_and_keyed_by_content(tmp_path,
     e = _handle(w.program)
     assert e.specialize().cubin_bytes == ib.cubin_bytes
     assert os.path.getsize(tmp_path / files[0]) == ib.cubin_bytes
+
+
+@needs_nvrtc
+def test_rolling_other_long_sums_or_declining_them(monkeypatch):
+    from symbanafis_b200.expr import diff
+    rng = np.random.default_rng(5)
+    g = " + ".join(f"{rng.uniform(0.2, 1):.6f}*exp(-((x - {rng.uniform(-2, 2):.5f})^2 + (y - {rng.uniform(-2, 2):.5f})^2)/"
+                   f"{rng.uniform(0.3, 2):.5f})" for _ in range(120))
+    e = parse(g)
+    mixture = compile_exprs([diff(e, "x"), diff(e, "y"), e], ["x", "y"])   # a Gaussian mixture, its gradient: three sums
+    poly = " + ".join(f"{rng.uniform(-1, 1):.6f}*x^{k % 7 + 1}*y^{k % 5 + 1}/(1 + {rng.uniform(0.1, 2):.5f}*x^2)" for k in range(150))
+    rational = compile_exprs([parse(poly)], ["x", "y"])                    # 35 different term shapes: not worth a loop
+    n = 700
+    cols = [rng.uniform(-2, 2, n), rng.uniform(-2, 2, n)]
+    for prog, expect_rolled in ((mixture, True), (rational, False)):
+        monkeypatch.delenv("SAF_SPEC_REROLL", raising=False)
+        straight = _handle(prog)
+        straight.specialize()
+        monkeypatch.setenv("SAF_SPEC_REROLL", "1")
+        rolled = _handle(prog)
+        rolled.specialize()
+        assert ("saf_rr_kt" in rolled.specialized_source()) == expect_rolled
+        a = host_kernel(straight.specialized_source()).run(cols, n, len(prog.result_regs), grid=2)
+        b = host_kernel(rolled.specialized_source()).run(cols, n, len(prog.result_regs), grid=2)
+        for x, y in zip(a, b):
+            assert bits_equal(x, y)
+        ref = OracleProgram.from_program(prog).eval_batch(cols, n)
+        for x, r in zip(b, ref):
+            assert_close(x, r, 1e-11, 1e-13, what="rolled vs oracle")
