@@ -141,3 +141,27 @@ def test_program_cache_is_thread_safe():
         t.join()
     assert not errs and len(set(got)) == 1 and got[0]
     L.saf_program_cache_clear()
+
+
+def test_header_is_valid_c99_and_links_against_the_library(tmp_path):
+    # the drop-in boundary is a C ABI: a C (not C++) translation unit that uses the specialisation entry points compiles
+    # with -pedantic, links against the library and runs the host-only calls without a device
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "saf_b200.h"\n'
+        "int main(void) {\n"
+        '  const char *exprs[] = {"x*x + sin(x)*exp(-x)"}; const char *params[] = {"x"};\n'
+        "  saf_program *p = 0; saf_specialized_info si;\n"
+        "  if (saf_compile_exprs(exprs, 1, params, 1, &p) != SAF_OK) return 1;\n"
+        "  if (saf_program_specialized_info(p, &si) != SAF_OK || si.compiled != 0) return 2;\n"
+        "  if (saf_specialize_available() && (saf_program_specialize(p) != SAF_OK || saf_program_specialized_info(p, &si) != SAF_OK ||\n"
+        "      si.compiled != 1 || saf_program_specialized_source(p, 0, 0, 0) == 0)) return 3;\n"
+        '  printf("%s\\n", saf_version());\n'
+        "  saf_program_destroy(p);\n  return 0;\n}\n")
+    exe = tmp_path / "use"
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), _lib.LIB_PATH, f"-Wl,-rpath,{lib_dir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "symbanafis-b200" in r.stdout, (r.returncode, r.stdout, r.stderr)
