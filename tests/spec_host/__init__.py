@@ -20,7 +20,12 @@ _cache = {}
 
 class HostKernel:
     def __init__(self, source: str):
-        key = hashlib.sha1(source.encode()).hexdigest()[:16]
+        h = hashlib.sha1(source.encode())
+        for dep in (os.path.join(CSRC, "spec_prelude.cuh"), os.path.join(CSRC, "devmath.cuh"), os.path.join(CSRC, "leanmath.cuh"),
+                    os.path.join(CSRC, "saf_isa.h"), os.path.join(HERE, "shim.h"), os.path.join(HERE, "driver.cpp")):
+            with open(dep, "rb") as f:
+                h.update(f.read())  # a change of any header rebuilds the cached library
+        key = h.hexdigest()[:16]
         d = os.path.join(tempfile.gettempdir(), "saf_spec_host")
         os.makedirs(d, exist_ok=True)
         cu, so = os.path.join(d, key + ".cu"), os.path.join(d, key + ".so")
